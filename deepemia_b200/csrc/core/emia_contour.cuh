@@ -1,0 +1,171 @@
+// emia_contour.cuh — external-contour extraction on a bit-packed crop (host/device).
+//
+// Replaces (reference call sites): cv2.findContours(mask, RETR_EXTERNAL, CHAIN_APPROX_SIMPLE) at
+// src/functions/inference.py:1164-1167 (measurement loop) and :2605 (compactness pre-filter of
+// deduplicate_masks_smart); cv2.contourArea at :1175 / src/utils/measurements.py:134 and cv2.arcLength at
+// inference.py:2607 / measurements.py:135,163.
+//
+// Algorithm = Suzuki-Abe border following as OpenCV implements it (raster scan; an outer border starts at an
+// unmarked foreground pixel whose left neighbour is background; in RETR_EXTERNAL mode the start is accepted
+// only if the nearest already-marked pixel to its left on the same row is a "right-exit" pixel (negative
+// label) or there is none; the border is followed with the 8-neighbour clockwise/counter-clockwise search and
+// every visited pixel is labelled +2, or -126 when its east neighbour was examined and found empty).
+// CHAIN_APPROX_SIMPLE keeps a point whenever the chain direction changes.
+// State per pixel is held in two extra bit planes (marked / negative) instead of OpenCV's int8 image, so
+// the scan for start pixels is word-parallel.
+#pragma once
+#include "emia_common.cuh"
+
+#define EMIA_PACK_PT(x, y) ((uint32_t)(x) | ((uint32_t)(y) << 16))
+#define EMIA_PT_X(p) ((int)((p) & 0xFFFFu))
+#define EMIA_PT_Y(p) ((int)((p) >> 16))
+
+struct EmiaContourOut {
+    uint32_t* pts;     // packed vertices (frame coordinates), contours stored back-to-back in DISCOVERY order
+    int cap_pts;
+    int* cstart;       // cstart[k]..cstart[k+1] = vertex range of k-th discovered contour; size cap_contours+1
+    int cap_contours;
+    int n_contours;
+    int n_pts;
+    int overflow;      // set when a capacity was exceeded (results invalid)
+};
+
+EMIA_HD void emia_contour_emit(EmiaContourOut& o, int fx, int fy) {
+    if (o.n_pts < o.cap_pts) o.pts[o.n_pts] = EMIA_PACK_PT(fx, fy);
+    else o.overflow = 1;
+    o.n_pts++;
+}
+
+struct EmiaMarks {
+    uint32_t* mk;   // marked plane   (h * wwords words)
+    uint32_t* ng;   // negative plane (h * wwords words)
+    int wwords;
+};
+EMIA_HD int emia_marked(const EmiaMarks& m, int lx, int ly) {
+    return (m.mk[ly * m.wwords + (lx >> 5)] >> (lx & 31)) & 1u;
+}
+EMIA_HD void emia_mark(const EmiaMarks& m, int lx, int ly, int negative) {
+    const int w = ly * m.wwords + (lx >> 5);
+    const uint32_t b = 1u << (lx & 31);
+    m.mk[w] |= b;
+    if (negative) m.ng[w] |= b;
+}
+
+// Follow one outer border starting at local pixel (x0,y0).
+EMIA_HD_NOINLINE void emia_trace_outer(const EmiaBitView& v, const EmiaMarks& m, int x0, int y0, EmiaContourOut& o) {
+    const int DX[8] = {1, 1, 0, -1, -1, -1, 0, 1};
+    const int DY[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+    int s = 4;
+    const int s_first_end = 4;
+    int x1 = 0, y1 = 0;
+    do {
+        s = (s - 1) & 7;
+        x1 = x0 + DX[s];
+        y1 = y0 + DY[s];
+    } while (!emia_view_px(v, x1, y1) && s != s_first_end);
+
+    if (s == s_first_end) {  // isolated pixel
+        emia_mark(m, x0, y0, 1);
+        emia_contour_emit(o, v.x_origin + x0, v.y_origin + y0);
+        return;
+    }
+    int x3 = x0, y3 = y0, x4 = x0, y4 = y0;
+    int prev_s = s ^ 4;
+    for (;;) {
+        const int s_end = s;
+        while (s < 15) {
+            ++s;
+            x4 = x3 + DX[s & 7];
+            y4 = y3 + DY[s & 7];
+            if (emia_view_px(v, x4, y4)) break;
+        }
+        s &= 7;
+        if ((unsigned)(s - 1) < (unsigned)s_end) emia_mark(m, x3, y3, 1);
+        else if (!emia_marked(m, x3, y3)) emia_mark(m, x3, y3, 0);
+        if (s != prev_s) {
+            emia_contour_emit(o, v.x_origin + x3, v.y_origin + y3);
+            prev_s = s;
+        }
+        if (x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) break;
+        x3 = x4;
+        y3 = y4;
+        s = (s + 4) & 7;
+    }
+}
+
+// All external contours of the crop, in discovery (raster) order.  OpenCV returns them in REVERSE discovery
+// order; consumers iterate k = n_contours-1 .. 0.  mk/ng must hold h*wwords words each (zeroed here).
+EMIA_HD_NOINLINE void emia_find_external_contours(const EmiaBitView& v, uint32_t* mk, uint32_t* ng, EmiaContourOut& o) {
+    EmiaMarks m;
+    m.mk = mk; m.ng = ng; m.wwords = v.wwords;
+    const int nw = v.h * v.wwords;
+    for (int i = 0; i < nw; ++i) { mk[i] = 0u; ng[i] = 0u; }
+    o.n_contours = 0; o.n_pts = 0; o.overflow = 0;
+    o.cstart[0] = 0;
+    for (int y = 0; y < v.h; ++y) {
+        const uint32_t* row = v.bits + (size_t)y * v.pitch_words;
+        for (int c = 0; c < v.wwords; ++c) {
+            uint32_t done_mask = 0u;  // bits of this word already examined
+            for (;;) {
+                // marks may have changed since the last candidate: recompute from the planes
+                const uint32_t F = row[c];
+                if (F == 0u) break;
+                const uint32_t left = (F << 1) | (c > 0 ? (row[c - 1] >> 31) : 0u);
+                uint32_t cand = F & ~left & ~mk[y * v.wwords + c] & ~done_mask;
+                if (cand == 0u) break;
+                const int b = emia_ctz(cand);
+                done_mask |= (b == 31) ? 0xFFFFFFFFu : ((2u << b) - 1u);
+                const int x = c * 32 + b;
+                // nearest marked pixel strictly left of x on this row
+                int accept = 1;
+                {
+                    int cc = c;
+                    uint32_t mw = mk[y * v.wwords + cc] & ((b == 0) ? 0u : ((1u << b) - 1u));
+                    while (mw == 0u && cc > 0) { --cc; mw = mk[y * v.wwords + cc]; }
+                    if (mw != 0u) {
+                        const int hb = emia_msb(mw);
+                        const int neg = (ng[y * v.wwords + cc] >> hb) & 1u;
+                        if (!neg) accept = 0;  // inside an already-followed outer border
+                    }
+                }
+                if (!accept) continue;
+                if (o.n_contours >= o.cap_contours) { o.overflow = 1; return; }
+                emia_trace_outer(v, m, x, y, o);
+                o.n_contours++;
+                o.cstart[o.n_contours] = o.n_pts;
+                if (o.overflow) return;
+            }
+        }
+    }
+}
+
+// cv2.contourArea on integer vertices: |shoelace| / 2 (exact; OpenCV accumulates integer-valued doubles).
+EMIA_HD double emia_contour_area(const uint32_t* pts, int n) {
+    if (n == 0) return 0.0;
+    long long a = 0;
+    int px = EMIA_PT_X(pts[n - 1]), py = EMIA_PT_Y(pts[n - 1]);
+    for (int i = 0; i < n; ++i) {
+        const int x = EMIA_PT_X(pts[i]), y = EMIA_PT_Y(pts[i]);
+        a += (long long)px * y - (long long)py * x;
+        px = x; py = y;
+    }
+    if (a < 0) a = -a;
+    return (double)a * 0.5;
+}
+
+// cv2.arcLength(c, closed=True): per-segment float32 sqrt of float32 (dx*dx+dy*dy), accumulated in double,
+// starting with the closing segment (last -> first).
+EMIA_HD double emia_arc_length_closed(const uint32_t* pts, int n) {
+    if (n <= 1) return 0.0;
+    double per = 0.0;
+    float px = (float)EMIA_PT_X(pts[n - 1]), py = (float)EMIA_PT_Y(pts[n - 1]);
+    for (int i = 0; i < n; ++i) {
+        const float x = (float)EMIA_PT_X(pts[i]), y = (float)EMIA_PT_Y(pts[i]);
+        const float dx = x - px, dy = y - py;
+        const float dx2 = dx * dx;
+        const float dy2 = dy * dy;
+        per += (double)sqrtf(dx2 + dy2);
+        px = x; py = y;
+    }
+    return per;
+}

@@ -1,0 +1,53 @@
+// hostsim.cpp — g++ build of the host/device core headers (deepemia_b200/csrc/core/*.cuh).
+// TEST INFRASTRUCTURE ONLY: lets the CPU-only CI (`pytest -m "not gpu"`) check the exact algorithms the CUDA
+// kernels execute against OpenCV / torch / the oracle without a GPU.  Nothing in deepemia_b200/ loads this.
+#include <vector>
+#include <cstring>
+#include <cstdlib>
+#include "../../deepemia_b200/csrc/core/emia_common.cuh"
+#include "../../deepemia_b200/csrc/core/emia_contour.cuh"
+#include "../../deepemia_b200/csrc/core/emia_hull.cuh"
+
+static void pack_bits(const uint8_t* mask, int H, int W, std::vector<uint32_t>& bits, int& ww) {
+    ww = (W + 31) / 32;
+    bits.assign((size_t)H * ww, 0u);
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x)
+            if (mask[(size_t)y * W + x]) bits[(size_t)y * ww + (x >> 5)] |= 1u << (x & 31);
+}
+
+extern "C" {
+
+// returns number of contours (discovery order) or -1 on overflow
+int sim_find_contours(const uint8_t* mask, int H, int W, uint32_t* pts, int cap_pts, int* cstart, int cap_c,
+                      int* n_pts) {
+    std::vector<uint32_t> bits; int ww;
+    pack_bits(mask, H, W, bits, ww);
+    std::vector<uint32_t> mk((size_t)H * ww), ng((size_t)H * ww);
+    EmiaBitView v{bits.data(), ww, H, ww, 0, 0};
+    EmiaContourOut o{pts, cap_pts, cstart, cap_c, 0, 0, 0};
+    emia_find_external_contours(v, mk.data(), ng.data(), o);
+    *n_pts = o.n_pts;
+    return o.overflow ? -1 : o.n_contours;
+}
+double sim_contour_area(const uint32_t* pts, int n) { return emia_contour_area(pts, n); }
+double sim_arc_length(const uint32_t* pts, int n) { return emia_arc_length_closed(pts, n); }
+
+
+int sim_convex_hull(const uint32_t* pts, int n, int clockwise, int* hull) {
+    std::vector<uint64_t> keys(n + 1); std::vector<int> stack(n + 3), tmp(n + 1);
+    return emia_convex_hull(pts, n, clockwise, keys.data(), stack.data(), hull, tmp.data());
+}
+// rect[5] = cx,cy,w,h,angle ; box[8] corners
+int sim_min_area_rect(const uint32_t* pts, int n, int clockwise, float* rect, float* box) {
+    std::vector<uint64_t> keys(n + 1); std::vector<int> stack(n + 3), tmp(n + 1), hull(n + 1);
+    int nh = emia_convex_hull(pts, n, clockwise, keys.data(), stack.data(), hull.data(), tmp.data());
+    std::vector<float> hp(2 * nh + 2), vect(2 * nh + 2), inv(nh + 1);
+    for (int i = 0; i < nh; ++i) { hp[2*i] = (float)EMIA_PT_X(pts[hull[i]]); hp[2*i+1] = (float)EMIA_PT_Y(pts[hull[i]]); }
+    EmiaRotRect r = emia_min_area_rect_from_hull(hp.data(), nh, vect.data(), inv.data());
+    if (nh > 2) emia_rotating_calipers(hp.data(), nh, vect.data(), inv.data(), rect + 5);
+    rect[0] = r.cx; rect[1] = r.cy; rect[2] = r.w; rect[3] = r.h; rect[4] = r.angle;
+    emia_box_points(r, box);
+    return nh;
+}
+}  // extern "C"
