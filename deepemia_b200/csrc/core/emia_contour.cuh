@@ -28,11 +28,15 @@ struct EmiaContourOut {
     int n_contours;
     int n_pts;
     int overflow;      // set when a capacity was exceeded (results invalid)
+    int max_len;       // longest contour (vertices)
+    int store;         // 0: count only (pts / cstart untouched, capacities ignored)
 };
 
 EMIA_HD void emia_contour_emit(EmiaContourOut& o, int fx, int fy) {
-    if (o.n_pts < o.cap_pts) o.pts[o.n_pts] = EMIA_PACK_PT(fx, fy);
-    else o.overflow = 1;
+    if (o.store) {
+        if (o.n_pts < o.cap_pts) o.pts[o.n_pts] = EMIA_PACK_PT(fx, fy);
+        else o.overflow = 1;
+    }
     o.n_pts++;
 }
 
@@ -100,8 +104,8 @@ EMIA_HD_NOINLINE void emia_find_external_contours(const EmiaBitView& v, uint32_t
     m.mk = mk; m.ng = ng; m.wwords = v.wwords;
     const int nw = v.h * v.wwords;
     for (int i = 0; i < nw; ++i) { mk[i] = 0u; ng[i] = 0u; }
-    o.n_contours = 0; o.n_pts = 0; o.overflow = 0;
-    o.cstart[0] = 0;
+    o.n_contours = 0; o.n_pts = 0; o.overflow = 0; o.max_len = 0;
+    if (o.store) o.cstart[0] = 0;
     for (int y = 0; y < v.h; ++y) {
         const uint32_t* row = v.bits + (size_t)y * v.pitch_words;
         for (int c = 0; c < v.wwords; ++c) {
@@ -129,10 +133,12 @@ EMIA_HD_NOINLINE void emia_find_external_contours(const EmiaBitView& v, uint32_t
                     }
                 }
                 if (!accept) continue;
-                if (o.n_contours >= o.cap_contours) { o.overflow = 1; return; }
+                if (o.store && o.n_contours >= o.cap_contours) { o.overflow = 1; return; }
+                const int before = o.n_pts;
                 emia_trace_outer(v, m, x, y, o);
                 o.n_contours++;
-                o.cstart[o.n_contours] = o.n_pts;
+                if (o.n_pts - before > o.max_len) o.max_len = o.n_pts - before;
+                if (o.store) o.cstart[o.n_contours] = o.n_pts;
                 if (o.overflow) return;
             }
         }

@@ -1,0 +1,439 @@
+// emia_kernels.cu — sm_100a kernels + C ABI (include/emia.h) of the deepEMIA post-head hot path.
+// Build: nvcc -O3 -lineinfo -fmad=false -gencode arch=compute_100a,code=sm_100a -shared -Xcompiler -fPIC
+// (-fmad=false: no implicit FMA contraction; see core/emia_common.cuh).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/emia.h"
+#include "core/emia_common.cuh"
+#include "core/emia_contour.cuh"
+#include "core/emia_hull.cuh"
+#include "core/emia_ellipse.cuh"
+#include "core/emia_measure.cuh"
+#include "core/emia_paste.cuh"
+#include "core/emia_nms.cuh"
+
+static thread_local char g_err[512] = "";
+static int emia_fail(int code, const char* fmt, const char* detail) {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+static int emia_check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return emia_fail(EMIA_ERR_LAUNCH, what, cudaGetErrorString(e));
+    return EMIA_OK;
+}
+static int emia_num_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+extern "C" int emia_version(void) { return 100; }
+extern "C" const char* emia_last_error(void) { return g_err; }
+
+// =================================================================================================
+// exclusive scan (int64), single CTA, three phases.  n is at most a few million and the kernel moves
+// 16 B per element: a single 1024-thread CTA finishes in tens of microseconds.
+// =================================================================================================
+__global__ void __launch_bounds__(1024) k_exclusive_scan_i64(int64_t* data, int64_t n) {
+    __shared__ int64_t part[1024];
+    const int t = threadIdx.x;
+    const int64_t chunk = (n + 1023) / 1024;
+    const int64_t lo = (int64_t)t * chunk;
+    const int64_t hi = lo + chunk < n ? lo + chunk : n;
+    int64_t s = 0;
+    for (int64_t i = lo; i < hi; ++i) s += data[i];
+    part[t] = s;
+    __syncthreads();
+    // Hillis-Steele inclusive scan of the 1024 partials
+    for (int off = 1; off < 1024; off <<= 1) {
+        int64_t v = (t >= off) ? part[t - off] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    int64_t run = (t == 0) ? 0 : part[t - 1];
+    for (int64_t i = lo; i < hi; ++i) {
+        const int64_t v = data[i];
+        data[i] = run;
+        run += v;
+    }
+    if (t == 1023) data[n] = part[1023];
+}
+
+extern "C" int emia_exclusive_scan_i64(int64_t* data, int64_t n, void* stream) {
+    if (!data || n < 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_exclusive_scan_i64: %s", "bad argument");
+    k_exclusive_scan_i64<<<1, 1024, 0, (cudaStream_t)stream>>>(data, n);
+    return emia_check_launch("emia_exclusive_scan_i64 launch: %s");
+}
+
+// =================================================================================================
+// K1 — paste + threshold + bit-pack
+// =================================================================================================
+__global__ void k_paste_plan(const float4* __restrict__ boxes, int64_t n, float sx, float sy, int H, int W,
+                             emia_inst_meta* __restrict__ meta, int64_t* __restrict__ crop_words) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 b = boxes[i];
+    const EmiaPasteBox pb = emia_paste_prepare(b.x, b.y, b.z, b.w, sx, sy, W, H);
+    emia_inst_meta m;
+    m.valid = pb.valid && pb.rx1 > pb.rx0 && pb.ry1 > pb.ry0;
+    if (m.valid) {
+        m.ry0 = pb.ry0; m.ch = pb.ry1 - pb.ry0;
+        m.rx0 = pb.rx0; m.rx1 = pb.rx1;
+        m.wc0 = pb.rx0 >> 5;
+        m.cw = ((pb.rx1 - 1) >> 5) - m.wc0 + 1;
+    } else {
+        m.ry0 = m.ch = m.rx0 = m.rx1 = m.wc0 = m.cw = 0;
+    }
+    m.valid = pb.valid;
+    m.reserved = 0;
+    meta[i] = m;
+    crop_words[i] = (int64_t)m.ch * m.cw;
+}
+
+extern "C" int emia_paste_plan(const float* boxes, int64_t n, float scale_x, float scale_y, int H, int W,
+                               emia_inst_meta* meta, int64_t* crop_words, void* stream) {
+    if (n < 0 || H <= 0 || W <= 0 || (n > 0 && (!boxes || !meta || !crop_words)))
+        return emia_fail(EMIA_ERR_BAD_ARG, "emia_paste_plan: %s", "bad argument");
+    if (n == 0) return EMIA_OK;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+    k_paste_plan<<<blocks, threads, 0, (cudaStream_t)stream>>>((const float4*)boxes, n, scale_x, scale_y, H, W, meta, crop_words);
+    return emia_check_launch("emia_paste_plan launch: %s");
+}
+
+#define EMIA_PASTE_THREADS 256
+#define EMIA_PASTE_TILE_WORDS 2048   // shared staging tile (words) for one band of crop rows
+
+__device__ __forceinline__ void emia_st_stream_u4(uint4* p, uint4 v) {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// One CTA per instance (grid-stride).  Frame = H rows x pitch_words words (pitch_words % 4 == 0).
+//  phase 0: stage the 28x28 probabilities and the per-column sampling taps in shared memory
+//  phase 1: zero-fill every 16-byte chunk of the frame that lies outside the crop's rows/chunk-columns
+//  phase 2: band by band: one warp per (row, word): 32 lanes sample 32 pixels, ballot -> word in shared memory;
+//           then the band is written out: crop words (coalesced) and the frame chunks (128-bit stores)
+template <bool kFrames>
+__global__ void __launch_bounds__(EMIA_PASTE_THREADS) k_paste(
+    const float* __restrict__ probs, const float4* __restrict__ boxes, const emia_inst_meta* __restrict__ meta,
+    const int64_t* __restrict__ crop_off, int64_t n, float sx, float sy, int H, int W, uint32_t* __restrict__ frames,
+    int64_t frame_slots, int pitch_words, uint32_t* __restrict__ crops, int32_t* __restrict__ bbox,
+    int32_t* __restrict__ area, int max_cols) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* s_prob = (float*)smem_raw;                                  // 784
+    uint32_t* s_tile = (uint32_t*)(s_prob + EMIA_MASK_SIDE * EMIA_MASK_SIDE);   // EMIA_PASTE_TILE_WORDS
+    int* s_ci0 = (int*)(s_tile + EMIA_PASTE_TILE_WORDS);               // max_cols
+    float* s_cw1 = (float*)(s_ci0 + max_cols);                         // max_cols
+    float* s_cw0 = s_cw1 + max_cols;                                   // max_cols
+    __shared__ int s_red[5];   // area, ymin, xmin, ymax, xmax
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int nwarps = EMIA_PASTE_THREADS / 32;
+    const int chunks_per_row = pitch_words >> 2;
+
+    for (int64_t inst = blockIdx.x; inst < n; inst += gridDim.x) {
+        const emia_inst_meta m = meta[inst];
+        const float4 bx = boxes[inst];
+        const EmiaPasteBox pb = emia_paste_prepare(bx.x, bx.y, bx.z, bx.w, sx, sy, W, H);
+        const bool live = m.valid && m.ch > 0 && m.cw > 0;
+        if (tid < 5) s_red[tid] = (tid == 0) ? 0 : ((tid == 1 || tid == 2) ? 0x7fffffff : -1);
+        if (live) {
+            const float* p = probs + inst * (EMIA_MASK_SIDE * EMIA_MASK_SIDE);
+            for (int k = tid; k < EMIA_MASK_SIDE * EMIA_MASK_SIDE; k += EMIA_PASTE_THREADS) s_prob[k] = p[k];
+            const int ncols = m.cw * 32;
+            for (int k = tid; k < ncols; k += EMIA_PASTE_THREADS) {
+                const int x = m.wc0 * 32 + k;
+                const EmiaAxisTap a = emia_paste_axis(x, pb.x0, pb.x1);
+                s_ci0[k] = a.i0; s_cw1[k] = a.w1; s_cw0[k] = a.w0;
+            }
+        }
+        // chunk-column range of the crop inside a frame row
+        const int cc0 = live ? (m.wc0 >> 2) : 0;
+        const int cc1 = live ? ((m.wc0 + m.cw - 1) >> 2) : -1;   // inclusive
+        uint4* frame = nullptr;
+        if (kFrames) {
+            frame = (uint4*)(frames + (size_t)(inst % frame_slots) * (size_t)H * (size_t)pitch_words);
+            // ---- phase 1: zero-fill outside the crop window
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            const int total = H * chunks_per_row;
+            if (!live) {
+                for (int q = tid; q < total; q += EMIA_PASTE_THREADS) emia_st_stream_u4(frame + q, z);
+            } else {
+                const int top = m.ry0 * chunks_per_row;                    // chunks above the crop rows
+                const int bot0 = (m.ry0 + m.ch) * chunks_per_row;          // first chunk below
+                for (int q = tid; q < top; q += EMIA_PASTE_THREADS) emia_st_stream_u4(frame + q, z);
+                for (int q = bot0 + tid; q < total; q += EMIA_PASTE_THREADS) emia_st_stream_u4(frame + q, z);
+                // rows of the crop: chunks left and right of [cc0, cc1]
+                const int side = chunks_per_row - (cc1 - cc0 + 1);
+                if (side > 0) {
+                    const int items = m.ch * side;
+                    for (int q = tid; q < items; q += EMIA_PASTE_THREADS) {
+                        const int r = q / side;
+                        int c = q - r * side;
+                        if (c >= cc0) c += (cc1 - cc0 + 1);
+                        emia_st_stream_u4(frame + (size_t)(m.ry0 + r) * chunks_per_row + c, z);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (live) {
+            // ---- phase 2: bands of rows
+            const int span_chunks = cc1 - cc0 + 1;
+            const int span_words = span_chunks * 4;           // staged row width (chunk aligned)
+            const int woff = m.wc0 - cc0 * 4;                 // crop word 0 sits at this word of the staged row
+            const int rows_per_band = emia_max(1, EMIA_PASTE_TILE_WORDS / span_words);
+            uint32_t* crop = crops + crop_off[inst];
+            int l_area = 0, l_ymin = 0x7fffffff, l_xmin = 0x7fffffff, l_ymax = -1, l_xmax = -1;
+            for (int r0 = 0; r0 < m.ch; r0 += rows_per_band) {
+                const int nr = emia_min(rows_per_band, m.ch - r0);
+                // clear the padding words of the staged band
+                for (int k = tid; k < nr * span_words; k += EMIA_PASTE_THREADS) s_tile[k] = 0u;
+                __syncthreads();
+                const int items = nr * m.cw;
+                for (int it = warp; it < items; it += nwarps) {
+                    const int r = it / m.cw;
+                    const int c = it - r * m.cw;
+                    const int y = m.ry0 + r0 + r;
+                    const EmiaAxisTap ay = emia_paste_axis(y, pb.y0, pb.y1);
+                    const int k = c * 32 + lane;
+                    const int x = m.wc0 * 32 + k;
+                    bool bit = false;
+                    if (x >= m.rx0 && x < m.rx1) {
+                        EmiaAxisTap ax;
+                        ax.i0 = s_ci0[k]; ax.w1 = s_cw1[k]; ax.w0 = s_cw0[k];
+                        bit = emia_paste_sample(s_prob, ax, ay) >= 0.5f;
+                    }
+                    const uint32_t word = __ballot_sync(0xffffffffu, bit);
+                    if (lane == 0) {
+                        s_tile[r * span_words + woff + c] = word;
+                        if (word) {
+                            l_area += __popc(word);
+                            l_ymin = min(l_ymin, y); l_ymax = max(l_ymax, y);
+                            l_xmin = min(l_xmin, (m.wc0 + c) * 32 + (__ffs((int)word) - 1));
+                            l_xmax = max(l_xmax, (m.wc0 + c) * 32 + (31 - __clz((int)word)));
+                        }
+                    }
+                }
+                __syncthreads();
+                // write the band: crop words
+                for (int k = tid; k < nr * m.cw; k += EMIA_PASTE_THREADS) {
+                    const int r = k / m.cw;
+                    const int c = k - r * m.cw;
+                    crop[(size_t)(r0 + r) * m.cw + c] = s_tile[r * span_words + woff + c];
+                }
+                if (kFrames) {
+                    const uint4* s4 = (const uint4*)s_tile;
+                    for (int k = tid; k < nr * span_chunks; k += EMIA_PASTE_THREADS) {
+                        const int r = k / span_chunks;
+                        const int c = k - r * span_chunks;
+                        emia_st_stream_u4(frame + (size_t)(m.ry0 + r0 + r) * chunks_per_row + cc0 + c, s4[r * span_chunks + c]);
+                    }
+                }
+                __syncthreads();
+            }
+            if (lane == 0 && l_area) {
+                atomicAdd(&s_red[0], l_area);
+                atomicMin(&s_red[1], l_ymin); atomicMin(&s_red[2], l_xmin);
+                atomicMax(&s_red[3], l_ymax); atomicMax(&s_red[4], l_xmax);
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            const int a = live ? s_red[0] : 0;
+            area[inst] = a;
+            int4 bb;
+            if (a > 0) bb = make_int4(s_red[1], s_red[2], s_red[3], s_red[4]);
+            else bb = make_int4(-1, -1, -1, -1);
+            ((int4*)bbox)[inst] = bb;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- variant 1: the frame is produced by bulk shared->global copies (cp.async.bulk, the TMA engine) ------------
+// A CTA keeps a zeroed 16 KB buffer in shared memory; every 16 KB piece of the frame that does not touch the
+// crop rows is one bulk copy from it (one instruction instead of 1024 STG.128); the pieces that do touch crop
+// rows are composed in a second shared buffer first.  Crops/bbox/area are produced exactly as in variant 0.
+#define EMIA_BULK_BYTES 16384
+__device__ __forceinline__ void emia_bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void emia_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void emia_bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void emia_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__global__ void __launch_bounds__(EMIA_PASTE_THREADS) k_paste_bulk(
+    const float* __restrict__ probs, const float4* __restrict__ boxes, const emia_inst_meta* __restrict__ meta,
+    const int64_t* __restrict__ crop_off, int64_t n, float sx, float sy, int H, int W, uint32_t* __restrict__ frames,
+    int64_t frame_slots, int pitch_words, uint32_t* __restrict__ crops, int32_t* __restrict__ bbox,
+    int32_t* __restrict__ area, int max_cols) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t* s_zero = (uint32_t*)smem_raw;                              // EMIA_BULK_BYTES
+    uint32_t* s_band = s_zero + EMIA_BULK_BYTES / 4;                     // EMIA_BULK_BYTES
+    float* s_prob = (float*)(s_band + EMIA_BULK_BYTES / 4);              // 784
+    int* s_ci0 = (int*)(s_prob + EMIA_MASK_SIDE * EMIA_MASK_SIDE);
+    float* s_cw1 = (float*)(s_ci0 + max_cols);
+    float* s_cw0 = s_cw1 + max_cols;
+    __shared__ int s_red[5];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int nwarps = EMIA_PASTE_THREADS / 32;
+    const int row_bytes = pitch_words * 4;
+    const int rows_per_piece = EMIA_BULK_BYTES / row_bytes;             // >= 1 (checked on the host)
+    const int piece_rows_bytes = rows_per_piece * row_bytes;
+
+    for (int k = tid; k < EMIA_BULK_BYTES / 4; k += EMIA_PASTE_THREADS) s_zero[k] = 0u;
+    emia_fence_async_smem();
+    __syncthreads();
+
+    for (int64_t inst = blockIdx.x; inst < n; inst += gridDim.x) {
+        const emia_inst_meta m = meta[inst];
+        const float4 bx = boxes[inst];
+        const EmiaPasteBox pb = emia_paste_prepare(bx.x, bx.y, bx.z, bx.w, sx, sy, W, H);
+        const bool live = m.valid && m.ch > 0 && m.cw > 0;
+        if (tid < 5) s_red[tid] = (tid == 0) ? 0 : ((tid == 1 || tid == 2) ? 0x7fffffff : -1);
+        if (live) {
+            const float* p = probs + inst * (EMIA_MASK_SIDE * EMIA_MASK_SIDE);
+            for (int k = tid; k < EMIA_MASK_SIDE * EMIA_MASK_SIDE; k += EMIA_PASTE_THREADS) s_prob[k] = p[k];
+            const int ncols = m.cw * 32;
+            for (int k = tid; k < ncols; k += EMIA_PASTE_THREADS) {
+                const int x = m.wc0 * 32 + k;
+                const EmiaAxisTap a = emia_paste_axis(x, pb.x0, pb.x1);
+                s_ci0[k] = a.i0; s_cw1[k] = a.w1; s_cw0[k] = a.w0;
+            }
+        }
+        unsigned char* frame = (unsigned char*)(frames + (size_t)(inst % frame_slots) * (size_t)H * (size_t)pitch_words);
+        const int crop_r0 = live ? m.ry0 : H, crop_r1 = live ? m.ry0 + m.ch : H;   // crop rows [r0, r1)
+        // pieces entirely outside the crop rows: straight from the zero buffer (issued by one thread)
+        if (tid == 0) {
+            for (int r = 0; r < H; r += rows_per_piece) {
+                const int re = emia_min(r + rows_per_piece, H);
+                if (re <= crop_r0 || r >= crop_r1)
+                    emia_bulk_s2g(frame + (size_t)r * row_bytes, s_zero, (uint32_t)((re - r) * row_bytes));
+            }
+            emia_bulk_commit();
+        }
+        __syncthreads();
+        int l_area = 0, l_ymin = 0x7fffffff, l_xmin = 0x7fffffff, l_ymax = -1, l_xmax = -1;
+        if (live) {
+            uint32_t* crop = crops + crop_off[inst];
+            const int p0 = (crop_r0 / rows_per_piece) * rows_per_piece;
+            for (int r = p0; r < crop_r1; r += rows_per_piece) {
+                const int re = emia_min(r + rows_per_piece, H);
+                const int nr = re - r;
+                // the previous bulk read of s_band must have completed before it is overwritten
+                if (tid == 0) emia_bulk_wait_read_all();
+                __syncthreads();
+                for (int k = tid; k < nr * pitch_words; k += EMIA_PASTE_THREADS) s_band[k] = 0u;
+                __syncthreads();
+                const int ya = emia_max(r, crop_r0), yb = emia_min(re, crop_r1);
+                const int items = (yb - ya) * m.cw;
+                for (int it = warp; it < items; it += nwarps) {
+                    const int rr = it / m.cw;
+                    const int c = it - rr * m.cw;
+                    const int y = ya + rr;
+                    const EmiaAxisTap ay = emia_paste_axis(y, pb.y0, pb.y1);
+                    const int k = c * 32 + lane;
+                    const int x = m.wc0 * 32 + k;
+                    bool bit = false;
+                    if (x >= m.rx0 && x < m.rx1) {
+                        EmiaAxisTap ax;
+                        ax.i0 = s_ci0[k]; ax.w1 = s_cw1[k]; ax.w0 = s_cw0[k];
+                        bit = emia_paste_sample(s_prob, ax, ay) >= 0.5f;
+                    }
+                    const uint32_t word = __ballot_sync(0xffffffffu, bit);
+                    if (lane == 0) {
+                        s_band[(y - r) * pitch_words + m.wc0 + c] = word;
+                        crop[(size_t)(y - crop_r0) * m.cw + c] = word;
+                        if (word) {
+                            l_area += __popc(word);
+                            l_ymin = min(l_ymin, y); l_ymax = max(l_ymax, y);
+                            l_xmin = min(l_xmin, (m.wc0 + c) * 32 + (__ffs((int)word) - 1));
+                            l_xmax = max(l_xmax, (m.wc0 + c) * 32 + (31 - __clz((int)word)));
+                        }
+                    }
+                }
+                emia_fence_async_smem();
+                __syncthreads();
+                if (tid == 0) {
+                    emia_bulk_s2g(frame + (size_t)r * row_bytes, s_band, (uint32_t)(nr * row_bytes));
+                    emia_bulk_commit();
+                }
+            }
+            if (lane == 0 && l_area) {
+                atomicAdd(&s_red[0], l_area);
+                atomicMin(&s_red[1], l_ymin); atomicMin(&s_red[2], l_xmin);
+                atomicMax(&s_red[3], l_ymax); atomicMax(&s_red[4], l_xmax);
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            const int a = live ? s_red[0] : 0;
+            area[inst] = a;
+            ((int4*)bbox)[inst] = a > 0 ? make_int4(s_red[1], s_red[2], s_red[3], s_red[4]) : make_int4(-1, -1, -1, -1);
+            emia_bulk_wait_read_all();   // s_band / s_zero reads done before the next instance touches s_band
+        }
+        __syncthreads();
+        (void)piece_rows_bytes;
+    }
+    // all bulk writes must be complete before the CTA (and its shared memory) goes away
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+extern "C" int emia_paste_threshold_bitpack(const float* probs, const float* boxes, const emia_inst_meta* meta,
+                                            const int64_t* crop_off, int64_t n, float scale_x, float scale_y, int H,
+                                            int W, uint32_t* frames, int64_t frame_slots, int pitch_words,
+                                            uint32_t* crops, int32_t* bbox, int32_t* area, int variant, void* stream) {
+    if (n < 0 || H <= 0 || W <= 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_paste_threshold_bitpack: %s", "bad shape");
+    if (n == 0) return EMIA_OK;
+    if (!probs || !boxes || !meta || !crop_off || !crops || !bbox || !area)
+        return emia_fail(EMIA_ERR_BAD_ARG, "emia_paste_threshold_bitpack: %s", "null pointer");
+    if (frames) {
+        if (pitch_words * 32 < W || (pitch_words & 3) || frame_slots <= 0)
+            return emia_fail(EMIA_ERR_BAD_ARG, "emia_paste_threshold_bitpack: %s", "pitch_words must be a multiple of 4 covering W; frame_slots > 0");
+        if (((uintptr_t)frames & 15) != 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_paste_threshold_bitpack: %s", "frames must be 16-byte aligned");
+    }
+    const int max_cols = ((W + 31) / 32 + 1) * 32;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int sms = emia_num_sms();
+    if (variant == 1 && frames) {
+        if (pitch_words * 4 > EMIA_BULK_BYTES) return emia_fail(EMIA_ERR_UNSUPPORTED, "emia_paste_threshold_bitpack: %s", "variant 1 needs a frame row <= 16 KB");
+        const size_t smem = 2 * EMIA_BULK_BYTES + EMIA_MASK_SIDE * EMIA_MASK_SIDE * 4 + (size_t)max_cols * 12;
+        cudaFuncSetAttribute(k_paste_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const unsigned grid = (unsigned)(n < (int64_t)sms * 4 ? n : (int64_t)sms * 4);
+        k_paste_bulk<<<grid, EMIA_PASTE_THREADS, smem, st>>>(probs, (const float4*)boxes, meta, crop_off, n, scale_x, scale_y, H, W,
+                                                             frames, frame_slots, pitch_words, crops, bbox, area, max_cols);
+        return emia_check_launch("emia_paste_threshold_bitpack (bulk) launch: %s");
+    }
+    const size_t smem = EMIA_MASK_SIDE * EMIA_MASK_SIDE * 4 + EMIA_PASTE_TILE_WORDS * 4 + (size_t)max_cols * 12;
+    const unsigned grid = (unsigned)(n < (int64_t)sms * 8 ? n : (int64_t)sms * 8);
+    if (frames) {
+        cudaFuncSetAttribute(k_paste<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_paste<true><<<grid, EMIA_PASTE_THREADS, smem, st>>>(probs, (const float4*)boxes, meta, crop_off, n, scale_x, scale_y, H, W,
+                                                              frames, frame_slots, pitch_words, crops, bbox, area, max_cols);
+    } else {
+        cudaFuncSetAttribute(k_paste<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_paste<false><<<grid, EMIA_PASTE_THREADS, smem, st>>>(probs, (const float4*)boxes, meta, crop_off, n, scale_x, scale_y, H, W,
+                                                               nullptr, 1, pitch_words, crops, bbox, area, max_cols);
+    }
+    return emia_check_launch("emia_paste_threshold_bitpack launch: %s");
+}
+
+#include "emia_masks.cuh"
+#include "emia_morpho_kernels.cuh"
+#include "emia_group_kernels.cuh"

@@ -1,0 +1,94 @@
+// emia_morpho_kernels.cuh — K5: external contours + morphometry (part of emia_kernels.cu).
+// One thread per instance: border following is inherently sequential per component, so parallelism comes from
+// the number of instances in flight (10^5..10^6 per launch); the crop (a few hundred bytes) stays in L1.
+#pragma once
+
+__device__ __forceinline__ EmiaBitView emia_make_view(const uint32_t* crops, const emia_inst_meta& m, int64_t off) {
+    EmiaBitView v;
+    v.bits = crops + off; v.pitch_words = m.cw; v.h = m.ch; v.wwords = m.cw;
+    v.x_origin = m.wc0 * 32; v.y_origin = m.ry0;
+    return v;
+}
+
+__global__ void __launch_bounds__(128) k_contour_count(const uint32_t* __restrict__ crops, const emia_inst_meta* __restrict__ meta,
+                                                       const int64_t* __restrict__ crop_off, int64_t n, uint32_t* __restrict__ marks,
+                                                       int64_t* __restrict__ n_contours, int64_t* __restrict__ n_points,
+                                                       int64_t* __restrict__ scratch_bytes) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const emia_inst_meta m = meta[i];
+    if (m.ch <= 0 || m.cw <= 0) { n_contours[i] = 0; n_points[i] = 0; scratch_bytes[i] = 0; return; }
+    const int64_t off = crop_off[i];
+    const EmiaBitView v = emia_make_view(crops, m, off);
+    uint32_t* mk = marks + 2 * off;
+    uint32_t* ng = mk + (size_t)m.ch * m.cw;
+    EmiaContourOut o;
+    o.pts = nullptr; o.cap_pts = 0; o.cstart = nullptr; o.cap_contours = 0; o.store = 0;
+    emia_find_external_contours(v, mk, ng, o);
+    n_contours[i] = o.n_contours;
+    n_points[i] = o.n_pts;
+    scratch_bytes[i] = o.n_contours ? (int64_t)((emia_measure_scratch_bytes(o.max_len) + 15) & ~(size_t)15) : 0;
+}
+
+__global__ void __launch_bounds__(128) k_contour_measure(const uint32_t* __restrict__ crops, const emia_inst_meta* __restrict__ meta,
+                                                         const int64_t* __restrict__ crop_off, int64_t n, uint32_t* __restrict__ marks,
+                                                         const int64_t* __restrict__ cont_off, const int64_t* __restrict__ pt_off,
+                                                         const int64_t* __restrict__ scratch_off, double um_pix, double min_area,
+                                                         uint32_t* __restrict__ pts, int32_t* __restrict__ cstart,
+                                                         double* __restrict__ records, int32_t* __restrict__ rec_inst,
+                                                         double* __restrict__ perim0, uint8_t* __restrict__ scratch) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const emia_inst_meta m = meta[i];
+    const int64_t c0 = cont_off[i];
+    const int nc = (int)(cont_off[i + 1] - c0);
+    int32_t* cs = cstart + c0 + i;
+    if (nc == 0 || m.ch <= 0 || m.cw <= 0) { cs[0] = 0; perim0[i] = 0.0; return; }
+    const int64_t off = crop_off[i];
+    const EmiaBitView v = emia_make_view(crops, m, off);
+    uint32_t* mk = marks + 2 * off;
+    uint32_t* ng = mk + (size_t)m.ch * m.cw;
+    uint32_t* p = pts + pt_off[i];
+    EmiaContourOut o;
+    o.pts = p; o.cap_pts = (int)(pt_off[i + 1] - pt_off[i]); o.cstart = cs; o.cap_contours = nc; o.store = 1;
+    emia_find_external_contours(v, mk, ng, o);
+    void* sc = scratch + scratch_off[i];
+    for (int j = 0; j < nc; ++j) {
+        const int k = nc - 1 - j;                     // OpenCV returns contours in reverse discovery order
+        const uint32_t* cp = p + cs[k];
+        const int len = cs[k + 1] - cs[k];
+        double* rec = records + (size_t)(c0 + j) * EMIA_REC_FIELDS;
+        emia_measure_contour(cp, len, um_pix, sc, rec);
+        rec[EMIA_REC_MEASURED] = (rec[EMIA_REC_AREA] >= min_area) ? 1.0 : 0.0;
+        rec_inst[c0 + j] = (int32_t)i;
+        if (j == 0) perim0[i] = rec[EMIA_REC_PERIMETER];
+    }
+}
+
+extern "C" int emia_contour_count(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n,
+                                  uint32_t* marks, int64_t* n_contours, int64_t* n_points, int64_t* scratch_bytes,
+                                  void* stream) {
+    if (n < 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_count: %s", "bad n");
+    if (n == 0) return EMIA_OK;
+    if (!crops || !meta || !crop_off || !marks || !n_contours || !n_points || !scratch_bytes)
+        return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_count: %s", "null pointer");
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    k_contour_count<<<grid, 128, 0, (cudaStream_t)stream>>>(crops, meta, crop_off, n, marks, n_contours, n_points, scratch_bytes);
+    return emia_check_launch("emia_contour_count launch: %s");
+}
+
+extern "C" int emia_contour_measure(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n,
+                                    uint32_t* marks, const int64_t* cont_off, const int64_t* pt_off,
+                                    const int64_t* scratch_off, double um_pix, double min_area, uint32_t* pts,
+                                    int32_t* cstart, double* records, int32_t* rec_inst, double* perim0,
+                                    uint8_t* scratch, void* stream) {
+    if (n < 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_measure: %s", "bad n");
+    if (n == 0) return EMIA_OK;
+    if (!crops || !meta || !crop_off || !marks || !cont_off || !pt_off || !scratch_off || !pts || !cstart || !records ||
+        !rec_inst || !perim0 || !scratch)
+        return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_measure: %s", "null pointer");
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    k_contour_measure<<<grid, 128, 0, (cudaStream_t)stream>>>(crops, meta, crop_off, n, marks, cont_off, pt_off, scratch_off, um_pix,
+                                                              min_area, pts, cstart, records, rec_inst, perim0, scratch);
+    return emia_check_launch("emia_contour_measure launch: %s");
+}

@@ -1,0 +1,154 @@
+/* emia.h — C ABI of libemia.so: the B200 (sm_100a) post-head hot path of deepEMIA.
+ *
+ * The reference (Deam0on/deepEMIA) is pure Python and has no FFI; the functions below are what a ctypes binding
+ * inside the reference's own modules would call instead of numpy/OpenCV/scipy.  Each entry
+ * cites the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises the host;
+ *   - no allocation, no global state: scratch comes from caller-provided workspaces sized by *_bytes() queries;
+ *   - return value: 0 = OK, negative = error (EMIA_ERR_*); emia_last_error() gives a thread-local message;
+ *   - masks are bit-packed: bit j (LSB first) of 32-bit word w of a row is pixel x = 32*w + j.
+ *
+ * Instance layout
+ *   An "instance" is one mask.  Its bits live in a CROP: rows [ry0, ry0+ch) x frame word-columns [wc0, wc0+cw),
+ *   stored contiguously (ch*cw words) at crops + crop_off[i].  Crops are word-aligned with the frame, so two
+ *   crops intersect with plain AND of words.  Optionally the same bits are also written into a full
+ *   H x pitch_words FRAME (the drop-in equivalent of Detectron2's N x H x W `pred_masks`).
+ *   Instances are grouped (one group = one image / tile / de-dup call) by cap_off[G+1]; the members of group g
+ *   that are currently alive are idx[cap_off[g] .. cap_off[g]+len[g]) (instance ids, in list order).
+ */
+#ifndef EMIA_H
+#define EMIA_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMIA_OK 0
+#define EMIA_ERR_BAD_ARG (-1)
+#define EMIA_ERR_UNSUPPORTED (-2)
+#define EMIA_ERR_LAUNCH (-3)
+#define EMIA_ERR_WORKSPACE (-4)
+
+#define EMIA_MASK_SIDE 28   /* Mask R-CNN mask head resolution */
+#define EMIA_REC_FIELDS 16  /* doubles per measurement record, see emia_rec_field */
+
+typedef struct emia_inst_meta {
+    int32_t ry0;     /* first frame row of the crop */
+    int32_t wc0;     /* first frame word-column of the crop */
+    int32_t ch;      /* crop rows */
+    int32_t cw;      /* crop words per row */
+    int32_t rx0;     /* first frame pixel column that may be set */
+    int32_t rx1;     /* one past the last frame pixel column that may be set */
+    int32_t valid;   /* 0: dropped by Boxes.nonempty() (detector_postprocess) */
+    int32_t reserved;
+} emia_inst_meta;
+
+/* order of the doubles in one measurement record (CSV columns of src/functions/inference.py:987-1010 + extras) */
+enum emia_rec_field {
+    EMIA_REC_MAJOR_AXIS = 0, EMIA_REC_MINOR_AXIS = 1, EMIA_REC_ECCENTRICITY = 2, EMIA_REC_LENGTH = 3,
+    EMIA_REC_WIDTH = 4, EMIA_REC_CIRCULAR_ED = 5, EMIA_REC_ASPECT = 6, EMIA_REC_CIRCULARITY = 7,
+    EMIA_REC_CHORDS = 8, EMIA_REC_FERET = 9, EMIA_REC_ROUNDNESS = 10, EMIA_REC_SPHERICITY = 11,
+    EMIA_REC_AREA = 12, EMIA_REC_PERIMETER = 13, EMIA_REC_NVERT = 14, EMIA_REC_MEASURED = 15
+};
+
+int emia_version(void);
+const char* emia_last_error(void);
+
+/* ---- utilities ------------------------------------------------------------------------------------------- */
+/* in-place exclusive prefix sum of data[0..n) with the total stored at data[n] (n+1 entries). */
+int emia_exclusive_scan_i64(int64_t* data, int64_t n, void* stream);
+
+/* ---- K1: paste + threshold + bit-pack ----------------------------------------------------------------------
+ * Replaces Detectron2 0.6 detector_postprocess + paste_masks_in_image(threshold 0.5) reached through
+ * `predictor(image)` at src/functions/inference.py:1395,1398,1507,1669,2107, the D2H of pred_masks at :1401,
+ * `np.sum(mask)` at :1683,:1800,:2604 and get_mask_bbox at :2722-2733.
+ * emia_paste_plan: box scale/clip/non-empty + sampling region -> meta[i], crop_words[i] = ch*cw (caller scans).
+ * emia_paste_threshold_bitpack: writes crops (+ full frames when frames != NULL: instance i goes to frame slot
+ *   i % frame_slots), bbox[i] = (y_min, x_min, y_max, x_max) inclusive or (-1,-1,-1,-1), area[i] = popcount.
+ *   variant: 0 = 128-bit streaming stores, 1 = bulk shared->global copies (TMA engine). */
+int emia_paste_plan(const float* boxes, int64_t n, float scale_x, float scale_y, int H, int W,
+                    emia_inst_meta* meta, int64_t* crop_words, void* stream);
+int emia_paste_threshold_bitpack(const float* probs, const float* boxes, const emia_inst_meta* meta,
+                                 const int64_t* crop_off, int64_t n, float scale_x, float scale_y, int H, int W,
+                                 uint32_t* frames, int64_t frame_slots, int pitch_words, uint32_t* crops,
+                                 int32_t* bbox, int32_t* area, int variant, void* stream);
+
+/* ---- mask import: byte masks -> crops (for callers that already hold H x W masks) ---------------------------
+ * Replaces the reference's list-of-H x W-numpy-arrays representation (src/functions/inference.py:1401-1403,
+ * :2413-2416).  emia_mask_bbox: bbox/area of n byte masks (non-zero = set) + meta + crop_words (caller scans);
+ * emia_mask_pack: bit-pack the bbox crops. */
+int emia_mask_bbox(const uint8_t* masks, int64_t n, int H, int W, emia_inst_meta* meta, int64_t* crop_words,
+                   int32_t* bbox, int32_t* area, void* stream);
+int emia_mask_pack(const uint8_t* masks, int64_t n, int H, int W, const emia_inst_meta* meta,
+                   const int64_t* crop_off, uint32_t* crops, void* stream);
+/* crops -> byte masks (0/1), full frame, for the drop-in list-of-arrays surface */
+int emia_mask_unpack(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off,
+                     const int32_t* idx, int64_t n_idx, int H, int W, uint8_t* masks_out, void* stream);
+
+/* ---- K5: external contours + morphometry --------------------------------------------------------------------
+ * Replaces cv2.findContours(RETR_EXTERNAL, CHAIN_APPROX_SIMPLE) + imutils.grab_contours at
+ * src/functions/inference.py:1164-1167 and :2605, cv2.contourArea :1175, the min-area gate :1178-1190,
+ * calculate_measurements src/utils/measurements.py:114-233 and cv2.arcLength(contours[0]) at inference.py:2607.
+ * Pass 1 (emia_contour_count) sizes the outputs; the caller scans n_contours / n_points / scratch sizes.
+ *   marks: 2 * total_crop_words words of scratch.
+ *   scratch_bytes[i] = bytes of per-instance hull scratch needed by pass 2.
+ * Pass 2 (emia_contour_measure): pts (packed x | y<<16, frame coordinates), cstart (per instance n_contours+1
+ *   entries at cont_off[i] + i, relative to pt_off[i], DISCOVERY order), records in OpenCV order (reverse
+ *   discovery) at cont_off[i] + j, rec_inst (instance id per record), perim0[i] = arcLength of the first
+ *   returned contour (0 if none).  records[..][EMIA_REC_MEASURED] = 1 when contourArea >= min_area. */
+int emia_contour_count(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n,
+                       uint32_t* marks, int64_t* n_contours, int64_t* n_points, int64_t* scratch_bytes,
+                       void* stream);
+int emia_contour_measure(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n,
+                         uint32_t* marks, const int64_t* cont_off, const int64_t* pt_off,
+                         const int64_t* scratch_off, double um_pix, double min_area, uint32_t* pts,
+                         int32_t* cstart, double* records, int32_t* rec_inst, double* perim0, uint8_t* scratch,
+                         void* stream);
+
+/* ---- K4: mask-IoU de-duplication and spatial constraints ----------------------------------------------------
+ * All operate on G groups at once; see "Instance layout".  total_cap = cap_off[G] (the host knows it).
+ * Workspace size: emia_group_workspace_bytes (pass exactly that many bytes: the tail is cleared per call).
+ * emia_dedup_smart       : deduplicate_masks_smart, src/functions/inference.py:2552-2677 (+ :2680-2733), incl. the
+ *                          artifact pre-filter (empty / aspect / compactness < 0.15) and quirks Q1, Q2, Q10.
+ *                          Output in keep order (score descending).
+ * emia_dedup_inorder     : greedy in-order de-dup with iou(), inference.py:1453-1459 (:422-435); also :2241-2246.
+ * emia_overlap_rules     : filter_by_overlap_rules, src/utils/spatial_constraints.py:192-277.
+ *                          rule_active[c] != 0 -> class c has an enforced rule with threshold rule_max_iou[c].
+ * emia_containment_rules : filter_by_containment_rules, spatial_constraints.py:280-398 (rules applied in order). */
+size_t emia_group_workspace_bytes(const int32_t* cap_off_host, int32_t G);
+int emia_dedup_smart(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off,
+                     const int32_t* bbox, const int32_t* area, const double* perim0, const int64_t* n_contours,
+                     const float* scores, const int32_t* classes, const int32_t* cap_off, int32_t G,
+                     int32_t total_cap, const int32_t* in_len, const int32_t* in_idx, double iou_threshold, double max_aspect_ratio,
+                     int32_t* out_len, int32_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
+int emia_dedup_inorder(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off,
+                       const int32_t* bbox, const int32_t* area, const int32_t* cap_off, int32_t G,
+                       int32_t total_cap, const int32_t* in_len, const int32_t* in_idx, double iou_threshold, int32_t* out_len,
+                       int32_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
+int emia_overlap_rules(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off,
+                       const int32_t* bbox, const int32_t* area, const float* scores, const int32_t* classes,
+                       const int32_t* cap_off, int32_t G, int32_t total_cap, const int32_t* in_len, const int32_t* in_idx,
+                       const int32_t* rule_active, const double* rule_max_iou, int32_t num_classes,
+                       int32_t* out_len, int32_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
+int emia_containment_rules(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off,
+                           const int32_t* bbox, const int32_t* area, const int32_t* classes,
+                           const int32_t* cap_off, int32_t G, int32_t total_cap, const int32_t* in_len, const int32_t* in_idx,
+                           const int32_t* child_class_host, const int32_t* parent_class_host, int32_t n_rules,
+                           double containment_threshold, int32_t* out_len, int32_t* out_idx, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
+/* pairwise helpers (drop-in for iou / calculate_iou / calculate_containment on explicit pairs):
+ * out[k] = {intersection, area_a, area_b} for pairs (pa[k], pb[k]). */
+int emia_pair_counts(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off,
+                     const int32_t* area, const int32_t* pa, const int32_t* pb, int64_t n_pairs, int64_t* out,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMIA_H */

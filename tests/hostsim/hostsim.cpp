@@ -7,6 +7,9 @@
 #include "../../deepemia_b200/csrc/core/emia_common.cuh"
 #include "../../deepemia_b200/csrc/core/emia_contour.cuh"
 #include "../../deepemia_b200/csrc/core/emia_hull.cuh"
+#include "../../deepemia_b200/csrc/core/emia_ellipse.cuh"
+#include "../../deepemia_b200/csrc/core/emia_measure.cuh"
+#include "../../deepemia_b200/csrc/core/emia_paste.cuh"
 
 static void pack_bits(const uint8_t* mask, int H, int W, std::vector<uint32_t>& bits, int& ww) {
     ww = (W + 31) / 32;
@@ -25,7 +28,7 @@ int sim_find_contours(const uint8_t* mask, int H, int W, uint32_t* pts, int cap_
     pack_bits(mask, H, W, bits, ww);
     std::vector<uint32_t> mk((size_t)H * ww), ng((size_t)H * ww);
     EmiaBitView v{bits.data(), ww, H, ww, 0, 0};
-    EmiaContourOut o{pts, cap_pts, cstart, cap_c, 0, 0, 0};
+    EmiaContourOut o{pts, cap_pts, cstart, cap_c, 0, 0, 0, 0, 1};
     emia_find_external_contours(v, mk.data(), ng.data(), o);
     *n_pts = o.n_pts;
     return o.overflow ? -1 : o.n_contours;
@@ -49,5 +52,33 @@ int sim_min_area_rect(const uint32_t* pts, int n, int clockwise, float* rect, fl
     rect[0] = r.cx; rect[1] = r.cy; rect[2] = r.w; rect[3] = r.h; rect[4] = r.angle;
     emia_box_points(r, box);
     return nh;
+}
+
+// out[5] = cx, cy, w, h, angle
+int sim_fit_ellipse(const uint32_t* pts, int n, float* out) {
+    EmiaEllipse e = emia_fit_ellipse_general(pts, n);
+    out[0] = e.cx; out[1] = e.cy; out[2] = e.w; out[3] = e.h; out[4] = e.angle;
+    return e.ok;
+}
+
+// rec[16]
+void sim_measure_contour(const uint32_t* pts, int n, double um_pix, double* rec) {
+    std::vector<uint64_t> scratch(emia_measure_scratch_bytes(n) / 8 + 2);
+    emia_measure_contour(pts, n, um_pix, scratch.data(), rec);
+}
+
+// paste one instance into an H x W uint8 frame (zero-initialised by caller). returns valid flag; region[4]=rx0,ry0,rx1,ry1
+int sim_paste(const float* prob, const float* box, float sx, float sy, int H, int W, uint8_t* out, int* region) {
+    EmiaPasteBox b = emia_paste_prepare(box[0], box[1], box[2], box[3], sx, sy, W, H);
+    region[0] = b.rx0; region[1] = b.ry0; region[2] = b.rx1; region[3] = b.ry1;
+    if (!b.valid) return 0;
+    for (int y = b.ry0; y < b.ry1; ++y) {
+        EmiaAxisTap ay = emia_paste_axis(y, b.y0, b.y1);
+        for (int x = b.rx0; x < b.rx1; ++x) {
+            EmiaAxisTap ax = emia_paste_axis(x, b.x0, b.x1);
+            out[(size_t)y * W + x] = emia_paste_sample(prob, ax, ay) >= 0.5f;
+        }
+    }
+    return 1;
 }
 }  // extern "C"
