@@ -65,12 +65,15 @@ def test_paste_frame_ring_and_crops_only(cuda_device):
     H, W = 256, 256
     probs, boxes, _, _ = _heads(3, 40, H, W, rmin=5, rmax=20, margin=10)
     tp, tb = _dev(cuda_device, probs, boxes)
-    ref = d2_paste.paste_masks_in_image(probs, boxes, (H, W))
-    ring = torch.full((8, H, engine.pitch_words_for(W)), -1, dtype=torch.int32, device=cuda_device)
+    ref = d2_paste.predictor_instances(probs, boxes, np.ones(len(boxes), np.float32), np.zeros(len(boxes), np.int32), 1.0, 1.0, H, W)[0]
+    assert len(ref) == len(boxes)
+    ring = torch.full((len(probs), H, engine.pitch_words_for(W)), -1, dtype=torch.int32, device=cuda_device)
     iset = engine.paste(tp, tb, H, W, frames=ring)
-    fr = _unpack_frames(ring, W)
-    for slot in range(8):
-        assert np.array_equal(fr[slot], ref[32 + slot])      # last writer of slot s is instance 32 + s
+    assert np.array_equal(_unpack_frames(ring, W), ref)
+    # a ring smaller than n is a scratch arena (slot = i % slots, last writer undefined): only crops/bbox/area are defined
+    small = torch.empty((8, H, engine.pitch_words_for(W)), dtype=torch.int32, device=cuda_device)
+    iset3 = engine.paste(tp, tb, H, W, frames=small)
+    assert torch.equal(iset.crops[:iset.total_crop_words], iset3.crops[:iset3.total_crop_words])
     iset2 = engine.paste(tp, tb, H, W, frames=None)
     assert torch.equal(iset.crops[:iset.total_crop_words], iset2.crops[:iset2.total_crop_words])
     assert torch.equal(iset.area, iset2.area) and torch.equal(iset.bbox, iset2.bbox)
