@@ -57,15 +57,16 @@ EMIA_HD void emia_mark(const EmiaMarks& m, int lx, int ly, int negative) {
 
 // Follow one outer border starting at local pixel (x0,y0).
 EMIA_HD_NOINLINE void emia_trace_outer(const EmiaBitView& v, const EmiaMarks& m, int x0, int y0, EmiaContourOut& o) {
-    const int DX[8] = {1, 1, 0, -1, -1, -1, 0, 1};
-    const int DY[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+    // 8-neighbourhood, direction s: 0=E 1=NE 2=N 3=NW 4=W 5=SW 6=S 7=SE (y grows downwards); (delta + 1) packed 4 bits each
+#define EMIA_DX(s) ((int)((0x21000122u >> (4 * (s))) & 0xFu) - 1)
+#define EMIA_DY(s) ((int)((0x22210001u >> (4 * (s))) & 0xFu) - 1)
     int s = 4;
     const int s_first_end = 4;
     int x1 = 0, y1 = 0;
     do {
         s = (s - 1) & 7;
-        x1 = x0 + DX[s];
-        y1 = y0 + DY[s];
+        x1 = x0 + EMIA_DX(s);
+        y1 = y0 + EMIA_DY(s);
     } while (!emia_view_px(v, x1, y1) && s != s_first_end);
 
     if (s == s_first_end) {  // isolated pixel
@@ -79,8 +80,8 @@ EMIA_HD_NOINLINE void emia_trace_outer(const EmiaBitView& v, const EmiaMarks& m,
         const int s_end = s;
         while (s < 15) {
             ++s;
-            x4 = x3 + DX[s & 7];
-            y4 = y3 + DY[s & 7];
+            x4 = x3 + EMIA_DX(s & 7);
+            y4 = y3 + EMIA_DY(s & 7);
             if (emia_view_px(v, x4, y4)) break;
         }
         s &= 7;

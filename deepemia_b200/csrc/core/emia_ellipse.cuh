@@ -89,6 +89,134 @@ EMIA_HD void emia_ellipse_ofs(int i, float eps, float* ox, float* oy) {
     *oy = (float)(((i & 2) - 1)) * eps;
 }
 
+// ---- fast least squares: normal equations + Cholesky + iterative refinement ---------------------------------------
+// Solves min |A x - rhs| for K unknowns from the accumulated Gram matrix G = A^T A (row-major, full) and g = A^T rhs.
+// Returns det(G) / trace(G)^K, a cheap lower bound of lambda_min / lambda_max (0 when the factorisation breaks down).
+template <int K>
+EMIA_HD double emia_chol_solve(const double* G, const double* g, double* L, double* x) {
+    double tr = 0.0;
+    for (int i = 0; i < K; ++i) tr += G[i * K + i];
+    double det = 1.0;
+    for (int j = 0; j < K; ++j) {
+        double d = G[j * K + j];
+        for (int k = 0; k < j; ++k) d -= L[j * K + k] * L[j * K + k];
+        if (!(d > 0.0)) return 0.0;
+        const double ljj = sqrt(d);
+        L[j * K + j] = ljj;
+        det *= d;
+        for (int i = j + 1; i < K; ++i) {
+            double v = G[i * K + j];
+            for (int k = 0; k < j; ++k) v -= L[i * K + k] * L[j * K + k];
+            L[i * K + j] = v / ljj;
+        }
+    }
+    // forward / backward substitution
+    double y[K];
+    for (int i = 0; i < K; ++i) {
+        double v = g[i];
+        for (int k = 0; k < i; ++k) v -= L[i * K + k] * y[k];
+        y[i] = v / L[i * K + i];
+    }
+    for (int i = K - 1; i >= 0; --i) {
+        double v = y[i];
+        for (int k = i + 1; k < K; ++k) v -= L[k * K + i] * x[k];
+        x[i] = v / L[i * K + i];
+    }
+    double trk = 1.0;
+    for (int i = 0; i < K; ++i) trk *= tr;
+    return det / trk;
+}
+template <int K>
+EMIA_HD void emia_chol_resolve(const double* L, const double* g, double* x) {
+    double y[K];
+    for (int i = 0; i < K; ++i) {
+        double v = g[i];
+        for (int k = 0; k < i; ++k) v -= L[i * K + k] * y[k];
+        y[i] = v / L[i * K + i];
+    }
+    for (int i = K - 1; i >= 0; --i) {
+        double v = y[i];
+        for (int k = i + 1; k < K; ++k) v -= L[k * K + i] * x[k];
+        x[i] = v / L[i * K + i];
+    }
+}
+
+struct EmiaEllipsePts {
+    const uint32_t* pts; int n; float cxf, cyf; double scale; int perturbed; float eps;
+};
+EMIA_HD void emia_ellipse_pt(const EmiaEllipsePts& P, int i, double* px, double* py) {
+    float fx = (float)EMIA_PT_X(P.pts[i]), fy = (float)EMIA_PT_Y(P.pts[i]);
+    if (P.perturbed) { float ox, oy; emia_ellipse_ofs(i, P.eps, &ox, &oy); fx = fx + ox; fy = fy + oy; }
+    const float dx = fx - P.cxf, dy = fy - P.cyf;
+    *px = dx * P.scale; *py = dy * P.scale;
+}
+
+// lower bound on lambda_min/lambda_max below which the fast path hands over to the rotation-based (QR + Jacobi) path
+#define EMIA_ELLIPSE_FAST_MIN_RATIO 1e-11
+
+// stage 1, fast: returns 1 and fills gfp when the system is comfortably well conditioned
+EMIA_HD int emia_ellipse_stage1_fast(const EmiaEllipsePts& P, double* gfp) {
+    double G[25], g[5], L[25];
+    for (int i = 0; i < 25; ++i) { G[i] = 0.0; L[i] = 0.0; }
+    for (int i = 0; i < 5; ++i) g[i] = 0.0;
+    for (int i = 0; i < P.n; ++i) {
+        double px, py; emia_ellipse_pt(P, i, &px, &py);
+        const double row[5] = {-px * px, -py * py, -px * py, px, py};
+        for (int a = 0; a < 5; ++a) {
+            for (int b = a; b < 5; ++b) G[a * 5 + b] += row[a] * row[b];
+            g[a] += row[a] * 10000.0;
+        }
+    }
+    for (int a = 0; a < 5; ++a) for (int b = 0; b < a; ++b) G[a * 5 + b] = G[b * 5 + a];
+    const double ratio = emia_chol_solve<5>(G, g, L, gfp);
+    if (!(ratio > EMIA_ELLIPSE_FAST_MIN_RATIO)) return 0;
+    // two steps of iterative refinement with residuals taken against the rows themselves
+    for (int it = 0; it < 2; ++it) {
+        double r5[5] = {0, 0, 0, 0, 0};
+        for (int i = 0; i < P.n; ++i) {
+            double px, py; emia_ellipse_pt(P, i, &px, &py);
+            const double row[5] = {-px * px, -py * py, -px * py, px, py};
+            double res = 10000.0;
+            for (int a = 0; a < 5; ++a) res -= row[a] * gfp[a];
+            for (int a = 0; a < 5; ++a) r5[a] += row[a] * res;
+        }
+        double dx5[5];
+        emia_chol_resolve<5>(L, r5, dx5);
+        for (int a = 0; a < 5; ++a) gfp[a] += dx5[a];
+    }
+    return 1;
+}
+EMIA_HD int emia_ellipse_stage2_fast(const EmiaEllipsePts& P, const double* rp, double* gfp) {
+    double G[9], g[3], L[9];
+    for (int i = 0; i < 9; ++i) { G[i] = 0.0; L[i] = 0.0; }
+    for (int i = 0; i < 3; ++i) g[i] = 0.0;
+    for (int i = 0; i < P.n; ++i) {
+        double px, py; emia_ellipse_pt(P, i, &px, &py);
+        const double row[3] = {(px - rp[0]) * (px - rp[0]), (py - rp[1]) * (py - rp[1]), (px - rp[0]) * (py - rp[1])};
+        for (int a = 0; a < 3; ++a) {
+            for (int b = a; b < 3; ++b) G[a * 3 + b] += row[a] * row[b];
+            g[a] += row[a];
+        }
+    }
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < a; ++b) G[a * 3 + b] = G[b * 3 + a];
+    const double ratio = emia_chol_solve<3>(G, g, L, gfp);
+    if (!(ratio > EMIA_ELLIPSE_FAST_MIN_RATIO)) return 0;
+    for (int it = 0; it < 2; ++it) {
+        double r3[3] = {0, 0, 0};
+        for (int i = 0; i < P.n; ++i) {
+            double px, py; emia_ellipse_pt(P, i, &px, &py);
+            const double row[3] = {(px - rp[0]) * (px - rp[0]), (py - rp[1]) * (py - rp[1]), (px - rp[0]) * (py - rp[1])};
+            double res = 1.0;
+            for (int a = 0; a < 3; ++a) res -= row[a] * gfp[a];
+            for (int a = 0; a < 3; ++a) r3[a] += row[a] * res;
+        }
+        double dx3[3];
+        emia_chol_resolve<3>(L, r3, dx3);
+        for (int a = 0; a < 3; ++a) gfp[a] += dx3[a];
+    }
+    return 1;
+}
+
 // General (non-"direct") fit; n >= 5 packed integer points.
 EMIA_HD_NOINLINE EmiaEllipse emia_fit_ellipse_general(const uint32_t* pts, int n) {
     EmiaEllipse box; box.cx = box.cy = box.w = box.h = box.angle = 0.f; box.ok = 0;
@@ -102,32 +230,33 @@ EMIA_HD_NOINLINE EmiaEllipse emia_fit_ellipse_general(const uint32_t* pts, int n
         const float dx = (float)EMIA_PT_X(pts[i]) - cxf, dy = (float)EMIA_PT_Y(pts[i]) - cyf;
         s += fabsf(dx) + fabsf(dy);
     }
-    const double scale = 100. / (s > FLT_EPSILON ? s : (double)FLT_EPSILON);
+    EmiaEllipsePts P;
+    P.pts = pts; P.n = n; P.cxf = cxf; P.cyf = cyf; P.perturbed = 0; P.eps = 0.f;
+    P.scale = 100. / (s > FLT_EPSILON ? s : (double)FLT_EPSILON);
+    const double scale = P.scale;
 
     double gfp[5], rp[5];
-    float eps = 0.f;
-    int perturbed = 0;
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        double R[25], qtb[5];
-        for (int i = 0; i < 25; ++i) R[i] = 0.0;
-        for (int i = 0; i < 5; ++i) qtb[i] = 0.0;
-        for (int i = 0; i < n; ++i) {
-            float fx = (float)EMIA_PT_X(pts[i]), fy = (float)EMIA_PT_Y(pts[i]);
-            if (perturbed) { float ox, oy; emia_ellipse_ofs(i, eps, &ox, &oy); fx = fx + ox; fy = fy + oy; }
-            const float dx = fx - cxf, dy = fy - cyf;
-            const double px = dx * scale, py = dy * scale;
-            double row[5] = {-px * px, -py * py, -px * py, px, py};
-            emia_givens_add_row<5>(R, qtb, row, 10000.0);
+    if (!emia_ellipse_stage1_fast(P, gfp)) {
+        // rotation-based path: row-streaming Givens QR; Jacobi singular values decide OpenCV's perturbation branch
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            double R[25], qtb[5];
+            for (int i = 0; i < 25; ++i) R[i] = 0.0;
+            for (int i = 0; i < 5; ++i) qtb[i] = 0.0;
+            for (int i = 0; i < n; ++i) {
+                double px, py; emia_ellipse_pt(P, i, &px, &py);
+                double row[5] = {-px * px, -py * py, -px * py, px, py};
+                emia_givens_add_row<5>(R, qtb, row, 10000.0);
+            }
+            double smax, smin;
+            emia_sv_extremes<5>(R, &smax, &smin);
+            if (attempt == 0 && smax * FLT_EPSILON > smin) {
+                P.eps = (float)(s / (n * 2) * 1e-3);
+                P.perturbed = 1;
+                continue;
+            }
+            emia_back_subst<5>(R, qtb, gfp);
+            break;
         }
-        double smax, smin;
-        emia_sv_extremes<5>(R, &smax, &smin);
-        if (attempt == 0 && smax * FLT_EPSILON > smin) {
-            eps = (float)(s / (n * 2) * 1e-3);
-            perturbed = 1;
-            continue;
-        }
-        emia_back_subst<5>(R, qtb, gfp);
-        break;
     }
     // conic centre
     {
@@ -137,15 +266,12 @@ EMIA_HD_NOINLINE EmiaEllipse emia_fit_ellipse_general(const uint32_t* pts, int n
         rp[1] = (a00 * gfp[4] - a01 * gfp[3]) / det;
     }
     // re-fit A', B', C' about that centre
-    {
+    if (!emia_ellipse_stage2_fast(P, rp, gfp)) {
         double R[9], qtb[3];
         for (int i = 0; i < 9; ++i) R[i] = 0.0;
         for (int i = 0; i < 3; ++i) qtb[i] = 0.0;
         for (int i = 0; i < n; ++i) {
-            float fx = (float)EMIA_PT_X(pts[i]), fy = (float)EMIA_PT_Y(pts[i]);
-            if (perturbed) { float ox, oy; emia_ellipse_ofs(i, eps, &ox, &oy); fx = fx + ox; fy = fy + oy; }
-            const float dx = fx - cxf, dy = fy - cyf;
-            const double px = dx * scale, py = dy * scale;
+            double px, py; emia_ellipse_pt(P, i, &px, &py);
             double row[3] = {(px - rp[0]) * (px - rp[0]), (py - rp[1]) * (py - rp[1]), (px - rp[0]) * (py - rp[1])};
             emia_givens_add_row<3>(R, qtb, row, 1.0);
         }

@@ -10,48 +10,58 @@ __device__ __forceinline__ EmiaBitView emia_make_view(const uint32_t* crops, con
     return v;
 }
 
-__global__ void __launch_bounds__(128) k_contour_count(const uint32_t* __restrict__ crops, const emia_inst_meta* __restrict__ meta,
-                                                       const int64_t* __restrict__ crop_off, int64_t n, uint32_t* __restrict__ marks,
-                                                       int64_t* __restrict__ n_contours, int64_t* __restrict__ n_points,
-                                                       int64_t* __restrict__ scratch_bytes) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// ---- border following: one THREAD per instance ---------------------------------------------------------------------
+#define EMIA_TRACE_THREADS 128
+
+template <bool kStore>
+__global__ void __launch_bounds__(EMIA_TRACE_THREADS) k_contour_trace(
+    const uint32_t* __restrict__ crops, const emia_inst_meta* __restrict__ meta, const int64_t* __restrict__ crop_off, int64_t n,
+    uint32_t* __restrict__ marks, int64_t* __restrict__ n_contours, int64_t* __restrict__ n_points,
+    int64_t* __restrict__ scratch_bytes, const int64_t* __restrict__ cont_off, const int64_t* __restrict__ pt_off,
+    uint32_t* __restrict__ pts, int32_t* __restrict__ cstart) {
+    const int64_t i = (int64_t)blockIdx.x * EMIA_TRACE_THREADS + threadIdx.x;
     if (i >= n) return;
     const emia_inst_meta m = meta[i];
-    if (m.ch <= 0 || m.cw <= 0) { n_contours[i] = 0; n_points[i] = 0; scratch_bytes[i] = 0; return; }
+    const int words = m.ch * m.cw;
+    if (words <= 0) {
+        if (kStore) cstart[cont_off[i] + i] = 0;
+        else { n_contours[i] = 0; n_points[i] = 0; scratch_bytes[i] = 0; }
+        return;
+    }
     const int64_t off = crop_off[i];
     const EmiaBitView v = emia_make_view(crops, m, off);
     uint32_t* mk = marks + 2 * off;
-    uint32_t* ng = mk + (size_t)m.ch * m.cw;
+    uint32_t* ng = mk + words;
     EmiaContourOut o;
-    o.pts = nullptr; o.cap_pts = 0; o.cstart = nullptr; o.cap_contours = 0; o.store = 0;
+    if (kStore) {
+        o.pts = pts + pt_off[i]; o.cap_pts = (int)(pt_off[i + 1] - pt_off[i]);
+        o.cstart = cstart + cont_off[i] + i; o.cap_contours = (int)(cont_off[i + 1] - cont_off[i]); o.store = 1;
+    } else {
+        o.pts = nullptr; o.cap_pts = 0; o.cstart = nullptr; o.cap_contours = 0; o.store = 0;
+    }
     emia_find_external_contours(v, mk, ng, o);
-    n_contours[i] = o.n_contours;
-    n_points[i] = o.n_pts;
-    scratch_bytes[i] = o.n_contours ? (int64_t)((emia_measure_scratch_bytes(o.max_len) + 15) & ~(size_t)15) : 0;
+    if (!kStore) {
+        n_contours[i] = o.n_contours;
+        n_points[i] = o.n_pts;
+        scratch_bytes[i] = o.n_contours ? (int64_t)((emia_measure_scratch_bytes(o.max_len) + 15) & ~(size_t)15) : 0;
+    }
 }
+#define EMIA_TRACE_SMEM_BYTES ((size_t)0)
 
-__global__ void __launch_bounds__(128) k_contour_measure(const uint32_t* __restrict__ crops, const emia_inst_meta* __restrict__ meta,
-                                                         const int64_t* __restrict__ crop_off, int64_t n, uint32_t* __restrict__ marks,
+// ---- morphometry: one THREAD per instance over the stored vertex lists ---------------------------------------------
+__global__ void __launch_bounds__(128) k_contour_measure(const emia_inst_meta* __restrict__ meta, int64_t n,
                                                          const int64_t* __restrict__ cont_off, const int64_t* __restrict__ pt_off,
                                                          const int64_t* __restrict__ scratch_off, double um_pix, double min_area,
-                                                         uint32_t* __restrict__ pts, int32_t* __restrict__ cstart,
+                                                         const uint32_t* __restrict__ pts, const int32_t* __restrict__ cstart,
                                                          double* __restrict__ records, int32_t* __restrict__ rec_inst,
                                                          double* __restrict__ perim0, uint8_t* __restrict__ scratch) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const emia_inst_meta m = meta[i];
     const int64_t c0 = cont_off[i];
     const int nc = (int)(cont_off[i + 1] - c0);
-    int32_t* cs = cstart + c0 + i;
-    if (nc == 0 || m.ch <= 0 || m.cw <= 0) { cs[0] = 0; perim0[i] = 0.0; return; }
-    const int64_t off = crop_off[i];
-    const EmiaBitView v = emia_make_view(crops, m, off);
-    uint32_t* mk = marks + 2 * off;
-    uint32_t* ng = mk + (size_t)m.ch * m.cw;
-    uint32_t* p = pts + pt_off[i];
-    EmiaContourOut o;
-    o.pts = p; o.cap_pts = (int)(pt_off[i + 1] - pt_off[i]); o.cstart = cs; o.cap_contours = nc; o.store = 1;
-    emia_find_external_contours(v, mk, ng, o);
+    if (nc == 0) { perim0[i] = 0.0; return; }
+    const int32_t* cs = cstart + c0 + i;
+    const uint32_t* p = pts + pt_off[i];
     void* sc = scratch + scratch_off[i];
     for (int j = 0; j < nc; ++j) {
         const int k = nc - 1 - j;                     // OpenCV returns contours in reverse discovery order
@@ -72,8 +82,9 @@ extern "C" int emia_contour_count(const uint32_t* crops, const emia_inst_meta* m
     if (n == 0) return EMIA_OK;
     if (!crops || !meta || !crop_off || !marks || !n_contours || !n_points || !scratch_bytes)
         return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_count: %s", "null pointer");
-    const unsigned grid = (unsigned)((n + 127) / 128);
-    k_contour_count<<<grid, 128, 0, (cudaStream_t)stream>>>(crops, meta, crop_off, n, marks, n_contours, n_points, scratch_bytes);
+    const unsigned grid = (unsigned)((n + EMIA_TRACE_THREADS - 1) / EMIA_TRACE_THREADS);
+    k_contour_trace<false><<<grid, EMIA_TRACE_THREADS, EMIA_TRACE_SMEM_BYTES, (cudaStream_t)stream>>>(crops, meta, crop_off, n, marks, n_contours, n_points,
+                                                                                  scratch_bytes, nullptr, nullptr, nullptr, nullptr);
     return emia_check_launch("emia_contour_count launch: %s");
 }
 
@@ -87,8 +98,11 @@ extern "C" int emia_contour_measure(const uint32_t* crops, const emia_inst_meta*
     if (!crops || !meta || !crop_off || !marks || !cont_off || !pt_off || !scratch_off || !pts || !cstart || !records ||
         !rec_inst || !perim0 || !scratch)
         return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_measure: %s", "null pointer");
+    const unsigned gridt = (unsigned)((n + EMIA_TRACE_THREADS - 1) / EMIA_TRACE_THREADS);
+    k_contour_trace<true><<<gridt, EMIA_TRACE_THREADS, EMIA_TRACE_SMEM_BYTES, (cudaStream_t)stream>>>(crops, meta, crop_off, n, marks, nullptr, nullptr, nullptr,
+                                                                                  cont_off, pt_off, pts, cstart);
     const unsigned grid = (unsigned)((n + 127) / 128);
-    k_contour_measure<<<grid, 128, 0, (cudaStream_t)stream>>>(crops, meta, crop_off, n, marks, cont_off, pt_off, scratch_off, um_pix,
-                                                              min_area, pts, cstart, records, rec_inst, perim0, scratch);
+    k_contour_measure<<<grid, 128, 0, (cudaStream_t)stream>>>(meta, n, cont_off, pt_off, scratch_off, um_pix, min_area, pts, cstart, records,
+                                                              rec_inst, perim0, scratch);
     return emia_check_launch("emia_contour_measure launch: %s");
 }

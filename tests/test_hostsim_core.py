@@ -1,0 +1,136 @@
+"""CPU: the host build of the device algorithms (deepemia_b200/csrc/core/*.cuh compiled by g++ into tests/hostsim) against
+OpenCV / torch and the reference-generated golden vectors.  These are the exact functions the sm_100a kernels execute."""
+import ctypes
+import os
+import subprocess
+
+import cv2
+import numpy as np
+import pytest
+
+from oracle import d2_paste, measure
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HS_DIR = os.path.join(HERE, "hostsim")
+HS = os.path.join(HS_DIR, "libemia_hostsim.so")
+
+
+@pytest.fixture(scope="module")
+def L():
+    srcs = [os.path.join(HS_DIR, "hostsim.cpp")] + [os.path.join(HERE, "..", "deepemia_b200", "csrc", "core", f)
+                                                    for f in os.listdir(os.path.join(HERE, "..", "deepemia_b200", "csrc", "core"))]
+    if not os.path.exists(HS) or any(os.path.getmtime(s) > os.path.getmtime(HS) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++", "hostsim.cpp", "-o", HS], cwd=HS_DIR)
+    lib = ctypes.CDLL(HS)
+    lib.sim_contour_area.restype = ctypes.c_double
+    lib.sim_arc_length.restype = ctypes.c_double
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _pack(c):
+    c = c[:, 0, :].astype(np.uint32)
+    return (c[:, 0] | (c[:, 1] << 16)).astype(np.uint32)
+
+
+def _contours(L, mask):
+    mask = np.ascontiguousarray(mask.astype(np.uint8))
+    H, W = mask.shape
+    pts = np.zeros(H * W + 16, np.uint32); cs = np.zeros(H * W // 2 + 2, np.int32); npts = ctypes.c_int()
+    n = L.sim_find_contours(_p(mask), H, W, _p(pts), len(pts), _p(cs), len(cs) - 1, ctypes.byref(npts))
+    return [pts[cs[k]:cs[k + 1]].copy() for k in range(n - 1, -1, -1)]
+
+
+def _shapes(rng, n, H=200, W=260):
+    for _ in range(n):
+        m = np.zeros((H, W), np.uint8)
+        u = rng.random()
+        if u < 0.3:
+            cv2.ellipse(m, (int(rng.integers(40, W - 40)), int(rng.integers(40, H - 40))), (int(rng.integers(1, 38)), int(rng.integers(1, 38))),
+                        float(rng.uniform(0, 180)), 0, 360, 1, -1)
+        elif u < 0.4:
+            x0, y0 = rng.integers(5, W - 60), rng.integers(5, H - 60)
+            m[y0:y0 + rng.integers(1, 50), x0:x0 + rng.integers(1, 50)] = 1
+        else:
+            k = rng.integers(3, 13); a = np.sort(rng.uniform(0, 2 * np.pi, k)); r = rng.uniform(0.5, 1, k) * rng.uniform(2, 38)
+            cx, cy = rng.integers(40, W - 40), rng.integers(40, H - 40)
+            cv2.fillPoly(m, [np.stack([cx + r * np.cos(a), cy + r * np.sin(a)], 1).astype(np.int32)], 1)
+        yield m
+
+
+def test_contours_area_perimeter_vs_opencv(L):
+    rng = np.random.default_rng(1)
+    imgs = [(rng.random((rng.integers(1, 40), rng.integers(1, 70))) < d).astype(np.uint8) for d in (0.1, 0.3, 0.5, 0.7, 0.9) for _ in range(120)]
+    imgs += list(_shapes(rng, 300))
+    for m in imgs:
+        ref = cv2.findContours(np.ascontiguousarray(m), cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)[0]
+        got = _contours(L, m)
+        assert len(ref) == len(got)
+        for r, p in zip(ref, got):
+            assert np.array_equal(_pack(r), p)
+            assert L.sim_contour_area(_p(p), len(p)) == cv2.contourArea(r)
+            assert L.sim_arc_length(_p(p), len(p)) == cv2.arcLength(r, True)
+
+
+def test_min_area_rect_and_box_points_bit_exact(L):
+    rng = np.random.default_rng(3)
+    n = 0
+    for m in _shapes(rng, 1500):
+        for c in cv2.findContours(m, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)[0]:
+            p = _pack(c); rect = np.zeros(11, np.float32); box = np.zeros(8, np.float32)
+            L.sim_min_area_rect(_p(p), len(p), 0, _p(rect), _p(box))
+            rr = cv2.minAreaRect(c)
+            assert np.array_equal(np.array([rr[0][0], rr[0][1], rr[1][0], rr[1][1], rr[2]], np.float32), rect[:5])
+            assert np.array_equal(cv2.boxPoints(rr).reshape(-1), box)
+            n += 1
+    assert n >= 1500
+
+
+def test_fit_ellipse_axes(L):
+    rng = np.random.default_rng(4)
+    tot = exact = 0
+    for m in _shapes(rng, 1500):
+        for c in cv2.findContours(m, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)[0]:
+            if len(c) < 6 or cv2.contourArea(c) < 5:     # n == 5 takes OpenCV's "direct" solver (known gap)
+                continue
+            p = _pack(c); out = np.zeros(5, np.float32)
+            L.sim_fit_ellipse(_p(p), len(p), _p(out))
+            (_, _), (w, h), _ = cv2.fitEllipse(c)
+            ref = np.array([w, h], np.float32)
+            tot += 1
+            exact += np.array_equal(ref, out[2:4])
+            np.testing.assert_allclose(out[2:4], ref, rtol=1e-5)
+    assert exact >= 0.99 * tot
+
+
+def test_measure_contour_vs_reference_golden(L):
+    g = np.load(os.path.join(HERE, "golden", "measure_golden.npz"))
+    for k in range(len(g["vals"])):
+        v = g["verts"][g["vstart"][k]:g["vstart"][k + 1]].astype(np.uint32)
+        p = (v[:, 0] | (v[:, 1] << 16)).astype(np.uint32)
+        rec = np.zeros(16)
+        L.sim_measure_contour(_p(p), len(p), ctypes.c_double(float(g["um"][k])), _p(rec))
+        np.testing.assert_allclose(rec[:12], g["vals"][k], rtol=1e-5, atol=0)
+        # integer-exact quantities
+        c = v.astype(np.int32).reshape(-1, 1, 2)
+        assert rec[12] == cv2.contourArea(c) and rec[13] == cv2.arcLength(c, True) and rec[14] == len(v)
+
+
+def test_paste_core_bit_exact_vs_torch(L):
+    rng = np.random.default_rng(0)
+    H, W = 129, 161
+    for t in range(60):
+        prob = [rng.random((28, 28)).astype(np.float32), rng.random((28, 28)).astype(np.float16).astype(np.float32),
+                (rng.integers(0, 257, (28, 28)) / 256).astype(np.float32)][t % 3]
+        x0, y0 = rng.uniform(-20, W - 5), rng.uniform(-20, H - 5)
+        box = np.array([x0, y0, x0 + rng.uniform(0.5, 90), y0 + rng.uniform(0.5, 90)], np.float32)
+        sx, sy = (1.0, 1.0) if t % 2 else (float(rng.uniform(0.5, 2)), float(rng.uniform(0.5, 2)))
+        ref, _, _, _ = d2_paste.predictor_instances(prob[None], box[None], np.array([0.9], np.float32), np.array([0]), sx, sy, H, W)
+        out = np.zeros((H, W), np.uint8); reg = np.zeros(4, np.int32)
+        v = L.sim_paste(_p(prob), _p(box), ctypes.c_float(sx), ctypes.c_float(sy), H, W, _p(out), _p(reg))
+        assert v == len(ref)
+        if v:
+            assert np.array_equal(ref[0], out.astype(bool))
