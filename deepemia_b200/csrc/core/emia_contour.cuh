@@ -55,93 +55,119 @@ EMIA_HD void emia_mark(const EmiaMarks& m, int lx, int ly, int negative) {
     if (negative) m.ng[w] |= b;
 }
 
-// Follow one outer border starting at local pixel (x0,y0).
-EMIA_HD_NOINLINE void emia_trace_outer(const EmiaBitView& v, const EmiaMarks& m, int x0, int y0, EmiaContourOut& o) {
-    // 8-neighbourhood, direction s: 0=E 1=NE 2=N 3=NW 4=W 5=SW 6=S 7=SE (y grows downwards); (delta + 1) packed 4 bits each
+// 8-neighbourhood, direction s: 0=E 1=NE 2=N 3=NW 4=W 5=SW 6=S 7=SE (y grows downwards); (delta + 1) packed 4 bits each
 #define EMIA_DX(s) ((int)((0x21000122u >> (4 * (s))) & 0xFu) - 1)
 #define EMIA_DY(s) ((int)((0x22210001u >> (4 * (s))) & 0xFu) - 1)
-    int s = 4;
-    const int s_first_end = 4;
-    int x1 = 0, y1 = 0;
-    do {
-        s = (s - 1) & 7;
-        x1 = x0 + EMIA_DX(s);
-        y1 = y0 + EMIA_DY(s);
-    } while (!emia_view_px(v, x1, y1) && s != s_first_end);
 
-    if (s == s_first_end) {  // isolated pixel
-        emia_mark(m, x0, y0, 1);
-        emia_contour_emit(o, v.x_origin + x0, v.y_origin + y0);
-        return;
-    }
-    int x3 = x0, y3 = y0, x4 = x0, y4 = y0;
-    int prev_s = s ^ 4;
-    for (;;) {
-        const int s_end = s;
-        while (s < 15) {
-            ++s;
-            x4 = x3 + EMIA_DX(s & 7);
-            y4 = y3 + EMIA_DY(s & 7);
-            if (emia_view_px(v, x4, y4)) break;
-        }
-        s &= 7;
-        if ((unsigned)(s - 1) < (unsigned)s_end) emia_mark(m, x3, y3, 1);
-        else if (!emia_marked(m, x3, y3)) emia_mark(m, x3, y3, 0);
-        if (s != prev_s) {
-            emia_contour_emit(o, v.x_origin + x3, v.y_origin + y3);
-            prev_s = s;
-        }
-        if (x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) break;
-        x3 = x4;
-        y3 = y4;
-        s = (s + 4) & 7;
-    }
+// bits of row ly at columns lx-1, lx, lx+1 (bit 0, 1, 2); anything outside the crop reads as 0
+EMIA_HD uint32_t emia_row3(const EmiaBitView& v, int lx, int ly) {
+    if ((unsigned)ly >= (unsigned)v.h) return 0u;
+    const uint32_t* row = v.bits + (size_t)ly * v.pitch_words;
+    if (lx == 0) return (row[0] << 1) & 7u;
+    const int c = (lx - 1) >> 5, sh = (lx - 1) & 31;
+    const uint32_t w0 = row[c];
+    const uint32_t w1 = (c + 1 < v.wwords) ? row[c + 1] : 0u;
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(w0, w1, sh) & 7u;
+#else
+    return (uint32_t)(((((uint64_t)w1) << 32) | w0) >> sh) & 7u;
+#endif
+}
+// 8-bit neighbour mask of local pixel (lx, ly): bit s set <=> the neighbour in direction s is foreground
+EMIA_HD uint32_t emia_nbr8(const EmiaBitView& v, int lx, int ly) {
+    const uint32_t up = emia_row3(v, lx, ly - 1), mid = emia_row3(v, lx, ly), dn = emia_row3(v, lx, ly + 1);
+    return ((mid >> 2) & 1u) | (((up >> 2) & 1u) << 1) | (((up >> 1) & 1u) << 2) | ((up & 1u) << 3) | ((mid & 1u) << 4) |
+           ((dn & 1u) << 5) | (((dn >> 1) & 1u) << 6) | (((dn >> 2) & 1u) << 7);
 }
 
-// All external contours of the crop, in discovery (raster) order.  OpenCV returns them in REVERSE discovery
-// order; consumers iterate k = n_contours-1 .. 0.  mk/ng must hold h*wwords words each (zeroed here).
+// All external contours of the crop, in discovery (raster) order.  OpenCV returns them in REVERSE discovery order;
+// consumers iterate k = n_contours-1 .. 0.  mk/ng must hold h*wwords words each (zeroed here).
+//
+// Written as ONE flat loop over a two-phase state machine (scan for the next start pixel / one border-following step)
+// so that the 32 instances of a warp share the instruction stream: a lane in the "follow" phase executes the same
+// branch-free step (3x3 neighbour mask -> rotate -> count-trailing-zeros picks the next direction) whatever the shape.
 EMIA_HD_NOINLINE void emia_find_external_contours(const EmiaBitView& v, uint32_t* mk, uint32_t* ng, EmiaContourOut& o) {
-    EmiaMarks m;
-    m.mk = mk; m.ng = ng; m.wwords = v.wwords;
-    const int nw = v.h * v.wwords;
+    const int ww = v.wwords;
+    const int nw = v.h * ww;
     for (int i = 0; i < nw; ++i) { mk[i] = 0u; ng[i] = 0u; }
     o.n_contours = 0; o.n_pts = 0; o.overflow = 0; o.max_len = 0;
     if (o.store) o.cstart[0] = 0;
-    for (int y = 0; y < v.h; ++y) {
-        const uint32_t* row = v.bits + (size_t)y * v.pitch_words;
-        for (int c = 0; c < v.wwords; ++c) {
-            uint32_t done_mask = 0u;  // bits of this word already examined
-            for (;;) {
-                // marks may have changed since the last candidate: recompute from the planes
-                const uint32_t F = row[c];
-                if (F == 0u) break;
-                const uint32_t left = (F << 1) | (c > 0 ? (row[c - 1] >> 31) : 0u);
-                uint32_t cand = F & ~left & ~mk[y * v.wwords + c] & ~done_mask;
-                if (cand == 0u) break;
-                const int b = emia_ctz(cand);
-                done_mask |= (b == 31) ? 0xFFFFFFFFu : ((2u << b) - 1u);
-                const int x = c * 32 + b;
-                // nearest marked pixel strictly left of x on this row
-                int accept = 1;
-                {
-                    int cc = c;
-                    uint32_t mw = mk[y * v.wwords + cc] & ((b == 0) ? 0u : ((1u << b) - 1u));
-                    while (mw == 0u && cc > 0) { --cc; mw = mk[y * v.wwords + cc]; }
-                    if (mw != 0u) {
-                        const int hb = emia_msb(mw);
-                        const int neg = (ng[y * v.wwords + cc] >> hb) & 1u;
-                        if (!neg) accept = 0;  // inside an already-followed outer border
-                    }
+    int y = 0, c = 0;
+    uint32_t done_mask = 0u;            // bits of the current word already examined
+    int phase = 0;                      // 0: scan, 1: follow
+    int x0 = 0, y0 = 0, x1 = 0, y1 = 0, x3 = 0, y3 = 0, s = 0, prev_s = 0, before = 0;
+    for (;;) {
+        if (phase == 0) {
+            if (y >= v.h) break;
+            const uint32_t* row = v.bits + (size_t)y * v.pitch_words;
+            const uint32_t F = row[c];
+            const uint32_t left = (F << 1) | (c > 0 ? (row[c - 1] >> 31) : 0u);
+            const uint32_t cand = F & ~left & ~mk[y * ww + c] & ~done_mask;
+            if (cand == 0u) {
+                done_mask = 0u;
+                if (++c >= ww) { c = 0; ++y; }
+                continue;
+            }
+            const int b = emia_ctz(cand);
+            done_mask |= (b == 31) ? 0xFFFFFFFFu : ((2u << b) - 1u);
+            const int x = c * 32 + b;
+            // RETR_EXTERNAL: nearest marked pixel strictly left of x on this row must carry a negative label (or not exist)
+            {
+                int cc = c;
+                uint32_t mw = mk[y * ww + cc] & ((b == 0) ? 0u : ((1u << b) - 1u));
+                while (mw == 0u && cc > 0) { --cc; mw = mk[y * ww + cc]; }
+                if (mw != 0u) {
+                    const int hb = emia_msb(mw);
+                    if (!((ng[y * ww + cc] >> hb) & 1u)) continue;   // inside an already-followed outer border
                 }
-                if (!accept) continue;
-                if (o.store && o.n_contours >= o.cap_contours) { o.overflow = 1; return; }
-                const int before = o.n_pts;
-                emia_trace_outer(v, m, x, y, o);
+            }
+            if (o.store && o.n_contours >= o.cap_contours) { o.overflow = 1; return; }
+            before = o.n_pts;
+            const uint32_t N8 = emia_nbr8(v, x, y);
+            // first neighbour clockwise from W: directions 3,2,1,0,7,6,5 -> bit k of M
+            const uint32_t M = ((N8 >> 3) & 1u) | (((N8 >> 2) & 1u) << 1) | (((N8 >> 1) & 1u) << 2) | ((N8 & 1u) << 3) |
+                               (((N8 >> 7) & 1u) << 4) | (((N8 >> 6) & 1u) << 5) | (((N8 >> 5) & 1u) << 6);
+            const int wi = y * ww + (x >> 5);
+            const uint32_t bit = 1u << (x & 31);
+            if (M == 0u) {   // isolated pixel
+                mk[wi] |= bit; ng[wi] |= bit;
+                emia_contour_emit(o, v.x_origin + x, v.y_origin + y);
                 o.n_contours++;
                 if (o.n_pts - before > o.max_len) o.max_len = o.n_pts - before;
                 if (o.store) o.cstart[o.n_contours] = o.n_pts;
                 if (o.overflow) return;
+                continue;
             }
+            s = (3 - emia_ctz(M)) & 7;
+            x0 = x; y0 = y; x1 = x + EMIA_DX(s); y1 = y + EMIA_DY(s);
+            x3 = x0; y3 = y0;
+            prev_s = s ^ 4;
+            phase = 1;
+        } else {
+            const uint32_t N8 = emia_nbr8(v, x3, y3);
+            const int s_end = s;
+            const int r = (s_end + 1) & 7;
+            const uint32_t rot = ((N8 >> r) | (N8 << (8 - r))) & 0xFFu;
+            s = (s_end + 1 + emia_ctz(rot)) & 7;                 // next foreground neighbour counter-clockwise
+            const int wi = y3 * ww + (x3 >> 5);
+            const uint32_t bit = 1u << (x3 & 31);
+            mk[wi] |= bit;                                        // label +2 ...
+            if ((unsigned)(s - 1) < (unsigned)s_end) ng[wi] |= bit;   // ... or -126 when the east neighbour was examined empty
+            if (s != prev_s) {
+                emia_contour_emit(o, v.x_origin + x3, v.y_origin + y3);
+                prev_s = s;
+            }
+            const int x4 = x3 + EMIA_DX(s), y4 = y3 + EMIA_DY(s);
+            if (x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) {
+                o.n_contours++;
+                if (o.n_pts - before > o.max_len) o.max_len = o.n_pts - before;
+                if (o.store) o.cstart[o.n_contours] = o.n_pts;
+                if (o.overflow) return;
+                phase = 0;
+                continue;
+            }
+            x3 = x4; y3 = y4;
+            s = (s + 4) & 7;
         }
     }
 }
