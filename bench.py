@@ -167,6 +167,7 @@ def main():
     ap.add_argument("--arena-gb", type=float, default=32.0)
     ap.add_argument("--ref-tiles", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="extra untimed pass with per-stage CUDA events (stderr)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -239,6 +240,15 @@ def main():
     barrier()
     launches = engine.LAUNCHES["count"] - l0
     ms_total = ev[0].elapsed_time(ev[1])
+    if args.breakdown and rank == 0:
+        engine.STAGE_TIMING["enabled"] = True
+        t0 = time.perf_counter()
+        step(d_probs, d_boxes, d_scores, d_classes)
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        engine.STAGE_TIMING["enabled"] = False
+        summ = engine.stage_summary()
+        print(json.dumps({"stage_ms": summ, "sum_ms": sum(summ.values()), "wall_ms": wall}), file=sys.stderr)
     # ---------------- end-to-end (host buffers) ----------------
     def e2e_step():
         p = h_probs.to(dev, non_blocking=True); b = h_boxes.to(dev, non_blocking=True)

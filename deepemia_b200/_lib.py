@@ -17,7 +17,8 @@ class EmiaError(RuntimeError):
 _SIGNATURES = {
     "emia_version": (c_int, []),
     "emia_last_error": (ctypes.c_char_p, []),
-    "emia_exclusive_scan_i64": (c_int, [c_void_p, c_int64, c_void_p]),
+    "emia_scan_workspace_bytes": (c_size_t, [c_int64]),
+    "emia_exclusive_scan_i64": (c_int, [c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
     "emia_paste_plan": (c_int, [c_void_p, c_int64, c_float, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "emia_paste_threshold_bitpack": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_int, c_int,
                                              c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
@@ -27,6 +28,11 @@ _SIGNATURES = {
     "emia_contour_count": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "emia_contour_measure": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
                                      c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "emia_contour_trace_plan": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "emia_contour_trace_slab": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p]),
+    "emia_contour_measure_stored": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_double, c_double,
+                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "emia_group_workspace_bytes": (c_size_t, [c_void_p, c_int]),
     "emia_dedup_smart": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_int, c_int, c_void_p, c_void_p, c_double, c_double, c_void_p, c_void_p, c_void_p,

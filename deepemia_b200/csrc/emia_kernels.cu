@@ -38,10 +38,77 @@ extern "C" int emia_version(void) { return 100; }
 extern "C" const char* emia_last_error(void) { return g_err; }
 
 // =================================================================================================
-// exclusive scan (int64), single CTA, three phases.  n is at most a few million and the kernel moves
-// 16 B per element: a single 1024-thread CTA finishes in tens of microseconds.
+// exclusive scan (int64): reduce-then-scan over 4096-element tiles.  Up to 1024 tiles (4 M elements) take three
+// launches (tile sums -> scan of the sums in one CTA -> per-tile scan + offset) with the tile sums in a caller workspace
+// (emia_scan_workspace_bytes); larger inputs, or no workspace, fall back to a single CTA that walks the array.
 // =================================================================================================
-__global__ void __launch_bounds__(1024) k_exclusive_scan_i64(int64_t* data, int64_t n) {
+#define EMIA_SCAN_THREADS 512
+#define EMIA_SCAN_ITEMS 8
+#define EMIA_SCAN_TILE (EMIA_SCAN_THREADS * EMIA_SCAN_ITEMS)
+#define EMIA_SCAN_MAX_TILES 1024
+
+__device__ __forceinline__ int64_t emia_block_exclusive_scan(int64_t v, int64_t* s_warp, int64_t* total) {
+    // exclusive scan of one value per thread across the CTA (EMIA_SCAN_THREADS threads)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int64_t inc = v;
+    for (int off = 1; off < 32; off <<= 1) {
+        const int64_t t = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int64_t w = (lane < EMIA_SCAN_THREADS / 32) ? s_warp[lane] : 0;
+        for (int off = 1; off < 32; off <<= 1) {
+            const int64_t t = __shfl_up_sync(0xffffffffu, w, off);
+            if (lane >= off) w += t;
+        }
+        if (lane < EMIA_SCAN_THREADS / 32) s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int64_t base = warp ? s_warp[warp - 1] : 0;
+    *total = s_warp[EMIA_SCAN_THREADS / 32 - 1];
+    __syncthreads();
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(EMIA_SCAN_THREADS) k_scan_tile_sums(const int64_t* __restrict__ data, int64_t n, int64_t* __restrict__ sums) {
+    __shared__ int64_t s_warp[EMIA_SCAN_THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * EMIA_SCAN_TILE;
+    int64_t v = 0;
+    for (int k = 0; k < EMIA_SCAN_ITEMS; ++k) {
+        const int64_t i = base + (int64_t)k * EMIA_SCAN_THREADS + threadIdx.x;
+        if (i < n) v += data[i];
+    }
+    int64_t total;
+    emia_block_exclusive_scan(v, s_warp, &total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(EMIA_SCAN_THREADS) k_scan_sums(int64_t* __restrict__ sums, int ntiles, int64_t* __restrict__ total_out) {
+    __shared__ int64_t s_warp[EMIA_SCAN_THREADS / 32];
+    // ntiles <= 1024 = 2 per thread
+    const int i0 = threadIdx.x * 2, i1 = i0 + 1;
+    const int64_t a = i0 < ntiles ? sums[i0] : 0, b = i1 < ntiles ? sums[i1] : 0;
+    int64_t total;
+    const int64_t ex = emia_block_exclusive_scan(a + b, s_warp, &total);
+    if (i0 < ntiles) sums[i0] = ex;
+    if (i1 < ntiles) sums[i1] = ex + a;
+    if (threadIdx.x == 0) *total_out = total;
+}
+__global__ void __launch_bounds__(EMIA_SCAN_THREADS) k_scan_apply(int64_t* __restrict__ data, int64_t n, const int64_t* __restrict__ sums) {
+    __shared__ int64_t s_warp[EMIA_SCAN_THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * EMIA_SCAN_TILE + (int64_t)threadIdx.x * EMIA_SCAN_ITEMS;
+    int64_t v[EMIA_SCAN_ITEMS];
+    int64_t t = 0;
+    for (int k = 0; k < EMIA_SCAN_ITEMS; ++k) { v[k] = (base + k < n) ? data[base + k] : 0; t += v[k]; }
+    int64_t total;
+    int64_t run = emia_block_exclusive_scan(t, s_warp, &total) + sums[blockIdx.x];
+    for (int k = 0; k < EMIA_SCAN_ITEMS; ++k) {
+        if (base + k < n) data[base + k] = run;
+        run += v[k];
+    }
+}
+__global__ void __launch_bounds__(1024) k_exclusive_scan_i64_serial(int64_t* data, int64_t n) {
     __shared__ int64_t part[1024];
     const int t = threadIdx.x;
     const int64_t chunk = (n + 1023) / 1024;
@@ -51,7 +118,6 @@ __global__ void __launch_bounds__(1024) k_exclusive_scan_i64(int64_t* data, int6
     for (int64_t i = lo; i < hi; ++i) s += data[i];
     part[t] = s;
     __syncthreads();
-    // Hillis-Steele inclusive scan of the 1024 partials
     for (int off = 1; off < 1024; off <<= 1) {
         int64_t v = (t >= off) ? part[t - off] : 0;
         __syncthreads();
@@ -67,9 +133,23 @@ __global__ void __launch_bounds__(1024) k_exclusive_scan_i64(int64_t* data, int6
     if (t == 1023) data[n] = part[1023];
 }
 
-extern "C" int emia_exclusive_scan_i64(int64_t* data, int64_t n, void* stream) {
+extern "C" size_t emia_scan_workspace_bytes(int64_t n) {
+    (void)n;
+    return (size_t)EMIA_SCAN_MAX_TILES * sizeof(int64_t);
+}
+
+extern "C" int emia_exclusive_scan_i64(int64_t* data, int64_t n, void* workspace, size_t workspace_bytes, void* stream) {
     if (!data || n < 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_exclusive_scan_i64: %s", "bad argument");
-    k_exclusive_scan_i64<<<1, 1024, 0, (cudaStream_t)stream>>>(data, n);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t ntiles = (n + EMIA_SCAN_TILE - 1) / EMIA_SCAN_TILE;
+    if (ntiles == 0 || ntiles > EMIA_SCAN_MAX_TILES || !workspace || workspace_bytes < (size_t)ntiles * sizeof(int64_t)) {
+        k_exclusive_scan_i64_serial<<<1, 1024, 0, st>>>(data, n);
+        return emia_check_launch("emia_exclusive_scan_i64 launch: %s");
+    }
+    int64_t* sums = (int64_t*)workspace;
+    k_scan_tile_sums<<<(unsigned)ntiles, EMIA_SCAN_THREADS, 0, st>>>(data, n, sums);
+    k_scan_sums<<<1, EMIA_SCAN_THREADS, 0, st>>>(sums, (int)ntiles, data + n);
+    k_scan_apply<<<(unsigned)ntiles, EMIA_SCAN_THREADS, 0, st>>>(data, n, sums);
     return emia_check_launch("emia_exclusive_scan_i64 launch: %s");
 }
 

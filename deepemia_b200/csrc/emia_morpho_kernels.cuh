@@ -53,14 +53,15 @@ __global__ void __launch_bounds__(128) k_contour_measure(const emia_inst_meta* _
                                                          const int64_t* __restrict__ cont_off, const int64_t* __restrict__ pt_off,
                                                          const int64_t* __restrict__ scratch_off, double um_pix, double min_area,
                                                          const uint32_t* __restrict__ pts, const int32_t* __restrict__ cstart,
-                                                         double* __restrict__ records, int32_t* __restrict__ rec_inst,
-                                                         double* __restrict__ perim0, uint8_t* __restrict__ scratch) {
+                                                         int cstart_stride, double* __restrict__ records,
+                                                         int32_t* __restrict__ rec_inst, double* __restrict__ perim0,
+                                                         uint8_t* __restrict__ scratch) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int64_t c0 = cont_off[i];
     const int nc = (int)(cont_off[i + 1] - c0);
     if (nc == 0) { perim0[i] = 0.0; return; }
-    const int32_t* cs = cstart + c0 + i;
+    const int32_t* cs = cstart_stride > 0 ? cstart + (size_t)i * cstart_stride : cstart + c0 + i;
     const uint32_t* p = pts + pt_off[i];
     void* sc = scratch + scratch_off[i];
     for (int j = 0; j < nc; ++j) {
@@ -102,7 +103,77 @@ extern "C" int emia_contour_measure(const uint32_t* crops, const emia_inst_meta*
     k_contour_trace<true><<<gridt, EMIA_TRACE_THREADS, EMIA_TRACE_SMEM_BYTES, (cudaStream_t)stream>>>(crops, meta, crop_off, n, marks, nullptr, nullptr, nullptr,
                                                                                   cont_off, pt_off, pts, cstart);
     const unsigned grid = (unsigned)((n + 127) / 128);
-    k_contour_measure<<<grid, 128, 0, (cudaStream_t)stream>>>(meta, n, cont_off, pt_off, scratch_off, um_pix, min_area, pts, cstart, records,
+    k_contour_measure<<<grid, 128, 0, (cudaStream_t)stream>>>(meta, n, cont_off, pt_off, scratch_off, um_pix, min_area, pts, cstart, 0, records,
                                                               rec_inst, perim0, scratch);
     return emia_check_launch("emia_contour_measure launch: %s");
+}
+
+
+// ---- single-pass variant: vertices go to per-instance slabs of bounded capacity -------------------------------------
+// cap_pts(i) = 4 * (ch + 32 * cw) + 32 (a blob's border is about 2 * (h + w) pixels); cstart slab of capc + 1 entries.
+// Instances that exceed either capacity raise *overflow; the caller then re-runs the exact two-pass path.
+__global__ void k_trace_caps(const emia_inst_meta* __restrict__ meta, int64_t n, int64_t* __restrict__ cap) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const emia_inst_meta m = meta[i];
+    cap[i] = (m.ch > 0 && m.cw > 0) ? (int64_t)(4 * (m.ch + 32 * m.cw) + 32) : 0;
+}
+
+__global__ void __launch_bounds__(EMIA_TRACE_THREADS) k_contour_trace_slab(
+    const uint32_t* __restrict__ crops, const emia_inst_meta* __restrict__ meta, const int64_t* __restrict__ crop_off, int64_t n,
+    uint32_t* __restrict__ marks, const int64_t* __restrict__ pt_cap_off, int capc, uint32_t* __restrict__ pts,
+    int32_t* __restrict__ cstart_slab, int64_t* __restrict__ n_contours, int64_t* __restrict__ scratch_bytes,
+    int32_t* __restrict__ overflow) {
+    const int64_t i = (int64_t)blockIdx.x * EMIA_TRACE_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const emia_inst_meta m = meta[i];
+    const int words = m.ch * m.cw;
+    int32_t* cs = cstart_slab + (size_t)i * (capc + 1);
+    if (words <= 0) { cs[0] = 0; n_contours[i] = 0; scratch_bytes[i] = 0; return; }
+    const int64_t off = crop_off[i];
+    const EmiaBitView v = emia_make_view(crops, m, off);
+    uint32_t* mk = marks + 2 * off;
+    uint32_t* ng = mk + words;
+    EmiaContourOut o;
+    o.pts = pts + pt_cap_off[i]; o.cap_pts = (int)(pt_cap_off[i + 1] - pt_cap_off[i]);
+    o.cstart = cs; o.cap_contours = capc; o.store = 1;
+    emia_find_external_contours(v, mk, ng, o);
+    if (o.overflow) { atomicAdd(overflow, 1); n_contours[i] = 0; scratch_bytes[i] = 0; return; }
+    n_contours[i] = o.n_contours;
+    scratch_bytes[i] = o.n_contours ? (int64_t)((emia_measure_scratch_bytes(o.max_len) + 15) & ~(size_t)15) : 0;
+}
+
+extern "C" int emia_contour_trace_plan(const emia_inst_meta* meta, int64_t n, int64_t* pt_cap, void* stream) {
+    if (n < 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_trace_plan: %s", "bad n");
+    if (n == 0) return EMIA_OK;
+    if (!meta || !pt_cap) return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_trace_plan: %s", "null pointer");
+    k_trace_caps<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(meta, n, pt_cap);
+    return emia_check_launch("emia_contour_trace_plan launch: %s");
+}
+
+extern "C" int emia_contour_trace_slab(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n,
+                                       uint32_t* marks, const int64_t* pt_cap_off, int32_t cap_contours, uint32_t* pts,
+                                       int32_t* cstart_slab, int64_t* n_contours, int64_t* scratch_bytes, int32_t* overflow,
+                                       void* stream) {
+    if (n < 0 || cap_contours < 1) return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_trace_slab: %s", "bad argument");
+    if (n == 0) return EMIA_OK;
+    if (!crops || !meta || !crop_off || !marks || !pt_cap_off || !pts || !cstart_slab || !n_contours || !scratch_bytes || !overflow)
+        return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_trace_slab: %s", "null pointer");
+    const unsigned grid = (unsigned)((n + EMIA_TRACE_THREADS - 1) / EMIA_TRACE_THREADS);
+    k_contour_trace_slab<<<grid, EMIA_TRACE_THREADS, 0, (cudaStream_t)stream>>>(crops, meta, crop_off, n, marks, pt_cap_off, cap_contours, pts,
+                                                                             cstart_slab, n_contours, scratch_bytes, overflow);
+    return emia_check_launch("emia_contour_trace_slab launch: %s");
+}
+
+extern "C" int emia_contour_measure_stored(const emia_inst_meta* meta, int64_t n, const int64_t* cont_off, const int64_t* pt_off,
+                                           const int32_t* cstart, int32_t cstart_stride, const int64_t* scratch_off, double um_pix,
+                                           double min_area, const uint32_t* pts, double* records, int32_t* rec_inst, double* perim0,
+                                           uint8_t* scratch, void* stream) {
+    if (n < 0 || cstart_stride < 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_measure_stored: %s", "bad argument");
+    if (n == 0) return EMIA_OK;
+    if (!meta || !cont_off || !pt_off || !cstart || !scratch_off || !pts || !records || !rec_inst || !perim0 || !scratch)
+        return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_measure_stored: %s", "null pointer");
+    k_contour_measure<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(meta, n, cont_off, pt_off, scratch_off, um_pix, min_area, pts,
+                                                                                  cstart, cstart_stride, records, rec_inst, perim0, scratch);
+    return emia_check_launch("emia_contour_measure_stored launch: %s");
 }

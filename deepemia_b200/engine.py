@@ -17,6 +17,33 @@ REC_FIELDS = 16
  REC_SPHER, REC_AREA, REC_PERIM, REC_NVERT, REC_MEASURED) = range(16)
 
 LAUNCHES = {"count": 0}   # kernels launched through the ABI (bench.py reports it as gpu_launches)
+STAGE_TIMING = {"enabled": False, "events": []}   # (name, start, end) CUDA events when enabled (bench.py --breakdown)
+
+
+class _stage:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if STAGE_TIMING["enabled"]:
+            self.a = torch.cuda.Event(enable_timing=True); self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if STAGE_TIMING["enabled"]:
+            self.b.record()
+            STAGE_TIMING["events"].append((self.name, self.a, self.b))
+        return False
+
+
+def stage_summary():
+    torch.cuda.synchronize()
+    out = {}
+    for name, a, b in STAGE_TIMING["events"]:
+        out.setdefault(name, []).append(a.elapsed_time(b))
+    STAGE_TIMING["events"].clear()
+    return {k: float(np.mean(v)) for k, v in out.items()}
 
 
 def _ptr(t):
@@ -41,8 +68,11 @@ def pitch_words_for(W):
 def exclusive_scan_(t):
     """In-place exclusive scan of t[0:n] with the total in t[n] (int64, n+1 entries)."""
     lib = _lib.load()
-    _lib.check(lib.emia_exclusive_scan_i64(_ptr(t), t.numel() - 1, _stream()), "emia_exclusive_scan_i64")
-    LAUNCHES["count"] += 1
+    n = t.numel() - 1
+    nb = int(lib.emia_scan_workspace_bytes(n))
+    ws = torch.empty(nb, dtype=torch.uint8, device=t.device)
+    _lib.check(lib.emia_exclusive_scan_i64(_ptr(t), n, _ptr(ws), nb, _stream()), "emia_exclusive_scan_i64")
+    LAUNCHES["count"] += 3
     return t
 
 
@@ -70,6 +100,7 @@ class InstanceSet:
     rec_inst: Optional[torch.Tensor] = None
     perim0: Optional[torch.Tensor] = None
     n_records: int = 0
+    cstart_stride: int = 0        # 0: packed cstart (cont_off[i] + i); else ints per instance slab
     extra: dict = field(default_factory=dict)
 
     @property
@@ -92,8 +123,9 @@ def paste(probs, boxes, H, W, scores=None, classes=None, scale_x=1.0, scale_y=1.
     meta = torch.empty((n, 8), dtype=torch.int32, device=dev)
     crop_off = torch.empty(n + 1, dtype=torch.int64, device=dev)
     st = _stream()
-    _lib.check(lib.emia_paste_plan(_ptr(boxes), n, scale_x, scale_y, H, W, _ptr(meta), _ptr(crop_off), st), "emia_paste_plan")
-    exclusive_scan_(crop_off)
+    with _stage("paste_plan+scan"):
+        _lib.check(lib.emia_paste_plan(_ptr(boxes), n, scale_x, scale_y, H, W, _ptr(meta), _ptr(crop_off), st), "emia_paste_plan")
+        exclusive_scan_(crop_off)
     LAUNCHES["count"] += 1
     total = int(crop_off[n].item()) if n else 0
     if crops_out is not None:
@@ -109,9 +141,10 @@ def paste(probs, boxes, H, W, scores=None, classes=None, scale_x=1.0, scale_y=1.
     slots = int(frames.shape[0]) if frames is not None else 1
     if frames is not None:
         assert frames.shape[1] == H and frames.shape[2] == pw and frames.is_contiguous()
-    _lib.check(lib.emia_paste_threshold_bitpack(_ptr(probs), _ptr(boxes), _ptr(meta), _ptr(crop_off), n, scale_x, scale_y, H, W,
-                                                _ptr(frames), slots, pw, _ptr(crops), _ptr(bbox), _ptr(area), variant, st),
-               "emia_paste_threshold_bitpack")
+    with _stage("k1_paste"):
+        _lib.check(lib.emia_paste_threshold_bitpack(_ptr(probs), _ptr(boxes), _ptr(meta), _ptr(crop_off), n, scale_x, scale_y, H, W,
+                                                    _ptr(frames), slots, pw, _ptr(crops), _ptr(bbox), _ptr(area), variant, st),
+                   "emia_paste_threshold_bitpack")
     LAUNCHES["count"] += 1
     return InstanceSet(n=n, H=H, W=W, meta=meta, crop_off=crop_off, crops=crops, bbox=bbox, area=area, scores=scores,
                        classes=classes, frames=frames, total_crop_words=total)
@@ -157,8 +190,13 @@ def unpack_masks(iset, idx=None):
     return out
 
 
-def measure(iset, um_pix=1.0, min_area=None):
-    """K5: external contours + morphometry records for every instance of the set (results stay on the device)."""
+CAP_CONTOURS = 8   # contours per instance held by the single-pass slab layout
+
+
+def measure(iset, um_pix=1.0, min_area=None, single_pass=True):
+    """K5: external contours + morphometry records for every instance of the set (results stay on the device).
+    single_pass: follow the borders once into bounded per-instance slabs; any overflow falls back to the exact
+    count -> scan -> store path."""
     lib = _lib.load()
     dev = iset.device
     n = iset.n
@@ -166,30 +204,89 @@ def measure(iset, um_pix=1.0, min_area=None):
         min_area = max(5, iset.H * iset.W * 0.000005 * 0.05)     # src/functions/inference.py:1178-1184
     st = _stream()
     marks = torch.empty(max(2 * iset.total_crop_words, 1), dtype=torch.int32, device=dev)
-    sizes = torch.empty((3, n + 1), dtype=torch.int64, device=dev)
-    _lib.check(lib.emia_contour_count(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), n, _ptr(marks), _ptr(sizes[0]),
-                                      _ptr(sizes[1]), _ptr(sizes[2]), st), "emia_contour_count")
-    for r in range(3):
-        exclusive_scan_(sizes[r])
-    LAUNCHES["count"] += 1
-    totals = sizes[:, n].tolist() if n else [0, 0, 0]
-    n_rec, n_pts, n_scr = int(totals[0]), int(totals[1]), int(totals[2])
-    pts = torch.empty(max(n_pts, 1), dtype=torch.int32, device=dev)
-    cstart = torch.empty(n_rec + n + 1, dtype=torch.int32, device=dev)
-    records = torch.empty((max(n_rec, 1), REC_FIELDS), dtype=torch.float64, device=dev)
-    rec_inst = torch.empty(max(n_rec, 1), dtype=torch.int32, device=dev)
     perim0 = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
-    scratch = torch.empty(max(n_scr, 16), dtype=torch.uint8, device=dev)
-    _lib.check(lib.emia_contour_measure(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), n, _ptr(marks), _ptr(sizes[0]),
-                                        _ptr(sizes[1]), _ptr(sizes[2]), float(um_pix), float(min_area), _ptr(pts), _ptr(cstart),
-                                        _ptr(records), _ptr(rec_inst), _ptr(perim0), _ptr(scratch), st), "emia_contour_measure")
-    LAUNCHES["count"] += 1
+    done = False
+    if single_pass and n:
+        sizes = torch.empty((3, n + 1), dtype=torch.int64, device=dev)     # rows: n_contours, pt capacity, scratch bytes
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        with _stage("k5_plan+scan"):
+            _lib.check(lib.emia_contour_trace_plan(_ptr(iset.meta), n, _ptr(sizes[1]), st), "emia_contour_trace_plan")
+            exclusive_scan_(sizes[1])
+        cap_total = iset.extra.get("pt_cap_total")
+        if cap_total is None:
+            # capacity is a pure function of the crop sizes: 4 * (sum ch + 32 * sum cw) + 32 * n_live; read it once
+            cap_total = int(sizes[1, n].item())
+        pts = torch.empty(max(cap_total, 1), dtype=torch.int32, device=dev)
+        cstart = torch.empty(n * (CAP_CONTOURS + 1) + 1, dtype=torch.int32, device=dev)
+        with _stage("k5_trace"):
+            _lib.check(lib.emia_contour_trace_slab(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), n, _ptr(marks), _ptr(sizes[1]),
+                                                   CAP_CONTOURS, _ptr(pts), _ptr(cstart), _ptr(sizes[0]), _ptr(sizes[2]), _ptr(flag),
+                                                   st), "emia_contour_trace_slab")
+        with _stage("k5_scans"):
+            exclusive_scan_(sizes[0])
+            exclusive_scan_(sizes[2])
+        LAUNCHES["count"] += 2
+        tot = torch.stack([sizes[0, n], sizes[2, n], flag[0].to(torch.int64)]).tolist()
+        n_rec, n_scr, overflow = int(tot[0]), int(tot[1]), int(tot[2])
+        if overflow == 0:
+            records = torch.empty((max(n_rec, 1), REC_FIELDS), dtype=torch.float64, device=dev)
+            rec_inst = torch.empty(max(n_rec, 1), dtype=torch.int32, device=dev)
+            scratch = torch.empty(max(n_scr, 16), dtype=torch.uint8, device=dev)
+            with _stage("k5_measure"):
+                _lib.check(lib.emia_contour_measure_stored(_ptr(iset.meta), n, _ptr(sizes[0]), _ptr(sizes[1]), _ptr(cstart),
+                                                           CAP_CONTOURS + 1, _ptr(sizes[2]), float(um_pix), float(min_area), _ptr(pts),
+                                                           _ptr(records), _ptr(rec_inst), _ptr(perim0), _ptr(scratch), st),
+                           "emia_contour_measure_stored")
+            LAUNCHES["count"] += 1
+            iset.cstart_stride = CAP_CONTOURS + 1
+            done = True
+    if not done:
+        sizes = torch.empty((3, n + 1), dtype=torch.int64, device=dev)     # rows: n_contours, n_points, scratch bytes
+        with _stage("k5_count"):
+            _lib.check(lib.emia_contour_count(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), n, _ptr(marks), _ptr(sizes[0]),
+                                              _ptr(sizes[1]), _ptr(sizes[2]), st), "emia_contour_count")
+        with _stage("k5_scans"):
+            for r in range(3):
+                exclusive_scan_(sizes[r])
+        LAUNCHES["count"] += 1
+        totals = sizes[:, n].tolist() if n else [0, 0, 0]
+        n_rec, n_pts, n_scr = int(totals[0]), int(totals[1]), int(totals[2])
+        pts = torch.empty(max(n_pts, 1), dtype=torch.int32, device=dev)
+        cstart = torch.empty(n_rec + n + 1, dtype=torch.int32, device=dev)
+        records = torch.empty((max(n_rec, 1), REC_FIELDS), dtype=torch.float64, device=dev)
+        rec_inst = torch.empty(max(n_rec, 1), dtype=torch.int32, device=dev)
+        scratch = torch.empty(max(n_scr, 16), dtype=torch.uint8, device=dev)
+        with _stage("k5_trace+measure"):
+            _lib.check(lib.emia_contour_measure(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), n, _ptr(marks), _ptr(sizes[0]),
+                                                _ptr(sizes[1]), _ptr(sizes[2]), float(um_pix), float(min_area), _ptr(pts), _ptr(cstart),
+                                                _ptr(records), _ptr(rec_inst), _ptr(perim0), _ptr(scratch), st), "emia_contour_measure")
+        LAUNCHES["count"] += 2
+        iset.cstart_stride = 0
     iset.cont_off, iset.pt_off = sizes[0], sizes[1]
     iset.pts, iset.cstart, iset.records, iset.rec_inst, iset.perim0 = pts, cstart, records[:n_rec], rec_inst[:n_rec], perim0
     iset.n_records = n_rec
     iset.extra["um_pix"] = um_pix
     iset.extra["min_area"] = min_area
+    iset.extra.pop("n_contours", None)
     return iset
+
+
+def contours_to_host(iset):
+    """Host copy of the contour vertex lists: list (per instance) of lists (OpenCV order) of int32 [k,2] arrays."""
+    pts = iset.pts.cpu().numpy().view(np.uint32)
+    cont_off = iset.cont_off.cpu().numpy(); pt_off = iset.pt_off.cpu().numpy(); cstart = iset.cstart.cpu().numpy()
+    out = []
+    for i in range(iset.n):
+        nc = int(cont_off[i + 1] - cont_off[i])
+        base = i * iset.cstart_stride if iset.cstart_stride else cont_off[i] + i
+        cs = cstart[base: base + nc + 1]
+        cl = []
+        for j in range(nc):
+            k = nc - 1 - j
+            p = pts[pt_off[i] + cs[k]: pt_off[i] + cs[k + 1]]
+            cl.append(np.stack([p & 0xFFFF, p >> 16], 1).astype(np.int32))
+        out.append(cl)
+    return out
 
 
 @dataclass
@@ -262,7 +359,8 @@ def dedup_smart(iset, groups, iou_threshold=0.4, max_aspect_ratio=None):
     if ncont is None:
         ncont = (iset.cont_off[1:] - iset.cont_off[:-1]).contiguous()
         iset.extra["n_contours"] = ncont
-    _lib.check(lib.emia_dedup_smart(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), _ptr(iset.bbox), _ptr(iset.area),
+    with _stage("k4_dedup_smart"):
+      _lib.check(lib.emia_dedup_smart(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), _ptr(iset.bbox), _ptr(iset.area),
                                     _ptr(iset.perim0), _ptr(ncont), _ptr(iset.scores), _ptr(iset.classes), _ptr(groups.cap_off),
                                     groups.G, groups.total_cap, _ptr(groups.length), _ptr(groups.idx), float(iou_threshold),
                                     float(max_aspect_ratio) if max_aspect_ratio else 0.0, _ptr(out.length), _ptr(out.idx),
@@ -303,7 +401,8 @@ def overlap_rules(iset, groups, rules):
     act_t, mi_t = torch.as_tensor(active, device=dev), torch.as_tensor(max_iou, device=dev)
     ws, nb = _workspace(groups, dev)
     out = _new_groups_like(groups)
-    _lib.check(lib.emia_overlap_rules(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), _ptr(iset.bbox), _ptr(iset.area),
+    with _stage("k4_overlap_rules"):
+      _lib.check(lib.emia_overlap_rules(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), _ptr(iset.bbox), _ptr(iset.area),
                                       _ptr(iset.scores), _ptr(iset.classes), _ptr(groups.cap_off), groups.G, groups.total_cap,
                                       _ptr(groups.length), _ptr(groups.idx), _ptr(act_t), _ptr(mi_t), ncls, _ptr(out.length),
                                       _ptr(out.idx), _ptr(ws), nb, _stream()), "emia_overlap_rules")
@@ -320,7 +419,8 @@ def containment_rules(iset, groups, rules, threshold=0.95):
     parent = np.asarray([int(p) for p in rules.values()], np.int32)
     ws, nb = _workspace(groups, iset.device)
     out = _new_groups_like(groups)
-    _lib.check(lib.emia_containment_rules(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), _ptr(iset.bbox), _ptr(iset.area),
+    with _stage("k4_containment"):
+      _lib.check(lib.emia_containment_rules(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), _ptr(iset.bbox), _ptr(iset.area),
                                           _ptr(iset.classes), _ptr(groups.cap_off), groups.G, groups.total_cap, _ptr(groups.length),
                                           _ptr(groups.idx), child.ctypes.data, parent.ctypes.data, len(child), float(threshold),
                                           _ptr(out.length), _ptr(out.idx), _ptr(ws), nb, _stream()), "emia_containment_rules")

@@ -60,8 +60,10 @@ int emia_version(void);
 const char* emia_last_error(void);
 
 /* ---- utilities ------------------------------------------------------------------------------------------- */
-/* in-place exclusive prefix sum of data[0..n) with the total stored at data[n] (n+1 entries). */
-int emia_exclusive_scan_i64(int64_t* data, int64_t n, void* stream);
+/* in-place exclusive prefix sum of data[0..n) with the total stored at data[n] (n+1 entries).
+ * workspace: emia_scan_workspace_bytes(n) bytes (may be NULL: slower single-CTA path). */
+size_t emia_scan_workspace_bytes(int64_t n);
+int emia_exclusive_scan_i64(int64_t* data, int64_t n, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- K1: paste + threshold + bit-pack ----------------------------------------------------------------------
  * Replaces Detectron2 0.6 detector_postprocess + paste_masks_in_image(threshold 0.5) reached through
@@ -109,6 +111,21 @@ int emia_contour_measure(const uint32_t* crops, const emia_inst_meta* meta, cons
                          const int64_t* scratch_off, double um_pix, double min_area, uint32_t* pts,
                          int32_t* cstart, double* records, int32_t* rec_inst, double* perim0, uint8_t* scratch,
                          void* stream);
+
+/* Single-pass variant (the fast path of engine.measure): emia_contour_trace_plan gives per-instance vertex capacities
+ * (caller scans them into pt_cap_off), emia_contour_trace_slab follows the borders once into those slabs
+ * (cstart_slab: cap_contours + 1 ints per instance) and raises *overflow (caller-zeroed counter) when a capacity is
+ * exceeded — the caller then falls back to emia_contour_count / emia_contour_measure; emia_contour_measure_stored
+ * computes the records from stored vertices (cstart_stride = cap_contours + 1 for slabs, 0 for the packed layout). */
+int emia_contour_trace_plan(const emia_inst_meta* meta, int64_t n, int64_t* pt_cap, void* stream);
+int emia_contour_trace_slab(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n,
+                            uint32_t* marks, const int64_t* pt_cap_off, int32_t cap_contours, uint32_t* pts,
+                            int32_t* cstart_slab, int64_t* n_contours, int64_t* scratch_bytes, int32_t* overflow,
+                            void* stream);
+int emia_contour_measure_stored(const emia_inst_meta* meta, int64_t n, const int64_t* cont_off, const int64_t* pt_off,
+                                const int32_t* cstart, int32_t cstart_stride, const int64_t* scratch_off, double um_pix,
+                                double min_area, const uint32_t* pts, double* records, int32_t* rec_inst, double* perim0,
+                                uint8_t* scratch, void* stream);
 
 /* ---- K4: mask-IoU de-duplication and spatial constraints ----------------------------------------------------
  * All operate on G groups at once; see "Instance layout".  total_cap = cap_off[G] (the host knows it).

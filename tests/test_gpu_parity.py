@@ -61,6 +61,16 @@ def test_paste_matches_detectron2_oracle(cuda_device, variant, shape):
             k += 1
 
 
+def test_exclusive_scan(cuda_device):
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 5, 4096, 4097, 100_003, 1_022_339, 4_300_000):
+        a = rng.integers(0, 1000, n + 1).astype(np.int64)
+        t = torch.as_tensor(a, device=cuda_device)
+        engine.exclusive_scan_(t)
+        ref = np.concatenate([[0], np.cumsum(a[:n])])
+        assert np.array_equal(t.cpu().numpy(), ref), n
+
+
 def test_paste_frame_ring_and_crops_only(cuda_device):
     H, W = 256, 256
     probs, boxes, _, _ = _heads(3, 40, H, W, rmin=5, rmax=20, margin=10)
@@ -97,7 +107,8 @@ def _check_records(iset, masks, classes, H, W, um):
     return exact, len(rows)
 
 
-def test_contours_and_measurements_match_opencv(cuda_device):
+@pytest.mark.parametrize("single_pass", [True, False])
+def test_contours_and_measurements_match_opencv(cuda_device, single_pass):
     import cv2
     H, W = 512, 640
     rng = np.random.default_rng(1000)
@@ -119,22 +130,17 @@ def test_contours_and_measurements_match_opencv(cuda_device):
     classes = [0] * len(masks)
     t = torch.as_tensor(np.stack(masks), device=cuda_device)
     iset = engine.from_masks(t)
-    engine.measure(iset, um_pix=0.5)
+    engine.measure(iset, um_pix=0.5, single_pass=single_pass)
     torch.cuda.synchronize()
     # contour vertices, exact
-    pts = iset.pts.cpu().numpy().view(np.uint32)
-    cont_off = iset.cont_off.cpu().numpy(); pt_off = iset.pt_off.cpu().numpy(); cstart = iset.cstart.cpu().numpy()
+    cont_off = iset.cont_off.cpu().numpy()
     rec = iset.records.cpu().numpy()
+    got = engine.contours_to_host(iset)
     for i, mk in enumerate(masks):
         ref = cv2.findContours((mk > 0).astype(np.uint8) * 255, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)[0]
-        nc = int(cont_off[i + 1] - cont_off[i])
-        assert nc == len(ref), f"instance {i}: {nc} contours vs {len(ref)}"
-        cs = cstart[cont_off[i] + i: cont_off[i] + i + nc + 1]
+        assert len(got[i]) == len(ref), f"instance {i}: {len(got[i])} contours vs {len(ref)}"
         for j, c in enumerate(ref):
-            k = nc - 1 - j
-            p = pts[pt_off[i] + cs[k]: pt_off[i] + cs[k + 1]]
-            xy = np.stack([p & 0xFFFF, p >> 16], 1).astype(np.int32)
-            assert np.array_equal(xy, c[:, 0, :]), f"instance {i} contour {j}"
+            assert np.array_equal(got[i][j], c[:, 0, :]), f"instance {i} contour {j}"
             r = rec[cont_off[i] + j]
             assert r[engine.REC_AREA] == cv2.contourArea(c) and r[engine.REC_PERIM] == cv2.arcLength(c, True)
             assert r[engine.REC_NVERT] == len(c)
@@ -142,6 +148,22 @@ def test_contours_and_measurements_match_opencv(cuda_device):
     assert exact >= 0.95 * total, f"only {exact}/{total} rows bit-exact"
     ar = iset.area.cpu().numpy()
     assert np.array_equal(ar, np.array([int(mk.sum()) for mk in masks]))
+
+
+def test_single_pass_overflow_falls_back(cuda_device):
+    """Noise masks exceed the slab capacities (contours per instance, vertices): the exact two-pass path must take over."""
+    import cv2
+    rng = np.random.default_rng(9)
+    masks = [(rng.random((96, 96)) < 0.45).astype(np.uint8) for _ in range(6)] + [np.zeros((96, 96), np.uint8)]
+    iset = engine.from_masks(torch.as_tensor(np.stack(masks), device=cuda_device))
+    engine.measure(iset, um_pix=1.0)
+    assert iset.cstart_stride == 0      # fell back
+    got = engine.contours_to_host(iset)
+    for i, mk in enumerate(masks):
+        ref = cv2.findContours(mk * 255, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)[0]
+        assert len(got[i]) == len(ref)
+        for a, b in zip(got[i], ref):
+            assert np.array_equal(a, b[:, 0, :])
 
 
 def _mask_lists(seed, n, H, W, dup=0.5):
