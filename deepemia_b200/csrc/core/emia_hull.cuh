@@ -93,10 +93,13 @@ EMIA_HD int emia_sklansky(const uint64_t* arr, int start, int end, int* stack, i
 // Convex hull of n packed integer points (counter-clockwise flag as cv2.convexHull(clockwise=...)).
 // keys: scratch n; stack: scratch n+2; hull: out, original point indices (capacity n); tmp: scratch n.
 // Returns hull size.
-EMIA_HD_NOINLINE int emia_convex_hull(const uint32_t* pts, int n, int clockwise, uint64_t* keys, int* stack, int* hull, int* tmp) {
+// presorted != 0: keys[] already holds the n keys in ascending order (sorted by a cooperative kernel beforehand).
+EMIA_HD_NOINLINE int emia_convex_hull(const uint32_t* pts, int n, int clockwise, uint64_t* keys, int* stack, int* hull, int* tmp, int presorted = 0) {
     if (n == 0) return 0;
-    for (int i = 0; i < n; ++i) keys[i] = EMIA_KEY(EMIA_PT_X(pts[i]), EMIA_PT_Y(pts[i]), i);
-    emia_sort_keys(keys, n);
+    if (!presorted) {
+        for (int i = 0; i < n; ++i) keys[i] = EMIA_KEY(EMIA_PT_X(pts[i]), EMIA_PT_Y(pts[i]), i);
+        emia_sort_keys(keys, n);
+    }
     int miny_ind = 0, maxy_ind = 0;
     for (int i = 1; i < n; ++i) {
         const int y = EMIA_KEY_Y(keys[i]);

@@ -3,6 +3,7 @@
 // (-fmad=false: no implicit FMA contraction; see core/emia_common.cuh).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "../../include/emia.h"
 #include "core/emia_common.cuh"
