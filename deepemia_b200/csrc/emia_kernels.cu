@@ -518,3 +518,4 @@ extern "C" int emia_paste_threshold_bitpack(const float* probs, const float* box
 #include "emia_masks.cuh"
 #include "emia_morpho_kernels.cuh"
 #include "emia_group_kernels.cuh"
+#include "emia_morph_kernels.cuh"

@@ -1,0 +1,406 @@
+// emia_morph_kernels.cuh — K2: bit-packed mask clean-up morphology (part of emia_kernels.cu).
+//
+// Replaces (reference): scipy.ndimage.binary_fill_holes + skimage erosion/dilation (3x3 cross; skimage 0.19.3 =
+// scipy grey_erosion/grey_dilation, mode 'reflect' => out-of-frame neighbours are ignored) + skimage.measure.label as used by
+//   postprocess_masks            src/utils/mask_utils.py:70-84     fill -> dilate -> erode -> first-come overlap removal -> >1 component => zero
+//   process_masks_parallel       src/functions/inference.py:189-203 fill -> erode -> dilate
+//   postprocess_masks_universal  src/functions/inference.py:1778-1806 fill -> erode [-> dilate], keep if sum >= min size
+//
+// One warp per instance.  The crop is copied into a padded plane (one extra row above/below, one extra WORD left/right)
+// in a global workspace; lanes own rows.  All operators are word-parallel shifts / AND / OR; fill-holes and the
+// connected-component test are flood fills iterated to a fixed point (row-local run flooding by carry propagation, so the
+// iteration count is the number of direction changes of the longest path, not its length).
+#pragma once
+
+struct EmiaPad {
+    uint32_t* p;      // (ch + 2) x (cw + 2) words
+    int rows, words;  // padded sizes
+};
+__device__ __forceinline__ uint32_t& emia_pad_at(const EmiaPad& P, int pr, int pc) { return P.p[pr * P.words + pc]; }
+
+// bit mask of the pixels of padded word pc that lie inside the frame columns [0, W)
+__device__ __forceinline__ uint32_t emia_valid_cols(int wc0, int pc, int W) {
+    const int x0 = (wc0 + pc - 1) * 32;
+    if (x0 + 32 <= 0 || x0 >= W) return 0u;
+    uint32_t m = 0xffffffffu;
+    if (x0 < 0) m = 0u;   // cannot happen partially: x0 is a multiple of 32
+    if (x0 + 32 > W) m &= (W - x0 >= 32) ? 0xffffffffu : ((1u << (W - x0)) - 1u);
+    return m;
+}
+// flood the seed bits s through the set bits of m inside one word, both directions (carry propagation)
+__device__ __forceinline__ uint32_t emia_flood_word(uint32_t s, uint32_t m) {
+    s &= m;
+    // smear along runs of m: 5 doubling steps each way
+    uint32_t r = s;
+    uint32_t mm = m;
+    r |= (r << 1) & mm; mm &= mm << 1;
+    r |= (r << 2) & mm; mm &= mm << 2;
+    r |= (r << 4) & mm; mm &= mm << 4;
+    r |= (r << 8) & mm; mm &= mm << 8;
+    r |= (r << 16) & mm;
+    mm = m;
+    r |= (r >> 1) & mm; mm &= mm >> 1;
+    r |= (r >> 2) & mm; mm &= mm >> 2;
+    r |= (r >> 4) & mm; mm &= mm >> 4;
+    r |= (r >> 8) & mm; mm &= mm >> 8;
+    r |= (r >> 16) & mm;
+    return r;
+}
+
+// R <- flood of seeds (already in R) through ALLOWED, 4- or 8-connected, to a fixed point.  Lanes own rows.
+__device__ void emia_flood(const EmiaPad& R, const EmiaPad& ALLOWED, int conn8, int lane) {
+    for (;;) {
+        bool changed = false;
+        for (int pr = lane; pr < R.rows; pr += 32) {
+            for (int pass = 0; pass < 2; ++pass) {
+                for (int k = 0; k < R.words; ++k) {
+                    const int pc = pass ? (R.words - 1 - k) : k;
+                    const uint32_t allow = emia_pad_at(ALLOWED, pr, pc);
+                    if (!allow) continue;
+                    uint32_t cur = emia_pad_at(R, pr, pc);
+                    uint32_t in = cur;
+                    // from the rows above / below (previous sweep's values: Jacobi between rows, fine for a fixed point)
+                    for (int d = -1; d <= 1; d += 2) {
+                        const int qr = pr + d;
+                        if (qr < 0 || qr >= R.rows) continue;
+                        uint32_t v = emia_pad_at(R, qr, pc);
+                        if (conn8) {
+                            uint32_t l = v << 1, r = v >> 1;
+                            if (pc > 0) l |= emia_pad_at(R, qr, pc - 1) >> 31;
+                            if (pc + 1 < R.words) r |= emia_pad_at(R, qr, pc + 1) << 31;
+                            v |= l | r;
+                        }
+                        in |= v;
+                    }
+                    // from the neighbouring words of this row
+                    if (pc > 0) in |= emia_pad_at(R, pr, pc - 1) >> 31;
+                    if (pc + 1 < R.words) in |= emia_pad_at(R, pr, pc + 1) << 31;
+                    const uint32_t nv = emia_flood_word(in & allow, allow) | cur;
+                    if (nv != cur) { emia_pad_at(R, pr, pc) = nv; changed = true; }
+                }
+            }
+        }
+        __syncwarp();
+        if (!__any_sync(0xffffffffu, changed)) break;
+    }
+}
+
+// dst <- erosion / dilation of src with the 3x3 cross.  Out-of-frame neighbours are ignored; out-of-crop (in-frame) ones are 0.
+__device__ void emia_cross_op(const EmiaPad& dst, const EmiaPad& src, int dilate, int ry0, int wc0, int H, int W, int lane) {
+    for (int pr = lane; pr < src.rows; pr += 32) {
+        const int y = ry0 + pr - 1;
+        const bool row_ok = (y >= 0 && y < H);
+        for (int pc = 0; pc < src.words; ++pc) {
+            const uint32_t vc = emia_valid_cols(wc0, pc, W);
+            uint32_t out = 0u;
+            if (row_ok && vc) {
+                const uint32_t c = emia_pad_at(src, pr, pc);
+                uint32_t l = c << 1, r = c >> 1;
+                if (pc > 0) l |= emia_pad_at(src, pr, pc - 1) >> 31;
+                if (pc + 1 < src.words) r |= emia_pad_at(src, pr, pc + 1) << 31;
+                uint32_t u = (pr > 0) ? emia_pad_at(src, pr - 1, pc) : 0u;
+                uint32_t d = (pr + 1 < src.rows) ? emia_pad_at(src, pr + 1, pc) : 0u;
+                // validity of the neighbours
+                const uint32_t vl = (vc << 1) | ((pc > 0 ? emia_valid_cols(wc0, pc - 1, W) : 0u) >> 31);
+                const uint32_t vr = (vc >> 1) | ((pc + 1 < src.words ? emia_valid_cols(wc0, pc + 1, W) : ((wc0 + pc) * 32 < W ? 0xffffffffu : 0u)) << 31);
+                const bool up_ok = (y - 1 >= 0), dn_ok = (y + 1 < H);
+                if (dilate) {
+                    out = c | (l & vl) | (r & vr) | (up_ok ? u : 0u) | (dn_ok ? d : 0u);
+                } else {
+                    out = c & (l | ~vl) & (r | ~vr) & (up_ok ? u : 0xffffffffu) & (dn_ok ? d : 0xffffffffu);
+                }
+                out &= vc;
+            }
+            emia_pad_at(dst, pr, pc) = out;
+        }
+    }
+    __syncwarp();
+}
+
+// ops: up to 4 operator codes.  out crops have the input geometry; area_out/keep are optional.
+__global__ void __launch_bounds__(32) k_morph(const uint32_t* __restrict__ crops, const emia_inst_meta* __restrict__ meta,
+                                              const int64_t* __restrict__ crop_off, int64_t n, int H, int W, int op0, int op1, int op2,
+                                              int op3, const int64_t* __restrict__ pad_off, uint32_t* __restrict__ work,
+                                              uint32_t* __restrict__ crops_out) {
+    const int lane = threadIdx.x;
+    const int64_t inst = blockIdx.x;
+    if (inst >= n) return;
+    const emia_inst_meta m = meta[inst];
+    if (m.ch <= 0 || m.cw <= 0) return;
+    const int rows = m.ch + 2, words = m.cw + 2;
+    const int plane = rows * words;
+    uint32_t* base = work + 3 * pad_off[inst];
+    EmiaPad A{base, rows, words}, B{base + plane, rows, words}, C{base + 2 * plane, rows, words};
+    const uint32_t* crop = crops + crop_off[inst];
+    for (int k = lane; k < plane; k += 32) {
+        const int pr = k / words, pc = k - pr * words;
+        uint32_t v = 0u;
+        if (pr >= 1 && pr <= m.ch && pc >= 1 && pc <= m.cw) v = crop[(size_t)(pr - 1) * m.cw + (pc - 1)];
+        A.p[k] = v;
+    }
+    __syncwarp();
+    const int ops[4] = {op0, op1, op2, op3};
+    EmiaPad cur = A, other = B;
+    for (int o = 0; o < 4; ++o) {
+        const int op = ops[o];
+        if (op == 0) break;
+        if (op == EMIA_MORPH_FILL) {
+            // background reachable from the padded border (4-connected) ; holes = the rest of the background
+            for (int k = lane; k < plane; k += 32) {
+                const int pr = k / words, pc = k - pr * words;
+                const bool ring = (pr == 0 || pr == rows - 1 || pc == 0 || pc == words - 1);
+                C.p[k] = ~cur.p[k];                       // allowed = background
+                other.p[k] = ring ? ~cur.p[k] : 0u;       // seeds
+            }
+            __syncwarp();
+            emia_flood(other, C, 0, lane);
+            for (int k = lane; k < plane; k += 32) {
+                const int pr = k / words, pc = k - pr * words;
+                const bool inner = (pr >= 1 && pr <= m.ch && pc >= 1 && pc <= m.cw);
+                other.p[k] = inner ? ~other.p[k] : 0u;    // mask | holes = everything the flood did not reach
+            }
+            __syncwarp();
+        } else {
+            emia_cross_op(other, cur, op == EMIA_MORPH_DILATE, m.ry0, m.wc0, H, W, lane);
+        }
+        EmiaPad t = cur; cur = other; other = t;
+    }
+    uint32_t* out = crops_out + crop_off[inst];
+    for (int k = lane; k < m.ch * m.cw; k += 32) {
+        const int r = k / m.cw, c = k - r * m.cw;
+        out[k] = emia_pad_at(cur, r + 1, c + 1);
+    }
+}
+
+// first-come overlap removal + "more than one 8-connected component => zero" (postprocess_masks tail), one warp per instance
+__global__ void __launch_bounds__(32) k_overlap_first_come(const uint32_t* __restrict__ crops, const emia_inst_meta* __restrict__ meta,
+                                                           const int64_t* __restrict__ crop_off, const int32_t* __restrict__ bbox,
+                                                           const int32_t* __restrict__ cap_off, int G, const int32_t* __restrict__ in_len,
+                                                           const int32_t* __restrict__ in_idx, const int64_t* __restrict__ pad_off,
+                                                           uint32_t* __restrict__ work, uint32_t* __restrict__ crops_out) {
+    const int lane = threadIdx.x;
+    const int s = blockIdx.x;                       // list slot
+    int lo = 0, hi = G;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (cap_off[mid] <= s) lo = mid; else hi = mid; }
+    const int g = lo, base = cap_off[g];
+    if (s - base >= in_len[g]) return;
+    const int inst = in_idx[s];
+    const emia_inst_meta m = meta[inst];
+    if (m.ch <= 0 || m.cw <= 0) return;
+    const int rows = m.ch + 2, words = m.cw + 2, plane = rows * words;
+    uint32_t* wb = work + 3 * pad_off[inst];
+    EmiaPad A{wb, rows, words}, R{wb + plane, rows, words};
+    const uint32_t* crop = crops + crop_off[inst];
+    for (int k = lane; k < plane; k += 32) {
+        const int pr = k / words, pc = k - pr * words;
+        uint32_t v = 0u;
+        if (pr >= 1 && pr <= m.ch && pc >= 1 && pc <= m.cw) v = crop[(size_t)(pr - 1) * m.cw + (pc - 1)];
+        A.p[k] = v; R.p[k] = 0u;
+    }
+    __syncwarp();
+    // remove what earlier list members cover
+    const int* bi = bbox + 4 * inst;
+    for (int k = 0; k < s - base; ++k) {
+        const int j = in_idx[base + k];
+        const int* bj = bbox + 4 * j;
+        if (!emia_bbox_overlap(bi, bj)) continue;
+        const emia_inst_meta mj = meta[j];
+        const uint32_t* cj = crops + crop_off[j];
+        const int r0 = max(m.ry0, mj.ry0), r1 = min(m.ry0 + m.ch, mj.ry0 + mj.ch);
+        const int c0 = max(m.wc0, mj.wc0), c1 = min(m.wc0 + m.cw, mj.wc0 + mj.cw);
+        const int nw = (r1 - r0) * (c1 - c0);
+        for (int t = lane; t < nw; t += 32) {
+            const int r = r0 + t / (c1 - c0), c = c0 + t % (c1 - c0);
+            emia_pad_at(A, r - m.ry0 + 1, c - m.wc0 + 1) &= ~cj[(size_t)(r - mj.ry0) * mj.cw + (c - mj.wc0)];
+        }
+        __syncwarp();
+    }
+    // seed = first set pixel in raster order
+    int first = 0x7fffffff;
+    for (int k = lane; k < plane; k += 32) if (A.p[k]) { first = k; break; }
+    for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+    bool multi = false;
+    if (first != 0x7fffffff) {
+        if (lane == 0) R.p[first] = A.p[first] & (0u - A.p[first]);   // lowest set bit
+        __syncwarp();
+        emia_flood(R, A, 1, lane);
+        bool diff = false;
+        for (int k = lane; k < plane; k += 32) diff |= (R.p[k] != A.p[k]);
+        multi = __any_sync(0xffffffffu, diff);
+    }
+    uint32_t* out = crops_out + crop_off[inst];
+    for (int k = lane; k < m.ch * m.cw; k += 32) {
+        const int r = k / m.cw, c = k - r * m.cw;
+        out[k] = multi ? 0u : emia_pad_at(A, r + 1, c + 1);
+    }
+}
+
+// bbox + area of bit-packed crops (after morphology), one warp per instance
+__global__ void __launch_bounds__(32) k_crop_stats(const uint32_t* __restrict__ crops, const emia_inst_meta* __restrict__ meta,
+                                                   const int64_t* __restrict__ crop_off, int64_t n, int32_t* __restrict__ bbox,
+                                                   int32_t* __restrict__ area) {
+    const int lane = threadIdx.x;
+    const int64_t inst = blockIdx.x;
+    if (inst >= n) return;
+    const emia_inst_meta m = meta[inst];
+    const uint32_t* crop = crops + crop_off[inst];
+    int a = 0, ymin = 0x7fffffff, xmin = 0x7fffffff, ymax = -1, xmax = -1;
+    for (int k = lane; k < m.ch * m.cw; k += 32) {
+        const uint32_t w = crop[k];
+        if (!w) continue;
+        const int r = k / m.cw, c = k - r * m.cw;
+        a += __popc(w);
+        ymin = min(ymin, m.ry0 + r); ymax = max(ymax, m.ry0 + r);
+        xmin = min(xmin, (m.wc0 + c) * 32 + (__ffs((int)w) - 1));
+        xmax = max(xmax, (m.wc0 + c) * 32 + (31 - __clz((int)w)));
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o)); xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+        ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o)); xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+    }
+    if (lane == 0) {
+        area[inst] = a;
+        ((int4*)bbox)[inst] = a > 0 ? make_int4(ymin, xmin, ymax, xmax) : make_int4(-1, -1, -1, -1);
+    }
+}
+
+// padded plane sizes (words) per instance, for the caller's scan
+__global__ void k_morph_plan(const emia_inst_meta* __restrict__ meta, int64_t n, int64_t* __restrict__ pad_words) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const emia_inst_meta m = meta[i];
+    pad_words[i] = (m.ch > 0 && m.cw > 0) ? (int64_t)(m.ch + 2) * (m.cw + 2) : 0;
+}
+
+extern "C" int emia_morph_plan(const emia_inst_meta* meta, int64_t n, int64_t* pad_words, void* stream) {
+    if (n < 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_morph_plan: %s", "bad n");
+    if (n == 0) return EMIA_OK;
+    if (!meta || !pad_words) return emia_fail(EMIA_ERR_BAD_ARG, "emia_morph_plan: %s", "null pointer");
+    k_morph_plan<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(meta, n, pad_words);
+    return emia_check_launch("emia_morph_plan launch: %s");
+}
+extern "C" int emia_morph(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n, int H, int W,
+                          const int32_t* ops_host, int32_t n_ops, const int64_t* pad_off, uint32_t* work, uint32_t* crops_out,
+                          void* stream) {
+    if (n < 0 || n_ops < 1 || n_ops > 4 || !ops_host) return emia_fail(EMIA_ERR_BAD_ARG, "emia_morph: %s", "bad argument");
+    if (n == 0) return EMIA_OK;
+    if (!crops || !meta || !crop_off || !pad_off || !work || !crops_out) return emia_fail(EMIA_ERR_BAD_ARG, "emia_morph: %s", "null pointer");
+    int ops[4] = {0, 0, 0, 0};
+    for (int i = 0; i < n_ops; ++i) {
+        if (ops_host[i] < 1 || ops_host[i] > 3) return emia_fail(EMIA_ERR_BAD_ARG, "emia_morph: %s", "unknown operator");
+        ops[i] = ops_host[i];
+    }
+    k_morph<<<(unsigned)n, 32, 0, (cudaStream_t)stream>>>(crops, meta, crop_off, n, H, W, ops[0], ops[1], ops[2], ops[3], pad_off, work, crops_out);
+    return emia_check_launch("emia_morph launch: %s");
+}
+extern "C" int emia_overlap_first_come(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, const int32_t* bbox,
+                                       const int32_t* cap_off, int32_t G, int32_t total_cap, const int32_t* in_len,
+                                       const int32_t* in_idx, const int64_t* pad_off, uint32_t* work, uint32_t* crops_out,
+                                       void* stream) {
+    if (G < 0 || total_cap < 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_overlap_first_come: %s", "bad argument");
+    if (G == 0 || total_cap == 0) return EMIA_OK;
+    if (!crops || !meta || !crop_off || !bbox || !cap_off || !in_len || !in_idx || !pad_off || !work || !crops_out)
+        return emia_fail(EMIA_ERR_BAD_ARG, "emia_overlap_first_come: %s", "null pointer");
+    k_overlap_first_come<<<(unsigned)total_cap, 32, 0, (cudaStream_t)stream>>>(crops, meta, crop_off, bbox, cap_off, G, in_len, in_idx, pad_off,
+                                                                            work, crops_out);
+    return emia_check_launch("emia_overlap_first_come launch: %s");
+}
+extern "C" int emia_crop_stats(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n, int32_t* bbox,
+                               int32_t* area, void* stream) {
+    if (n < 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_crop_stats: %s", "bad n");
+    if (n == 0) return EMIA_OK;
+    if (!crops || !meta || !crop_off || !bbox || !area) return emia_fail(EMIA_ERR_BAD_ARG, "emia_crop_stats: %s", "null pointer");
+    k_crop_stats<<<(unsigned)n, 32, 0, (cudaStream_t)stream>>>(crops, meta, crop_off, n, bbox, area);
+    return emia_check_launch("emia_crop_stats launch: %s");
+}
+
+// list members with area >= min_area, in list order (postprocess_masks_universal's `np.sum(final) >= min_crys_size`), one warp per group
+__global__ void k_group_filter_area(const int32_t* __restrict__ cap_off, int G, const int32_t* __restrict__ in_len,
+                                    const int32_t* __restrict__ in_idx, const int32_t* __restrict__ area, int min_area,
+                                    int32_t* __restrict__ out_len, int32_t* __restrict__ out_idx) {
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (g >= G) return;
+    const int base = cap_off[g], len = in_len[g];
+    int run = 0;
+    for (int k0 = 0; k0 < len; k0 += 32) {
+        const int k = k0 + lane;
+        const int inst = (k < len) ? in_idx[base + k] : 0;
+        const int keep = (k < len) && area[inst] >= min_area;
+        const unsigned b = __ballot_sync(0xffffffffu, keep);
+        if (keep) out_idx[base + run + __popc(b & ((1u << lane) - 1u))] = inst;
+        run += __popc(b);
+    }
+    if (lane == 0) out_len[g] = run;
+}
+
+// postprocess_masks' column gate (mask_utils.py:62-68): np.sum(masks, axis=(0,1)) is a vector over the W frame
+// columns; K = number of columns whose total exceeds min_size; if K < len the list is truncated to its first K members
+// (K == 0 => empty list).  One CTA per group, column totals in shared memory.
+__global__ void __launch_bounds__(256) k_column_gate(const uint32_t* __restrict__ crops, const emia_inst_meta* __restrict__ meta,
+                                                     const int64_t* __restrict__ crop_off, const int32_t* __restrict__ cap_off,
+                                                     const int32_t* __restrict__ in_len, const int32_t* __restrict__ in_idx, int W,
+                                                     int min_size, int32_t* __restrict__ out_len, int32_t* __restrict__ out_idx) {
+    extern __shared__ int s_col[];
+    __shared__ int s_cnt;
+    const int g = blockIdx.x;
+    const int base = cap_off[g], len = in_len[g];
+    for (int x = threadIdx.x; x < W; x += blockDim.x) s_col[x] = 0;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int k = warp; k < len; k += nwarps) {
+        const int inst = in_idx[base + k];
+        const emia_inst_meta m = meta[inst];
+        const uint32_t* crop = crops + crop_off[inst];
+        // lanes own word columns; the per-bit column totals of one word column are accumulated over the rows first
+        for (int c = lane; c < m.cw; c += 32) {
+            for (int b0 = 0; b0 < 32; b0 += 8) {
+                int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                for (int r = 0; r < m.ch; ++r) {
+                    const uint32_t w = crop[(size_t)r * m.cw + c] >> b0;
+                    for (int j = 0; j < 8; ++j) cnt[j] += (w >> j) & 1u;
+                }
+                for (int j = 0; j < 8; ++j) {
+                    const int x = (m.wc0 + c) * 32 + b0 + j;
+                    if (cnt[j] && x < W) atomicAdd(&s_col[x], cnt[j]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    int mine = 0;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) mine += (s_col[x] > min_size);
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if (lane == 0 && mine) atomicAdd(&s_cnt, mine);
+    __syncthreads();
+    const int K = s_cnt;
+    const int nl = (K < len) ? K : len;
+    for (int k = threadIdx.x; k < nl; k += blockDim.x) out_idx[base + k] = in_idx[base + k];
+    if (threadIdx.x == 0) out_len[g] = nl;
+}
+
+extern "C" int emia_group_filter_area(const int32_t* cap_off, int32_t G, const int32_t* in_len, const int32_t* in_idx,
+                                      const int32_t* area, int32_t min_area, int32_t* out_len, int32_t* out_idx, void* stream) {
+    if (G < 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_group_filter_area: %s", "bad G");
+    if (G == 0) return EMIA_OK;
+    if (!cap_off || !in_len || !in_idx || !area || !out_len || !out_idx)
+        return emia_fail(EMIA_ERR_BAD_ARG, "emia_group_filter_area: %s", "null pointer");
+    k_group_filter_area<<<(unsigned)(((size_t)G * 32 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(cap_off, G, in_len, in_idx, area,
+                                                                                                   min_area, out_len, out_idx);
+    return emia_check_launch("emia_group_filter_area launch: %s");
+}
+extern "C" int emia_column_gate(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, const int32_t* cap_off,
+                                int32_t G, const int32_t* in_len, const int32_t* in_idx, int W, int32_t min_size,
+                                int32_t* out_len, int32_t* out_idx, void* stream) {
+    if (G < 0 || W <= 0 || W > 49152) return emia_fail(EMIA_ERR_BAD_ARG, "emia_column_gate: %s", "bad argument (W <= 49152)");
+    if (G == 0) return EMIA_OK;
+    if (!crops || !meta || !crop_off || !cap_off || !in_len || !in_idx || !out_len || !out_idx)
+        return emia_fail(EMIA_ERR_BAD_ARG, "emia_column_gate: %s", "null pointer");
+    const size_t smem = (size_t)W * 4;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_column_gate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_column_gate<<<(unsigned)G, 256, smem, (cudaStream_t)stream>>>(crops, meta, crop_off, cap_off, in_len, in_idx, W, min_size,
+                                                                   out_len, out_idx);
+    return emia_check_launch("emia_column_gate launch: %s");
+}

@@ -190,6 +190,112 @@ def unpack_masks(iset, idx=None):
     return out
 
 
+MORPH_FILL, MORPH_ERODE, MORPH_DILATE = 1, 2, 3
+
+
+def _pad_plan(iset):
+    """Padded-plane offsets ((ch+2) x (cw+2) words per instance) and the 3-plane work buffer of the K2 kernels."""
+    cached = iset.extra.get("pad_plan")
+    if cached is not None:
+        return cached
+    lib = _lib.load()
+    pad_off = torch.empty(iset.n + 1, dtype=torch.int64, device=iset.device)
+    _lib.check(lib.emia_morph_plan(_ptr(iset.meta), iset.n, _ptr(pad_off), _stream()), "emia_morph_plan")
+    exclusive_scan_(pad_off)
+    LAUNCHES["count"] += 1
+    total = int(pad_off[iset.n].item()) if iset.n else 0
+    work = torch.empty(max(3 * total, 1), dtype=torch.int32, device=iset.device)
+    iset.extra["pad_plan"] = (pad_off, work)
+    return pad_off, work
+
+
+def _derived(iset, crops):
+    """A new InstanceSet with the geometry (meta, crop_off) of `iset` and new crop bits; bbox/area recomputed."""
+    lib = _lib.load()
+    bbox = torch.empty_like(iset.bbox)
+    area = torch.empty_like(iset.area)
+    _lib.check(lib.emia_crop_stats(_ptr(crops), _ptr(iset.meta), _ptr(iset.crop_off), iset.n, _ptr(bbox), _ptr(area), _stream()),
+               "emia_crop_stats")
+    LAUNCHES["count"] += 1
+    out = InstanceSet(n=iset.n, H=iset.H, W=iset.W, meta=iset.meta, crop_off=iset.crop_off, crops=crops, bbox=bbox, area=area,
+                      scores=iset.scores, classes=iset.classes, total_crop_words=iset.total_crop_words)
+    if "pad_plan" in iset.extra:
+        out.extra["pad_plan"] = iset.extra["pad_plan"]
+    return out
+
+
+def morph(iset, ops):
+    """K2: apply `ops` (MORPH_FILL / MORPH_ERODE / MORPH_DILATE, 3x3 cross, at most 4) to every instance.  The result has
+    the geometry of the input (every chain the reference uses — closing, opening, erosion — stays inside the crop)."""
+    lib = _lib.load()
+    ops = np.ascontiguousarray(ops, dtype=np.int32)
+    pad_off, work = _pad_plan(iset)
+    crops = torch.empty_like(iset.crops)
+    if iset.n:
+        with _stage("k2_morph"):
+            _lib.check(lib.emia_morph(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), iset.n, iset.H, iset.W, ops.ctypes.data,
+                                      len(ops), _ptr(pad_off), _ptr(work), _ptr(crops), _stream()), "emia_morph")
+        LAUNCHES["count"] += 1
+    return _derived(iset, crops)
+
+
+def overlap_first_come(iset, groups):
+    """Tail of postprocess_masks (src/utils/mask_utils.py:77-82): list member k loses the pixels earlier members cover, then is
+    zeroed if it has more than one 8-connected component.  Members keep their list position (Q6)."""
+    lib = _lib.load()
+    pad_off, work = _pad_plan(iset)
+    crops = iset.crops.clone()
+    if iset.n and groups.total_cap:
+        with _stage("k2_overlap_first_come"):
+            _lib.check(lib.emia_overlap_first_come(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), _ptr(iset.bbox),
+                                                   _ptr(groups.cap_off), groups.G, groups.total_cap, _ptr(groups.length),
+                                                   _ptr(groups.idx), _ptr(pad_off), _ptr(work), _ptr(crops), _stream()),
+                       "emia_overlap_first_come")
+        LAUNCHES["count"] += 1
+    return _derived(iset, crops)
+
+
+def filter_area(iset, groups, min_area):
+    lib = _lib.load()
+    out = _new_groups_like(groups)
+    _lib.check(lib.emia_group_filter_area(_ptr(groups.cap_off), groups.G, _ptr(groups.length), _ptr(groups.idx), _ptr(iset.area),
+                                          int(min_area), _ptr(out.length), _ptr(out.idx), _stream()), "emia_group_filter_area")
+    LAUNCHES["count"] += 1
+    return out
+
+
+def column_gate(iset, groups, min_size):
+    lib = _lib.load()
+    out = _new_groups_like(groups)
+    _lib.check(lib.emia_column_gate(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), _ptr(groups.cap_off), groups.G,
+                                    _ptr(groups.length), _ptr(groups.idx), iset.W, int(min_size), _ptr(out.length), _ptr(out.idx),
+                                    _stream()), "emia_column_gate")
+    LAUNCHES["count"] += 1
+    return out
+
+
+def postprocess_masks(iset, groups, min_crys_size=2):
+    """postprocess_masks (src/utils/mask_utils.py:38-84) on every group: column gate (Q5) -> fill holes -> closing ->
+    first-come overlap removal -> multi-component masks zeroed (kept in the list, Q6).  Returns (InstanceSet, Groups)."""
+    gated = column_gate(iset, groups, min_crys_size)
+    closed = morph(iset, [MORPH_FILL, MORPH_DILATE, MORPH_ERODE])
+    return overlap_first_come(closed, gated), gated
+
+
+def process_masks_parallel(iset):
+    """process_masks_parallel (src/functions/inference.py:170-213): fill holes -> erosion(disk 1) -> dilation(disk 1)."""
+    return morph(iset, [MORPH_FILL, MORPH_ERODE, MORPH_DILATE])
+
+
+def postprocess_masks_universal(iset, groups, is_small_class, min_crys_size=None):
+    """postprocess_masks_universal (src/functions/inference.py:1739-1813).  Returns (InstanceSet, Groups of survivors)."""
+    if min_crys_size is None:
+        a = iset.H * iset.W
+        min_crys_size = max(3, int(a * 0.000005)) if is_small_class else max(25, int(a * 0.0001))
+    out = morph(iset, [MORPH_FILL, MORPH_ERODE] if is_small_class else [MORPH_FILL, MORPH_ERODE, MORPH_DILATE])
+    return out, filter_area(out, groups, min_crys_size)
+
+
 CAP_CONTOURS = 8   # contours per instance held by the single-pass slab layout
 
 

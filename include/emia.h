@@ -159,6 +159,37 @@ int emia_containment_rules(const uint32_t* crops, const emia_inst_meta* meta, co
                            double containment_threshold, int32_t* out_len, int32_t* out_idx, void* workspace,
                            size_t workspace_bytes, void* stream);
 
+/* ---- K2: bit-packed clean-up morphology -------------------------------------------------------------------------
+ * Replaces scipy.ndimage.binary_fill_holes + skimage erosion/dilation (3x3 cross, out-of-frame neighbours ignored) +
+ * skimage.measure.label in postprocess_masks (src/utils/mask_utils.py:70-84), process_masks_parallel
+ * (src/functions/inference.py:189-203) and postprocess_masks_universal (inference.py:1778-1806).
+ * emia_morph_plan: padded plane size per instance (caller scans -> pad_off); work = 3 * pad_off[n] words.
+ * emia_morph: applies n_ops (<= 4) operators in order (1 = fill holes, 2 = erode, 3 = dilate) to every crop.
+ * emia_overlap_first_come: list member k loses the pixels of members 0..k-1 (in list order), then is zeroed when it has
+ *   more than one 8-connected component (mask_utils.py:77-82); members keep their place in the list (Q6).
+ * emia_crop_stats: recompute bbox / area after the masks changed. */
+#define EMIA_MORPH_FILL 1
+#define EMIA_MORPH_ERODE 2
+#define EMIA_MORPH_DILATE 3
+int emia_morph_plan(const emia_inst_meta* meta, int64_t n, int64_t* pad_words, void* stream);
+int emia_morph(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n, int H, int W,
+               const int32_t* ops_host, int32_t n_ops, const int64_t* pad_off, uint32_t* work, uint32_t* crops_out,
+               void* stream);
+int emia_overlap_first_come(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off,
+                            const int32_t* bbox, const int32_t* cap_off, int32_t G, int32_t total_cap,
+                            const int32_t* in_len, const int32_t* in_idx, const int64_t* pad_off, uint32_t* work,
+                            uint32_t* crops_out, void* stream);
+int emia_crop_stats(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n,
+                    int32_t* bbox, int32_t* area, void* stream);
+/* list members with area >= min_area, list order kept (inference.py:1800 `np.sum(final_mask) >= min_crys_size`). */
+int emia_group_filter_area(const int32_t* cap_off, int32_t G, const int32_t* in_len, const int32_t* in_idx,
+                           const int32_t* area, int32_t min_area, int32_t* out_len, int32_t* out_idx, void* stream);
+/* postprocess_masks' column gate (mask_utils.py:62-68): K = #frame columns whose total over all list members exceeds
+ * min_size; the list is truncated to its first min(K, len) members. */
+int emia_column_gate(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, const int32_t* cap_off,
+                     int32_t G, const int32_t* in_len, const int32_t* in_idx, int W, int32_t min_size, int32_t* out_len,
+                     int32_t* out_idx, void* stream);
+
 /* pairwise helpers (drop-in for iou / calculate_iou / calculate_containment on explicit pairs):
  * out[k] = {intersection, area_a, area_b} for pairs (pa[k], pb[k]). */
 int emia_pair_counts(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off,
