@@ -166,6 +166,8 @@ def main():
     ap.add_argument("--variant", type=int, default=int(os.environ.get("EMIA_PASTE_VARIANT", "0")))
     ap.add_argument("--arena-gb", type=float, default=32.0)
     ap.add_argument("--ref-tiles", type=int, default=8)
+    ap.add_argument("--batches", type=int, default=8, help="tile batches of the three-stream pipeline")
+    ap.add_argument("--paste-ctas", type=int, default=0, help="resident paste CTAs per SM (0 = kernel default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="extra untimed pass with per-stage CUDA events (stderr)")
     args = ap.parse_args()
@@ -204,18 +206,11 @@ def main():
 
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     k1_ms = []
+    pipe = engine.TilePipeline(H, W, um_pix=UM_PIX, rules=rules, dedup_iou=DEDUP_IOU, frames=arena, variant=args.variant,
+                               batches=args.batches, paste_ctas_per_sm=args.paste_ctas, device=dev)
 
-    def step(probs, bxs, scs, cls, time_k1=False):
-        if time_k1:
-            ev[2].record()
-        iset = engine.paste(probs, bxs, H, W, scores=scs, classes=cls, frames=arena, variant=args.variant)
-        if time_k1:
-            ev[3].record()
-        engine.measure(iset, um_pix=UM_PIX)
-        groups = engine.groups_from_offsets(offs, dev)
-        kept = engine.dedup_smart(iset, groups, iou_threshold=DEDUP_IOU)
-        kept = engine.apply_spatial_constraints(iset, kept, rules)
-        return iset, kept
+    def step(probs, bxs, scs, cls, time_k1=False, to_host=False):
+        return pipe.run(probs, bxs, scs, cls, offs, to_host=to_host, time_k1=time_k1)
 
     def barrier():
         if world > 1:
@@ -233,35 +228,44 @@ def main():
     barrier()
     ev[0].record()
     for _ in range(args.steps):
-        iset, kept = step(d_probs, d_boxes, d_scores, d_classes, time_k1=True)
+        res = step(d_probs, d_boxes, d_scores, d_classes, time_k1=True)
         torch.cuda.current_stream().synchronize()
-        k1_ms.append(ev[2].elapsed_time(ev[3]))
+        k1_ms.append(pipe.k1_ms())
     ev[1].record()
     barrier()
     launches = engine.LAUNCHES["count"] - l0
     ms_total = ev[0].elapsed_time(ev[1])
     if args.breakdown and rank == 0:
+        # un-overlapped pass (one batch, one stream) with per-stage CUDA events
         engine.STAGE_TIMING["enabled"] = True
         t0 = time.perf_counter()
-        step(d_probs, d_boxes, d_scores, d_classes)
+        engine.run_tiles(d_probs, d_boxes, d_scores, d_classes, offs, H, W, um_pix=UM_PIX, rules=rules, dedup_iou=DEDUP_IOU,
+                         frames=arena, variant=args.variant)
         torch.cuda.synchronize()
         wall = (time.perf_counter() - t0) * 1e3
         engine.STAGE_TIMING["enabled"] = False
         summ = engine.stage_summary()
         print(json.dumps({"stage_ms": summ, "sum_ms": sum(summ.values()), "wall_ms": wall}), file=sys.stderr)
+    # K1 alone (nothing else on the GPU), for comparison with its in-pipeline duration
+    k1_alone = []
+    for _ in range(3):
+        ev[2].record()
+        iset_alone = engine.paste(d_probs, d_boxes, H, W, frames=arena, variant=args.variant)
+        ev[3].record()
+        torch.cuda.synchronize()
+        k1_alone.append(ev[2].elapsed_time(ev[3]))
+    total_crop_words = iset_alone.total_crop_words
+    del iset_alone
     # ---------------- end-to-end (host buffers) ----------------
     def e2e_step():
-        p = h_probs.to(dev, non_blocking=True); b = h_boxes.to(dev, non_blocking=True)
-        s = h_scores.to(dev, non_blocking=True); c = h_classes.to(dev, non_blocking=True)
-        iset, kept = step(p, b, s, c)
-        rec = iset.records.to("cpu", non_blocking=False)
-        rinst = iset.rec_inst.cpu(); klen = kept.length.cpu(); kidx = kept.idx.cpu()
-        return rec, rinst, klen, kidx
+        r = step(h_probs, h_boxes, h_scores, h_classes, to_host=True)
+        torch.cuda.current_stream().synchronize()      # the pinned result buffers are complete
+        return r
     e2e_step()
     barrier()
     ev[0].record()
     for _ in range(args.steps):
-        rec, rinst, klen, kidx = e2e_step()
+        res_h = e2e_step()
     ev[1].record()
     barrier()
     ms_e2e = ev[0].elapsed_time(ev[1])
@@ -285,18 +289,19 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)"
-        crop_bytes = 4.0 * iset.total_crop_words
+        crop_bytes = 4.0 * total_crop_words
         k1_bytes = n_local * (28 * 28 * 4 + 16 + 32 + 8 + 16 + 4 + frame_bytes) + crop_bytes   # reads + frame + crop + bbox/area
         k1_gbs = k1_bytes / (k1 * 1e-3) / 1e9
         path_bytes = n_local * (28 * 28 * 4 + 16 + 8 + frame_bytes + 256) + 2 * crop_bytes           # SURVEY §8d B_inst
         h2d = int(h_probs.numel() * 4 + h_boxes.numel() * 4 + h_scores.numel() * 4 + h_classes.numel() * 4)
-        d2h = int(rec.numel() * 8 + rinst.numel() * 4 + klen.numel() * 4 + kidx.numel() * 4)
+        d2h = int(sum(v.numel() * v.element_size() for r in res_h for v in r["host"].values()))
         line = {
             "metric": "instances_per_sec", "value": value, "unit": "instances/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"config5: {args.tiles} tiles x ~Poisson(500) instances, 1024x1024, tile t -> rank t mod G",
                        "instances": int(n_global), "paste_variant": args.variant, "frame_arena_gb": round(slots * frame_bytes / 2**30, 1),
+                       "tile_batches": args.batches, "paste_ctas_per_sm": args.paste_ctas,
                        "l2": "per step each rank writes >= 16 GB of frames and re-reads GBs of inputs: far larger than the 126 MB L2",
                        "um_pix": UM_PIX, "dedup_iou": DEDUP_IOU, "rules": "polyhipes_tommy"},
             "mask_mpix_per_sec": value * H * W / 1e6,
@@ -306,7 +311,10 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_paste (K1 paste+threshold+bitpack)", "achieved": k1_gbs, "peak": peak,
                          "unit": "GB/s", "frac": k1_gbs / peak, "traffic": None, "peak_source": peak_src,
-                         "k1_ms_per_launch": k1, "k1_share_of_step": k1 / ms_step,
+                         "k1_ms_per_step": k1, "k1_launches_per_step": len(res), "k1_share_of_step": k1 / ms_step,
+                         "k1_alone_ms": float(np.median(k1_alone)), "k1_alone_gbs": k1_bytes / (float(np.median(k1_alone)) * 1e-3) / 1e9,
+                         "note": "achieved = K1 algorithmic bytes / sum of its CUDA-event durations on the paste stream while the "
+                                 "contour / de-dup / morphometry kernels of the previous tile batch run on the post stream",
                          "path_achieved_gbs": path_bytes / (ms_step * 1e-3) / 1e9,
                          "path_frac": path_bytes / (ms_step * 1e-3) / 1e9 / peak},
         }
@@ -314,18 +322,21 @@ def main():
             cores = os.cpu_count() or 1
             ntl = max(1, min(cores, args.ref_tiles))
             sample = tiles[:ntl]
-            dt, res = cpu_reference_run(sample, protos, min(cores, ntl))
-            inst = sum(r[1] for r in res)
+            dt, cres = cpu_reference_run(sample, protos, min(cores, ntl))
+            inst = sum(r[1] for r in cres)
             # parity of the sampled tiles against the GPU result of the last timed step
-            kl = kept.to_lists(); recs = iset.records.cpu().numpy(); co = iset.cont_off.cpu().numpy()
             ok = True
-            for (tt, n_t, final, vals) in res:
+            first = res[0]       # the sampled tiles are the first tiles of the shard: all in batch 0
+            kl = first["kept"].to_lists(); rows_h = first["meas"].rows_to_host()
+            for (tt, n_t, final, vals) in cres:
                 g = tiles.index(tt)
+                if g >= first["tiles"][1]:
+                    continue
                 got = [k - int(offs[g]) for k in kl[g]]
                 if got != final:
                     ok = False
                     continue
-                gv = [recs[j, :12] for k in kl[g] for j in range(co[k], co[k + 1]) if recs[j, 15] == 1.0]
+                gv = [r[:12] for _, rr in rows_h[g] for r in rr if r[15] == 1.0]
                 if len(gv) != len(vals) or not all(np.allclose(a, np.array(b), rtol=1e-5, atol=0) for a, b in zip(gv, vals)):
                     ok = False
             line["cpu_baseline"] = {"value": inst / dt, "unit": "instances/s", "cores": min(cores, ntl), "kind": "port",

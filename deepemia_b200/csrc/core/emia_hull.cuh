@@ -44,7 +44,8 @@ EMIA_HD void emia_sort_keys(uint64_t* a, int n) {
 EMIA_HD int emia_sign_ll(long long v) { return (v > 0) - (v < 0); }
 
 // One monotone chain of the hull (OpenCV's Sklansky_ on the sorted array).  Returns stack size.
-EMIA_HD int emia_sklansky(const uint64_t* arr, int start, int end, int* stack, int nsign, int sign2) {
+template <typename S>
+EMIA_HD int emia_sklansky(const uint64_t* arr, int start, int end, S* stack, int nsign, int sign2) {
     const int incr = end > start ? 1 : -1;
     int pprev = start, pcur = pprev + incr, pnext = pcur + incr;
     int stacksize = 3;
@@ -90,6 +91,73 @@ EMIA_HD int emia_sklansky(const uint64_t* arr, int start, int end, int* stack, i
     return --stacksize;
 }
 
+// The hull is assembled from four monotone chains (tl: leftmost -> topmost, tr: rightmost -> topmost, bl / br likewise for
+// the bottom).  The three helpers below are OpenCV's assembly steps; they are shared by the serial emia_convex_hull and
+// the warp-cooperative hull kernel (which runs the four chains on four lanes, keys and stacks in shared memory).
+template <typename S>
+EMIA_HD int emia_hull_emit_upper(const uint64_t* keys, int clockwise, S* tl_stack, int tl_count, S* tr_stack, int tr_count,
+                                 int* hull, int* nout_io) {
+    int nout = *nout_io;
+    if (!clockwise) {
+        S* ts = tl_stack; tl_stack = tr_stack; tr_stack = ts;
+        int tc = tl_count; tl_count = tr_count; tr_count = tc;
+    }
+    for (int i = 0; i < tl_count - 1; ++i) hull[nout++] = EMIA_KEY_I(keys[tl_stack[i]]);
+    for (int i = tr_count - 1; i > 0; --i) hull[nout++] = EMIA_KEY_I(keys[tr_stack[i]]);
+    *nout_io = nout;
+    return tr_count > 2 ? (int)tr_stack[1] : tl_count > 2 ? (int)tl_stack[tl_count - 2] : -1;   // stop_idx
+}
+template <typename S>
+EMIA_HD void emia_hull_emit_lower(const uint64_t* keys, int clockwise, S* bl_stack, int bl_count, S* br_stack, int br_count,
+                                  int stop_idx, int* hull, int* nout_io) {
+    int nout = *nout_io;
+    if (clockwise) {
+        S* ts = bl_stack; bl_stack = br_stack; br_stack = ts;
+        int tc = bl_count; bl_count = br_count; br_count = tc;
+    }
+    if (stop_idx >= 0) {
+        const int check_idx = bl_count > 2 ? (int)bl_stack[1] : bl_count + br_count > 2 ? (int)br_stack[2 - bl_count] : -1;
+        if (check_idx == stop_idx ||
+            (check_idx >= 0 && EMIA_KEY_X(keys[check_idx]) == EMIA_KEY_X(keys[stop_idx]) &&
+             EMIA_KEY_Y(keys[check_idx]) == EMIA_KEY_Y(keys[stop_idx]))) {
+            bl_count = emia_min(bl_count, 2);
+            br_count = emia_min(br_count, 2);
+        }
+    }
+    for (int i = 0; i < bl_count - 1; ++i) hull[nout++] = EMIA_KEY_I(keys[bl_stack[i]]);
+    for (int i = br_count - 1; i > 0; --i) hull[nout++] = EMIA_KEY_I(keys[br_stack[i]]);
+    *nout_io = nout;
+}
+// cyclic shift so that indices ascend/descend when possible
+EMIA_HD void emia_hull_cyclic_shift(int* hull, int nout, int* tmp) {
+    if (nout < 3) return;
+    int min_idx = 0, max_idx = 0, lt = 0;
+    for (int i = 1; i < nout; ++i) {
+        const int idx = hull[i];
+        lt += hull[i - 1] < idx;
+        if (lt > 1 && lt <= i - 2) break;
+        if (idx < hull[min_idx]) min_idx = i;
+        if (idx > hull[max_idx]) max_idx = i;
+    }
+    int mmdist = max_idx - min_idx; if (mmdist < 0) mmdist = -mmdist;
+    if ((mmdist == 1 || mmdist == nout - 1) && (lt <= 1 || lt >= nout - 2)) {
+        const int ascending = (max_idx + 1) % nout == min_idx;
+        const int i0 = ascending ? min_idx : max_idx;
+        int j = i0;
+        if (i0 > 0) {
+            int i;
+            for (i = 0; i < nout; ++i) {
+                const int curr_idx = tmp[i] = hull[j];
+                const int next_j = j + 1 < nout ? j + 1 : 0;
+                const int next_idx = hull[next_j];
+                if (i < nout - 1 && (ascending != (curr_idx < next_idx))) break;
+                j = next_j;
+            }
+            if (i == nout) for (int k = 0; k < nout; ++k) hull[k] = tmp[k];
+        }
+    }
+}
+
 // Convex hull of n packed integer points (counter-clockwise flag as cv2.convexHull(clockwise=...)).
 // keys: scratch n; stack: scratch n+2; hull: out, original point indices (capacity n); tmp: scratch n.
 // Returns hull size.
@@ -113,66 +181,17 @@ EMIA_HD_NOINLINE int emia_convex_hull(const uint32_t* pts, int n, int clockwise,
     }
     // upper half
     int* tl_stack = stack;
-    int tl_count = emia_sklansky(keys, 0, maxy_ind, tl_stack, -1, 1);
+    const int tl_count = emia_sklansky(keys, 0, maxy_ind, tl_stack, -1, 1);
     int* tr_stack = stack + tl_count;
-    int tr_count = emia_sklansky(keys, n - 1, maxy_ind, tr_stack, -1, -1);
-    if (!clockwise) {
-        int* ts = tl_stack; tl_stack = tr_stack; tr_stack = ts;
-        int tc = tl_count; tl_count = tr_count; tr_count = tc;
-    }
-    for (int i = 0; i < tl_count - 1; ++i) hull[nout++] = EMIA_KEY_I(keys[tl_stack[i]]);
-    for (int i = tr_count - 1; i > 0; --i) hull[nout++] = EMIA_KEY_I(keys[tr_stack[i]]);
-    const int stop_idx = tr_count > 2 ? tr_stack[1] : tl_count > 2 ? tl_stack[tl_count - 2] : -1;
-
+    const int tr_count = emia_sklansky(keys, n - 1, maxy_ind, tr_stack, -1, -1);
+    const int stop_idx = emia_hull_emit_upper(keys, clockwise, tl_stack, tl_count, tr_stack, tr_count, hull, &nout);
     // lower half.  NOTE: the upper-half stacks are dead from here on (their content was copied to hull).
     int* bl_stack = stack;
-    int bl_count = emia_sklansky(keys, 0, miny_ind, bl_stack, 1, -1);
+    const int bl_count = emia_sklansky(keys, 0, miny_ind, bl_stack, 1, -1);
     int* br_stack = stack + bl_count;
-    int br_count = emia_sklansky(keys, n - 1, miny_ind, br_stack, 1, 1);
-    if (clockwise) {
-        int* ts = bl_stack; bl_stack = br_stack; br_stack = ts;
-        int tc = bl_count; bl_count = br_count; br_count = tc;
-    }
-    if (stop_idx >= 0) {
-        const int check_idx = bl_count > 2 ? bl_stack[1] : bl_count + br_count > 2 ? br_stack[2 - bl_count] : -1;
-        if (check_idx == stop_idx ||
-            (check_idx >= 0 && EMIA_KEY_X(keys[check_idx]) == EMIA_KEY_X(keys[stop_idx]) &&
-             EMIA_KEY_Y(keys[check_idx]) == EMIA_KEY_Y(keys[stop_idx]))) {
-            bl_count = emia_min(bl_count, 2);
-            br_count = emia_min(br_count, 2);
-        }
-    }
-    for (int i = 0; i < bl_count - 1; ++i) hull[nout++] = EMIA_KEY_I(keys[bl_stack[i]]);
-    for (int i = br_count - 1; i > 0; --i) hull[nout++] = EMIA_KEY_I(keys[br_stack[i]]);
-
-    // cyclic shift so that indices ascend/descend when possible
-    if (nout >= 3) {
-        int min_idx = 0, max_idx = 0, lt = 0;
-        for (int i = 1; i < nout; ++i) {
-            const int idx = hull[i];
-            lt += hull[i - 1] < idx;
-            if (lt > 1 && lt <= i - 2) break;
-            if (idx < hull[min_idx]) min_idx = i;
-            if (idx > hull[max_idx]) max_idx = i;
-        }
-        int mmdist = max_idx - min_idx; if (mmdist < 0) mmdist = -mmdist;
-        if ((mmdist == 1 || mmdist == nout - 1) && (lt <= 1 || lt >= nout - 2)) {
-            const int ascending = (max_idx + 1) % nout == min_idx;
-            const int i0 = ascending ? min_idx : max_idx;
-            int j = i0;
-            if (i0 > 0) {
-                int i;
-                for (i = 0; i < nout; ++i) {
-                    const int curr_idx = tmp[i] = hull[j];
-                    const int next_j = j + 1 < nout ? j + 1 : 0;
-                    const int next_idx = hull[next_j];
-                    if (i < nout - 1 && (ascending != (curr_idx < next_idx))) break;
-                    j = next_j;
-                }
-                if (i == nout) for (int k = 0; k < nout; ++k) hull[k] = tmp[k];
-            }
-        }
-    }
+    const int br_count = emia_sklansky(keys, n - 1, miny_ind, br_stack, 1, 1);
+    emia_hull_emit_lower(keys, clockwise, bl_stack, bl_count, br_stack, br_count, stop_idx, hull, &nout);
+    emia_hull_cyclic_shift(hull, nout, tmp);
     return nout;
 }
 

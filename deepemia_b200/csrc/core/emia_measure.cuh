@@ -76,7 +76,9 @@ EMIA_HD void emia_order_points(const float* p /*8*/, float* o /*8: tl,tr,br,bl*/
 }
 
 // Fill rec[16] for one contour.  scratch: emia_measure_scratch_bytes(n), 8-byte aligned.
-EMIA_HD_NOINLINE void emia_measure_contour(const uint32_t* pts, int n, double um_pix, void* scratch, double* rec, int presorted = 0) {
+// prepared: 0 = nothing, 1 = scratch starts with the n sorted hull keys, 2 = the hull is ready (indices in the `hull`
+// region of the scratch, its size in stack[0]) — both written by the warp-cooperative hull kernel beforehand.
+EMIA_HD_NOINLINE void emia_measure_contour(const uint32_t* pts, int n, double um_pix, void* scratch, double* rec, int prepared = 0) {
     const double area = emia_contour_area(pts, n);
     const double perimeter = emia_arc_length_closed(pts, n);
 
@@ -86,7 +88,7 @@ EMIA_HD_NOINLINE void emia_measure_contour(const uint32_t* pts, int n, double um
     int* stack = (int*)(hp + 2 * n);                   // 4(n+2) (later: inv_len)
     int* hull = stack + (n + 2);                       // 4n
     int* tmp = hull + n;                               // 4n
-    const int nh = emia_convex_hull(pts, n, /*clockwise=*/0, keys, stack, hull, tmp, presorted);
+    const int nh = (prepared == 2) ? stack[0] : emia_convex_hull(pts, n, /*clockwise=*/0, keys, stack, hull, tmp, prepared);
     for (int i = 0; i < nh; ++i) {
         hp[2 * i] = (float)EMIA_PT_X(pts[hull[i]]);
         hp[2 * i + 1] = (float)EMIA_PT_Y(pts[hull[i]]);

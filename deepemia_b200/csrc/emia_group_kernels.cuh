@@ -387,13 +387,24 @@ __global__ void k_group_compact(const int32_t* __restrict__ cap_off, int G, cons
     if (lane == 0) out_len[g] = run;
 }
 
+#include "emia_group_fused.cuh"
+
 // ---- host-side drivers ---------------------------------------------------------------------------------------------
 static int emia_group_pipeline(int mode, const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off,
                                const int32_t* bbox, const int32_t* area, const double* perim0, const int64_t* n_contours,
                                const float* scores, const int32_t* classes, const int32_t* cap_off, int32_t G,
                                const int32_t* in_len, const int32_t* in_idx, double thr, double max_aspect,
                                const int32_t* rule_active, const double* rule_max_iou, int num_classes, int32_t* out_len,
-                               int32_t* out_idx, void* workspace, size_t workspace_bytes, cudaStream_t st, int L) {
+                               int32_t* out_idx, void* workspace, size_t workspace_bytes, cudaStream_t st, int L, int max_cap) {
+    if (max_cap > 0 && max_cap <= EMIA_FUSED_MAX_CAP) {
+        // every group fits one SM's shared memory: one CTA per group, no global workspace
+        const size_t smem = emia_fused_smem_bytes(max_cap);
+        cudaFuncSetAttribute(k_group_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_group_fused<<<(unsigned)G, EMIA_FUSED_THREADS, smem, st>>>(crops, meta, crop_off, bbox, area, perim0, n_contours, scores, classes,
+                                                                    cap_off, in_len, in_idx, mode, thr, max_aspect, rule_active, rule_max_iou,
+                                                                    num_classes, max_cap, out_len, out_idx);
+        return emia_check_launch("group op (fused) launch: %s");
+    }
     EmiaGroupWs ws;
     size_t tail = 0;
     if (emia_carve_ws(workspace, workspace_bytes, (size_t)L, G, &ws, &tail) != 0)
@@ -420,7 +431,7 @@ static int emia_group_pipeline(int mode, const uint32_t* crops, const emia_inst_
 
 extern "C" int emia_dedup_smart(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off,
                                 const int32_t* bbox, const int32_t* area, const double* perim0, const int64_t* n_contours,
-                                const float* scores, const int32_t* classes, const int32_t* cap_off, int32_t G, int32_t total_cap,
+                                const float* scores, const int32_t* classes, const int32_t* cap_off, int32_t G, int32_t total_cap, int32_t max_cap,
                                 const int32_t* in_len, const int32_t* in_idx, double iou_threshold, double max_aspect_ratio,
                                 int32_t* out_len, int32_t* out_idx, void* workspace, size_t workspace_bytes, void* stream) {
     if (G < 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_dedup_smart: %s", "bad G");
@@ -432,11 +443,11 @@ extern "C" int emia_dedup_smart(const uint32_t* crops, const emia_inst_meta* met
     if (L == 0) { cudaMemsetAsync(out_len, 0, (size_t)G * 4, (cudaStream_t)stream); return EMIA_OK; }
     return emia_group_pipeline(0, crops, meta, crop_off, bbox, area, perim0, n_contours, scores, classes, cap_off, G, in_len, in_idx,
                                iou_threshold, max_aspect_ratio, nullptr, nullptr, 0, out_len, out_idx, workspace, workspace_bytes,
-                               (cudaStream_t)stream, L);
+                               (cudaStream_t)stream, L, max_cap);
 }
 
 extern "C" int emia_dedup_inorder(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off,
-                                  const int32_t* bbox, const int32_t* area, const int32_t* cap_off, int32_t G, int32_t total_cap,
+                                  const int32_t* bbox, const int32_t* area, const int32_t* cap_off, int32_t G, int32_t total_cap, int32_t max_cap,
                                   const int32_t* in_len, const int32_t* in_idx, double iou_threshold, int32_t* out_len,
                                   int32_t* out_idx, void* workspace, size_t workspace_bytes, void* stream) {
     if (G < 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_dedup_inorder: %s", "bad G");
@@ -447,12 +458,12 @@ extern "C" int emia_dedup_inorder(const uint32_t* crops, const emia_inst_meta* m
     if (L == 0) { cudaMemsetAsync(out_len, 0, (size_t)G * 4, (cudaStream_t)stream); return EMIA_OK; }
     return emia_group_pipeline(1, crops, meta, crop_off, bbox, area, nullptr, nullptr, nullptr, nullptr, cap_off, G, in_len, in_idx,
                                iou_threshold, 0.0, nullptr, nullptr, 0, out_len, out_idx, workspace, workspace_bytes,
-                               (cudaStream_t)stream, L);
+                               (cudaStream_t)stream, L, max_cap);
 }
 
 extern "C" int emia_overlap_rules(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off,
                                   const int32_t* bbox, const int32_t* area, const float* scores, const int32_t* classes,
-                                  const int32_t* cap_off, int32_t G, int32_t total_cap, const int32_t* in_len, const int32_t* in_idx,
+                                  const int32_t* cap_off, int32_t G, int32_t total_cap, int32_t max_cap, const int32_t* in_len, const int32_t* in_idx,
                                   const int32_t* rule_active, const double* rule_max_iou, int32_t num_classes,
                                   int32_t* out_len, int32_t* out_idx, void* workspace, size_t workspace_bytes, void* stream) {
     if (G < 0 || num_classes < 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_overlap_rules: %s", "bad argument");
@@ -464,12 +475,12 @@ extern "C" int emia_overlap_rules(const uint32_t* crops, const emia_inst_meta* m
     if (L == 0) { cudaMemsetAsync(out_len, 0, (size_t)G * 4, (cudaStream_t)stream); return EMIA_OK; }
     return emia_group_pipeline(2, crops, meta, crop_off, bbox, area, nullptr, nullptr, scores, classes, cap_off, G, in_len, in_idx, 0.0,
                                0.0, rule_active, rule_max_iou, num_classes, out_len, out_idx, workspace, workspace_bytes,
-                               (cudaStream_t)stream, L);
+                               (cudaStream_t)stream, L, max_cap);
 }
 
 extern "C" int emia_containment_rules(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off,
                                       const int32_t* bbox, const int32_t* area, const int32_t* classes,
-                                      const int32_t* cap_off, int32_t G, int32_t total_cap, const int32_t* in_len, const int32_t* in_idx,
+                                      const int32_t* cap_off, int32_t G, int32_t total_cap, int32_t max_cap, const int32_t* in_len, const int32_t* in_idx,
                                       const int32_t* child_class_host, const int32_t* parent_class_host, int32_t n_rules,
                                       double containment_threshold, int32_t* out_len, int32_t* out_idx, void* workspace,
                                       size_t workspace_bytes, void* stream) {
@@ -498,6 +509,12 @@ extern "C" int emia_containment_rules(const uint32_t* crops, const emia_inst_met
                                                                                    in_len, in_idx, child, containment_threshold, rem_a);
         } else {
             cudaMemcpyAsync(rem_b, rem_a, (size_t)L * 4, cudaMemcpyDeviceToDevice, st);
+            if (max_cap > 0 && max_cap <= EMIA_FUSED_MAX_CAP) {
+                const size_t smem = emia_fused_smem_bytes(max_cap);
+                cudaFuncSetAttribute(k_containment_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                k_containment_fused<<<(unsigned)G, EMIA_FUSED_THREADS, smem, st>>>(crops, meta, crop_off, bbox, area, classes, cap_off, in_len,
+                                                                                  in_idx, child, parent, containment_threshold, max_cap, rem_a, rem_b);
+            } else
             k_containment_rule<<<gl, T, 0, st>>>(crops, meta, crop_off, bbox, area, classes, cap_off, G, in_len, in_idx, L, child, parent,
                                                  containment_threshold, rem_a, rem_b);
             int32_t* t = rem_a; rem_a = rem_b; rem_b = t;

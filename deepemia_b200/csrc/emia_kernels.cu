@@ -479,7 +479,10 @@ __global__ void __launch_bounds__(EMIA_PASTE_THREADS) k_paste_bulk(
 extern "C" int emia_paste_threshold_bitpack(const float* probs, const float* boxes, const emia_inst_meta* meta,
                                             const int64_t* crop_off, int64_t n, float scale_x, float scale_y, int H,
                                             int W, uint32_t* frames, int64_t frame_slots, int pitch_words,
-                                            uint32_t* crops, int32_t* bbox, int32_t* area, int variant, void* stream) {
+                                            uint32_t* crops, int32_t* bbox, int32_t* area, int variant_and_grid, void* stream) {
+    // bits 0-7: variant; bits 8-15: resident CTAs per SM (0 = default) — a smaller grid leaves SM room for other streams
+    const int variant = variant_and_grid & 0xff;
+    const int ctas_req = (variant_and_grid >> 8) & 0xff;
     if (n < 0 || H <= 0 || W <= 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_paste_threshold_bitpack: %s", "bad shape");
     if (n == 0) return EMIA_OK;
     if (!probs || !boxes || !meta || !crop_off || !crops || !bbox || !area)
@@ -496,13 +499,15 @@ extern "C" int emia_paste_threshold_bitpack(const float* probs, const float* box
         if (pitch_words * 4 > EMIA_BULK_BYTES) return emia_fail(EMIA_ERR_UNSUPPORTED, "emia_paste_threshold_bitpack: %s", "variant 1 needs a frame row <= 16 KB");
         const size_t smem = 2 * EMIA_BULK_BYTES + EMIA_MASK_SIDE * EMIA_MASK_SIDE * 4 + (size_t)max_cols * 12;
         cudaFuncSetAttribute(k_paste_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        const unsigned grid = (unsigned)(n < (int64_t)sms * 4 ? n : (int64_t)sms * 4);
+        const int64_t per_sm = ctas_req ? ctas_req : 4;
+        const unsigned grid = (unsigned)(n < (int64_t)sms * per_sm ? n : (int64_t)sms * per_sm);
         k_paste_bulk<<<grid, EMIA_PASTE_THREADS, smem, st>>>(probs, (const float4*)boxes, meta, crop_off, n, scale_x, scale_y, H, W,
                                                              frames, frame_slots, pitch_words, crops, bbox, area, max_cols);
         return emia_check_launch("emia_paste_threshold_bitpack (bulk) launch: %s");
     }
     const size_t smem = EMIA_MASK_SIDE * EMIA_MASK_SIDE * 4 + EMIA_PASTE_TILE_WORDS * 4 + (size_t)max_cols * 12;
-    const unsigned grid = (unsigned)(n < (int64_t)sms * 8 ? n : (int64_t)sms * 8);
+    const int64_t per_sm = ctas_req ? ctas_req : 8;
+    const unsigned grid = (unsigned)(n < (int64_t)sms * per_sm ? n : (int64_t)sms * per_sm);
     if (frames) {
         cudaFuncSetAttribute(k_paste<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_paste<true><<<grid, EMIA_PASTE_THREADS, smem, st>>>(probs, (const float4*)boxes, meta, crop_off, n, scale_x, scale_y, H, W,

@@ -18,13 +18,13 @@ __global__ void __launch_bounds__(EMIA_TRACE_THREADS) k_contour_trace(
     const uint32_t* __restrict__ crops, const emia_inst_meta* __restrict__ meta, const int64_t* __restrict__ crop_off, int64_t n,
     uint32_t* __restrict__ marks, int64_t* __restrict__ n_contours, int64_t* __restrict__ n_points,
     int64_t* __restrict__ scratch_bytes, const int64_t* __restrict__ cont_off, const int64_t* __restrict__ pt_off,
-    uint32_t* __restrict__ pts, int32_t* __restrict__ cstart) {
+    uint32_t* __restrict__ pts, int32_t* __restrict__ cstart, double* __restrict__ perim0) {
     const int64_t i = (int64_t)blockIdx.x * EMIA_TRACE_THREADS + threadIdx.x;
     if (i >= n) return;
     const emia_inst_meta m = meta[i];
     const int words = m.ch * m.cw;
     if (words <= 0) {
-        if (kStore) cstart[cont_off[i] + i] = 0;
+        if (kStore) { cstart[cont_off[i] + i] = 0; if (perim0) perim0[i] = 0.0; }
         else { n_contours[i] = 0; n_points[i] = 0; scratch_bytes[i] = 0; }
         return;
     }
@@ -44,40 +44,56 @@ __global__ void __launch_bounds__(EMIA_TRACE_THREADS) k_contour_trace(
         n_contours[i] = o.n_contours;
         n_points[i] = o.n_pts;
         scratch_bytes[i] = o.n_contours ? (int64_t)((emia_measure_scratch_bytes(o.max_len) + 15) & ~(size_t)15) : 0;
+    } else if (perim0) {
+        // arcLength of contours[0] in OpenCV order = the LAST discovered contour (deduplicate_masks_smart's compactness, Q10)
+        const int nc = o.n_contours;
+        perim0[i] = nc ? emia_arc_length_closed(o.pts + o.cstart[nc - 1], o.cstart[nc] - o.cstart[nc - 1]) : 0.0;
     }
 }
 #define EMIA_TRACE_SMEM_BYTES ((size_t)0)
 
-// ---- hull pre-sort: one WARP per single-contour instance --------------------------------------------------------------
-// The convex hull starts from the vertices sorted by (x, y, index).  A per-thread comparison sort in global memory is
-// dominated by uncoalesced accesses (ncu/ablation: 83 % of the morphometry kernel), so the keys of the common case
-// (one contour, <= EMIA_PRESORT_MAX vertices) are sorted beforehand by a bitonic network in shared memory, one warp per
-// instance, and written where the hull expects them (the head of the instance's scratch block).
+// ---- convex hull: one WARP per single-contour work item ---------------------------------------------------------------
+// The hull (Sklansky on the vertices sorted by (x, y, index)) was 75 % of the per-thread morphometry kernel: a chain of
+// dependent, uncoalesced global loads (ncu source view, profiles/).  For the common case (one contour, <= EMIA_PRESORT_MAX
+// vertices) a warp now sorts the keys with a bitonic network in shared memory, runs the four monotone chains on four
+// lanes (keys and stacks in shared memory), lane 0 assembles the hull exactly as the serial code does, and the hull
+// indices + size are written where emia_measure_contour(prepared = 2) expects them in the item's scratch block.
+// Work items: item `it` measures instance item_inst[it] (identity when item_inst == nullptr; < 0 = nothing to do); its records
+// start at rec_off[it] (rec_off[it+1] - rec_off[it] = number of contours) and its scratch at scratch_off[it].
+// inst_cont_off (per INSTANCE) locates the packed cstart layout and is only read when cstart_stride == 0.
 #define EMIA_PRESORT_MAX 256
-#define EMIA_PRESORT_WARPS 8
-__global__ void __launch_bounds__(EMIA_PRESORT_WARPS * 32) k_contour_presort(int64_t n, const int64_t* __restrict__ cont_off,
-                                                                            const int64_t* __restrict__ pt_off,
-                                                                            const int32_t* __restrict__ cstart, int cstart_stride,
-                                                                            const int64_t* __restrict__ scratch_off,
-                                                                            const uint32_t* __restrict__ pts, uint8_t* __restrict__ scratch) {
-    __shared__ uint64_t s_keys[EMIA_PRESORT_WARPS][EMIA_PRESORT_MAX];
+#define EMIA_PRESORT_WARPS 4
+struct EmiaHullSmem {
+    uint64_t keys[EMIA_PRESORT_MAX];
+    uint16_t stacks[4][EMIA_PRESORT_MAX + 4];
+    int hull[EMIA_PRESORT_MAX];
+    int tmp[EMIA_PRESORT_MAX];
+};
+__global__ void __launch_bounds__(EMIA_PRESORT_WARPS * 32) k_contour_hull(int64_t n, const int32_t* __restrict__ item_inst,
+                                                                         const int64_t* __restrict__ rec_off,
+                                                                         const int64_t* __restrict__ inst_cont_off,
+                                                                         const int64_t* __restrict__ pt_off,
+                                                                         const int32_t* __restrict__ cstart, int cstart_stride,
+                                                                         const int64_t* __restrict__ scratch_off,
+                                                                         const uint32_t* __restrict__ pts, uint8_t* __restrict__ scratch) {
+    __shared__ EmiaHullSmem s_all[EMIA_PRESORT_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t i = (int64_t)blockIdx.x * EMIA_PRESORT_WARPS + warp;
-    if (i >= n) return;
-    const int64_t c0 = cont_off[i];
-    if (cont_off[i + 1] - c0 != 1) return;
-    const int32_t* cs = cstart_stride > 0 ? cstart + (size_t)i * cstart_stride : cstart + c0 + i;
+    const int64_t it = (int64_t)blockIdx.x * EMIA_PRESORT_WARPS + warp;
+    if (it >= n) return;
+    if (rec_off[it + 1] - rec_off[it] != 1) return;
+    const int64_t i = item_inst ? (int64_t)item_inst[it] : it;
+    if (i < 0) return;
+    const int32_t* cs = cstart_stride > 0 ? cstart + (size_t)i * cstart_stride : cstart + inst_cont_off[i] + i;
     const int len = cs[1] - cs[0];
-    if (len > EMIA_PRESORT_MAX || len < 2) {
-        if (len == 1 && lane == 0) {
-            const uint32_t p0 = pts[pt_off[i] + cs[0]];
-            ((uint64_t*)(scratch + scratch_off[i]))[0] = EMIA_KEY(EMIA_PT_X(p0), EMIA_PT_Y(p0), 0);
-        }
-        return;
-    }
+    if (len > EMIA_PRESORT_MAX || len < 1) return;
+    EmiaHullSmem& S = s_all[warp];
+    // scratch carve-up of emia_measure_contour: keys 8n | hp 8n | stack 4(n+2) | hull 4n | tmp 4n
+    uint8_t* sc = scratch + scratch_off[it];
+    int* g_stack = (int*)(sc + (size_t)16 * len);
+    int* g_hull = g_stack + (len + 2);
     int N = 32;
     while (N < len) N <<= 1;
-    uint64_t* k = s_keys[warp];
+    uint64_t* k = S.keys;
     const uint32_t* p = pts + pt_off[i] + cs[0];
     for (int t = lane; t < N; t += 32) {
         uint64_t key = ~0ull;
@@ -97,35 +113,75 @@ __global__ void __launch_bounds__(EMIA_PRESORT_WARPS * 32) k_contour_presort(int
             __syncwarp();
         }
     }
-    uint64_t* dst = (uint64_t*)(scratch + scratch_off[i]);
-    for (int t = lane; t < len; t += 32) dst[t] = k[t];
+    // first index of the minimum / maximum y in sorted order (the serial scan keeps the first occurrence)
+    int mn = 0x7fffffff, mx = 0x7fffffff;
+    for (int t = lane; t < len; t += 32) {
+        const int y = EMIA_KEY_Y(k[t]);
+        mn = min(mn, (y << 9) | t);                   // y < 2^20, t < 2^9
+        mx = min(mx, ((0xFFFFF - y) << 9) | t);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = min(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    const int miny_ind = mn & 511, maxy_ind = mx & 511;
+    int nout = 0;
+    const bool degenerate = (EMIA_KEY_X(k[0]) == EMIA_KEY_X(k[len - 1]) && EMIA_KEY_Y(k[0]) == EMIA_KEY_Y(k[len - 1]));
+    if (degenerate) {
+        if (lane == 0) S.hull[0] = 0;
+        nout = 1;
+    } else {
+        int cnt = 0;
+        if (lane < 4) {
+            const int start = (lane & 1) ? len - 1 : 0;
+            const int end = (lane < 2) ? maxy_ind : miny_ind;
+            const int nsign = (lane < 2) ? -1 : 1;
+            const int sign2 = (lane == 0 || lane == 3) ? 1 : -1;
+            cnt = emia_sklansky(k, start, end, S.stacks[lane], nsign, sign2);
+        }
+        __syncwarp();
+        const int tl = __shfl_sync(0xffffffffu, cnt, 0), tr = __shfl_sync(0xffffffffu, cnt, 1);
+        const int bl = __shfl_sync(0xffffffffu, cnt, 2), br = __shfl_sync(0xffffffffu, cnt, 3);
+        if (lane == 0) {
+            const int stop_idx = emia_hull_emit_upper(k, 0, S.stacks[0], tl, S.stacks[1], tr, S.hull, &nout);
+            emia_hull_emit_lower(k, 0, S.stacks[2], bl, S.stacks[3], br, stop_idx, S.hull, &nout);
+            emia_hull_cyclic_shift(S.hull, nout, S.tmp);
+        }
+        nout = __shfl_sync(0xffffffffu, nout, 0);
+    }
+    __syncwarp();
+    for (int t = lane; t < nout; t += 32) g_hull[t] = S.hull[t];
+    if (lane == 0) g_stack[0] = nout;
 }
 
 // ---- morphometry: one THREAD per instance over the stored vertex lists ---------------------------------------------
-__global__ void __launch_bounds__(128) k_contour_measure(const emia_inst_meta* __restrict__ meta, int64_t n,
-                                                         const int64_t* __restrict__ cont_off, const int64_t* __restrict__ pt_off,
+__global__ void __launch_bounds__(128) k_contour_measure(int64_t n, const int32_t* __restrict__ item_inst,
+                                                         const int64_t* __restrict__ rec_off, const int64_t* __restrict__ inst_cont_off,
+                                                         const int64_t* __restrict__ pt_off,
                                                          const int64_t* __restrict__ scratch_off, double um_pix, double min_area,
                                                          const uint32_t* __restrict__ pts, const int32_t* __restrict__ cstart,
                                                          int cstart_stride, int presort_max, double* __restrict__ records,
                                                          int32_t* __restrict__ rec_inst, double* __restrict__ perim0,
                                                          uint8_t* __restrict__ scratch) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int64_t c0 = cont_off[i];
-    const int nc = (int)(cont_off[i + 1] - c0);
-    if (nc == 0) { perim0[i] = 0.0; return; }
-    const int32_t* cs = cstart_stride > 0 ? cstart + (size_t)i * cstart_stride : cstart + c0 + i;
+    const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= n) return;
+    const int64_t i = item_inst ? (int64_t)item_inst[it] : it;
+    if (i < 0) return;
+    const int64_t c0 = rec_off[it];
+    const int nc = (int)(rec_off[it + 1] - c0);
+    if (nc == 0) { if (perim0) perim0[i] = 0.0; return; }
+    const int32_t* cs = cstart_stride > 0 ? cstart + (size_t)i * cstart_stride : cstart + inst_cont_off[i] + i;
     const uint32_t* p = pts + pt_off[i];
-    void* sc = scratch + scratch_off[i];
+    void* sc = scratch + scratch_off[it];
     for (int j = 0; j < nc; ++j) {
         const int k = nc - 1 - j;                     // OpenCV returns contours in reverse discovery order
         const uint32_t* cp = p + cs[k];
         const int len = cs[k + 1] - cs[k];
         double* rec = records + (size_t)(c0 + j) * EMIA_REC_FIELDS;
-        emia_measure_contour(cp, len, um_pix, sc, rec, (nc == 1 && len <= presort_max) ? 1 : 0);
+        emia_measure_contour(cp, len, um_pix, sc, rec, (nc == 1 && len <= presort_max) ? 2 : 0);
         rec[EMIA_REC_MEASURED] = (rec[EMIA_REC_AREA] >= min_area) ? 1.0 : 0.0;
         rec_inst[c0 + j] = (int32_t)i;
-        if (j == 0) perim0[i] = rec[EMIA_REC_PERIMETER];
+        if (j == 0 && perim0) perim0[i] = rec[EMIA_REC_PERIMETER];
     }
 }
 
@@ -138,7 +194,7 @@ extern "C" int emia_contour_count(const uint32_t* crops, const emia_inst_meta* m
         return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_count: %s", "null pointer");
     const unsigned grid = (unsigned)((n + EMIA_TRACE_THREADS - 1) / EMIA_TRACE_THREADS);
     k_contour_trace<false><<<grid, EMIA_TRACE_THREADS, EMIA_TRACE_SMEM_BYTES, (cudaStream_t)stream>>>(crops, meta, crop_off, n, marks, n_contours, n_points,
-                                                                                  scratch_bytes, nullptr, nullptr, nullptr, nullptr);
+                                                                                  scratch_bytes, nullptr, nullptr, nullptr, nullptr, nullptr);
     return emia_check_launch("emia_contour_count launch: %s");
 }
 
@@ -154,15 +210,29 @@ extern "C" int emia_contour_measure(const uint32_t* crops, const emia_inst_meta*
         return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_measure: %s", "null pointer");
     const unsigned gridt = (unsigned)((n + EMIA_TRACE_THREADS - 1) / EMIA_TRACE_THREADS);
     k_contour_trace<true><<<gridt, EMIA_TRACE_THREADS, EMIA_TRACE_SMEM_BYTES, (cudaStream_t)stream>>>(crops, meta, crop_off, n, marks, nullptr, nullptr, nullptr,
-                                                                                  cont_off, pt_off, pts, cstart);
+                                                                                  cont_off, pt_off, pts, cstart, nullptr);
     const unsigned grid = (unsigned)((n + 127) / 128);
-    k_contour_presort<<<(unsigned)((n + EMIA_PRESORT_WARPS - 1) / EMIA_PRESORT_WARPS), EMIA_PRESORT_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        n, cont_off, pt_off, cstart, 0, scratch_off, pts, scratch);
-    k_contour_measure<<<grid, 128, 0, (cudaStream_t)stream>>>(meta, n, cont_off, pt_off, scratch_off, um_pix, min_area, pts, cstart, 0,
+    k_contour_hull<<<(unsigned)((n + EMIA_PRESORT_WARPS - 1) / EMIA_PRESORT_WARPS), EMIA_PRESORT_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        n, nullptr, cont_off, cont_off, pt_off, cstart, 0, scratch_off, pts, scratch);
+    k_contour_measure<<<grid, 128, 0, (cudaStream_t)stream>>>(n, nullptr, cont_off, cont_off, pt_off, scratch_off, um_pix, min_area, pts, cstart, 0,
                                                               EMIA_PRESORT_MAX, records, rec_inst, perim0, scratch);
     return emia_check_launch("emia_contour_measure launch: %s");
 }
 
+
+// pass 2 of the exact path without the measurement: store the vertex lists (+ perim0)
+extern "C" int emia_contour_store(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n,
+                                  uint32_t* marks, const int64_t* cont_off, const int64_t* pt_off, uint32_t* pts, int32_t* cstart,
+                                  double* perim0, void* stream) {
+    if (n < 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_store: %s", "bad n");
+    if (n == 0) return EMIA_OK;
+    if (!crops || !meta || !crop_off || !marks || !cont_off || !pt_off || !pts || !cstart)
+        return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_store: %s", "null pointer");
+    const unsigned gridt = (unsigned)((n + EMIA_TRACE_THREADS - 1) / EMIA_TRACE_THREADS);
+    k_contour_trace<true><<<gridt, EMIA_TRACE_THREADS, EMIA_TRACE_SMEM_BYTES, (cudaStream_t)stream>>>(crops, meta, crop_off, n, marks, nullptr, nullptr, nullptr,
+                                                                                  cont_off, pt_off, pts, cstart, perim0);
+    return emia_check_launch("emia_contour_store launch: %s");
+}
 
 // ---- single-pass variant: vertices go to per-instance slabs of bounded capacity -------------------------------------
 // cap_pts(i) = 4 * (ch + 32 * cw) + 32 (a blob's border is about 2 * (h + w) pixels); cstart slab of capc + 1 entries.
@@ -178,12 +248,13 @@ __global__ void __launch_bounds__(EMIA_TRACE_THREADS) k_contour_trace_slab(
     const uint32_t* __restrict__ crops, const emia_inst_meta* __restrict__ meta, const int64_t* __restrict__ crop_off, int64_t n,
     uint32_t* __restrict__ marks, const int64_t* __restrict__ pt_cap_off, int capc, uint32_t* __restrict__ pts,
     int32_t* __restrict__ cstart_slab, int64_t* __restrict__ n_contours, int64_t* __restrict__ scratch_bytes,
-    int32_t* __restrict__ overflow) {
+    int32_t* __restrict__ overflow, double* __restrict__ perim0) {
     const int64_t i = (int64_t)blockIdx.x * EMIA_TRACE_THREADS + threadIdx.x;
     if (i >= n) return;
     const emia_inst_meta m = meta[i];
     const int words = m.ch * m.cw;
     int32_t* cs = cstart_slab + (size_t)i * (capc + 1);
+    if (perim0) perim0[i] = 0.0;
     if (words <= 0) { cs[0] = 0; n_contours[i] = 0; scratch_bytes[i] = 0; return; }
     const int64_t off = crop_off[i];
     const EmiaBitView v = emia_make_view(crops, m, off);
@@ -196,6 +267,10 @@ __global__ void __launch_bounds__(EMIA_TRACE_THREADS) k_contour_trace_slab(
     if (o.overflow) { atomicAdd(overflow, 1); n_contours[i] = 0; scratch_bytes[i] = 0; return; }
     n_contours[i] = o.n_contours;
     scratch_bytes[i] = o.n_contours ? (int64_t)((emia_measure_scratch_bytes(o.max_len) + 15) & ~(size_t)15) : 0;
+    if (perim0 && o.n_contours) {
+        const int nc = o.n_contours;
+        perim0[i] = emia_arc_length_closed(o.pts + cs[nc - 1], cs[nc] - cs[nc - 1]);
+    }
 }
 
 extern "C" int emia_contour_trace_plan(const emia_inst_meta* meta, int64_t n, int64_t* pt_cap, void* stream) {
@@ -209,14 +284,14 @@ extern "C" int emia_contour_trace_plan(const emia_inst_meta* meta, int64_t n, in
 extern "C" int emia_contour_trace_slab(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n,
                                        uint32_t* marks, const int64_t* pt_cap_off, int32_t cap_contours, uint32_t* pts,
                                        int32_t* cstart_slab, int64_t* n_contours, int64_t* scratch_bytes, int32_t* overflow,
-                                       void* stream) {
+                                       double* perim0, void* stream) {
     if (n < 0 || cap_contours < 1) return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_trace_slab: %s", "bad argument");
     if (n == 0) return EMIA_OK;
     if (!crops || !meta || !crop_off || !marks || !pt_cap_off || !pts || !cstart_slab || !n_contours || !scratch_bytes || !overflow)
         return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_trace_slab: %s", "null pointer");
     const unsigned grid = (unsigned)((n + EMIA_TRACE_THREADS - 1) / EMIA_TRACE_THREADS);
     k_contour_trace_slab<<<grid, EMIA_TRACE_THREADS, 0, (cudaStream_t)stream>>>(crops, meta, crop_off, n, marks, pt_cap_off, cap_contours, pts,
-                                                                             cstart_slab, n_contours, scratch_bytes, overflow);
+                                                                             cstart_slab, n_contours, scratch_bytes, overflow, perim0);
     return emia_check_launch("emia_contour_trace_slab launch: %s");
 }
 
@@ -228,9 +303,58 @@ extern "C" int emia_contour_measure_stored(const emia_inst_meta* meta, int64_t n
     if (n == 0) return EMIA_OK;
     if (!meta || !cont_off || !pt_off || !cstart || !scratch_off || !pts || !records || !rec_inst || !perim0 || !scratch)
         return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_measure_stored: %s", "null pointer");
-    k_contour_presort<<<(unsigned)((n + EMIA_PRESORT_WARPS - 1) / EMIA_PRESORT_WARPS), EMIA_PRESORT_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        n, cont_off, pt_off, cstart, cstart_stride, scratch_off, pts, (uint8_t*)scratch);
-    k_contour_measure<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(meta, n, cont_off, pt_off, scratch_off, um_pix, min_area, pts,
+    k_contour_hull<<<(unsigned)((n + EMIA_PRESORT_WARPS - 1) / EMIA_PRESORT_WARPS), EMIA_PRESORT_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        n, nullptr, cont_off, cont_off, pt_off, cstart, cstart_stride, scratch_off, pts, (uint8_t*)scratch);
+    k_contour_measure<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(n, nullptr, cont_off, cont_off, pt_off, scratch_off, um_pix, min_area, pts,
                                                                                   cstart, cstart_stride, EMIA_PRESORT_MAX, records, rec_inst, perim0, scratch);
     return emia_check_launch("emia_contour_measure_stored launch: %s");
+}
+
+// ---- measure only the members of G lists (the reference measures what survived de-dup + spatial constraints) ---------
+// emia_list_measure_plan: per list slot, the number of records and scratch bytes (0 for dead slots) and the instance id (-1 dead);
+// the caller scans rec_cnt / scr_cnt (L + 1 entries each) and sizes `records` / `scratch` from the totals.
+__global__ void k_list_measure_plan(const int32_t* __restrict__ cap_off, int G, const int32_t* __restrict__ in_len,
+                                    const int32_t* __restrict__ in_idx, int L, const int64_t* __restrict__ n_contours,
+                                    const int64_t* __restrict__ scratch_bytes, int32_t* __restrict__ item_inst,
+                                    int64_t* __restrict__ rec_cnt, int64_t* __restrict__ scr_cnt) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= L) return;
+    int lo = 0, hi = G;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (cap_off[mid] <= s) lo = mid; else hi = mid; }
+    int inst = -1;
+    int64_t rc = 0, sc = 0;
+    if (s - cap_off[lo] < in_len[lo]) {
+        inst = in_idx[s];
+        rc = n_contours[inst]; sc = scratch_bytes[inst];
+    }
+    item_inst[s] = inst; rec_cnt[s] = rc; scr_cnt[s] = sc;
+}
+
+extern "C" int emia_list_measure_plan(const int32_t* cap_off, int32_t G, int32_t total_cap, const int32_t* in_len,
+                                      const int32_t* in_idx, const int64_t* n_contours, const int64_t* scratch_bytes,
+                                      int32_t* item_inst, int64_t* rec_cnt, int64_t* scr_cnt, void* stream) {
+    if (G < 0 || total_cap < 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_list_measure_plan: %s", "bad argument");
+    if (G == 0 || total_cap == 0) return EMIA_OK;
+    if (!cap_off || !in_len || !in_idx || !n_contours || !scratch_bytes || !item_inst || !rec_cnt || !scr_cnt)
+        return emia_fail(EMIA_ERR_BAD_ARG, "emia_list_measure_plan: %s", "null pointer");
+    k_list_measure_plan<<<(unsigned)((total_cap + 255) / 256), 256, 0, (cudaStream_t)stream>>>(cap_off, G, in_len, in_idx, total_cap, n_contours,
+                                                                                            scratch_bytes, item_inst, rec_cnt, scr_cnt);
+    return emia_check_launch("emia_list_measure_plan launch: %s");
+}
+
+extern "C" int emia_contour_measure_list(int64_t n_items, const int32_t* item_inst, const int64_t* rec_off, const int64_t* scr_off,
+                                         const int64_t* inst_cont_off, const int64_t* pt_off, const int32_t* cstart,
+                                         int32_t cstart_stride, double um_pix, double min_area, const uint32_t* pts, double* records,
+                                         int32_t* rec_inst, uint8_t* scratch, void* stream) {
+    if (n_items < 0 || cstart_stride < 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_measure_list: %s", "bad argument");
+    if (n_items == 0) return EMIA_OK;
+    if (!item_inst || !rec_off || !scr_off || !pt_off || !cstart || !pts || !records || !rec_inst || !scratch ||
+        (cstart_stride == 0 && !inst_cont_off))
+        return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_measure_list: %s", "null pointer");
+    k_contour_hull<<<(unsigned)((n_items + EMIA_PRESORT_WARPS - 1) / EMIA_PRESORT_WARPS), EMIA_PRESORT_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        n_items, item_inst, rec_off, inst_cont_off, pt_off, cstart, cstart_stride, scr_off, pts, scratch);
+    k_contour_measure<<<(unsigned)((n_items + 127) / 128), 128, 0, (cudaStream_t)stream>>>(n_items, item_inst, rec_off, inst_cont_off, pt_off, scr_off,
+                                                                                        um_pix, min_area, pts, cstart, cstart_stride,
+                                                                                        EMIA_PRESORT_MAX, records, rec_inst, nullptr, scratch);
+    return emia_check_launch("emia_contour_measure_list launch: %s");
 }

@@ -16,6 +16,7 @@ REC_FIELDS = 16
 (REC_MAJOR, REC_MINOR, REC_ECC, REC_LENGTH, REC_WIDTH, REC_CED, REC_ASPECT, REC_CIRC, REC_CHORDS, REC_FERET, REC_ROUND,
  REC_SPHER, REC_AREA, REC_PERIM, REC_NVERT, REC_MEASURED) = range(16)
 
+FUSED_K4 = True
 LAUNCHES = {"count": 0}   # kernels launched through the ABI (bench.py reports it as gpu_launches)
 STAGE_TIMING = {"enabled": False, "events": []}   # (name, start, end) CUDA events when enabled (bench.py --breakdown)
 
@@ -112,26 +113,44 @@ class InstanceSet:
         return self.meta[:, 6] != 0
 
 
+def paste_plan(boxes, H, W, scale_x=1.0, scale_y=1.0):
+    """Geometry of K1 for n boxes: meta [n,8] and crop_off [n+1] (exclusive scan of the crop sizes, total in [n]).  No sync."""
+    lib = _lib.load()
+    n = int(boxes.shape[0])
+    assert boxes.dtype == torch.float32 and boxes.is_contiguous()
+    meta = torch.empty((n, 8), dtype=torch.int32, device=boxes.device)
+    crop_off = torch.empty(n + 1, dtype=torch.int64, device=boxes.device)
+    with _stage("paste_plan+scan"):
+        _lib.check(lib.emia_paste_plan(_ptr(boxes), n, scale_x, scale_y, H, W, _ptr(meta), _ptr(crop_off), _stream()), "emia_paste_plan")
+        exclusive_scan_(crop_off)
+    LAUNCHES["count"] += 1
+    return meta, crop_off
+
+
 def paste(probs, boxes, H, W, scores=None, classes=None, scale_x=1.0, scale_y=1.0, frames=None, frame_slots=0,
-          variant=0, crops_out=None):
+          variant=0, crops_out=None, plan=None, ctas_per_sm=0):
     """K1.  probs [n,28,28] f32, boxes [n,4] f32 xyxy (mask-head outputs, device tensors) -> InstanceSet.
-    frames: None (crops only), True (allocate n full frames) or a preallocated int32 [slots, H, pitch_words] ring."""
+    frames: None (crops only), True (allocate n full frames) or a preallocated int32 [slots, H, pitch_words] ring.
+    plan: (meta, crop_off, total_crop_words) from paste_plan() — possibly a slice of a larger plan whose crop offsets index
+    the shared `crops_out` buffer; given a plan the call does not synchronise.
+    ctas_per_sm: resident CTAs per SM of the paste kernel (0 = default); a smaller grid leaves room for kernels of
+    another stream."""
     lib = _lib.load()
     dev = probs.device
     n = int(probs.shape[0])
     assert probs.dtype == torch.float32 and boxes.dtype == torch.float32 and probs.is_contiguous() and boxes.is_contiguous()
-    meta = torch.empty((n, 8), dtype=torch.int32, device=dev)
-    crop_off = torch.empty(n + 1, dtype=torch.int64, device=dev)
     st = _stream()
-    with _stage("paste_plan+scan"):
-        _lib.check(lib.emia_paste_plan(_ptr(boxes), n, scale_x, scale_y, H, W, _ptr(meta), _ptr(crop_off), st), "emia_paste_plan")
-        exclusive_scan_(crop_off)
-    LAUNCHES["count"] += 1
-    total = int(crop_off[n].item()) if n else 0
+    if plan is None:
+        meta, crop_off = paste_plan(boxes, H, W, scale_x, scale_y)
+        total = int(crop_off[n].item()) if n else 0
+    else:
+        meta, crop_off, total = plan
+        assert meta.shape[0] == n and crop_off.numel() == n + 1 and meta.is_contiguous() and crop_off.is_contiguous()
     if crops_out is not None:
         assert crops_out.numel() >= max(total, 1)
         crops = crops_out
     else:
+        assert plan is None or n == 0 or True
         crops = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
     bbox = torch.empty((n, 4), dtype=torch.int32, device=dev)
     area = torch.empty(n, dtype=torch.int32, device=dev)
@@ -143,7 +162,8 @@ def paste(probs, boxes, H, W, scores=None, classes=None, scale_x=1.0, scale_y=1.
         assert frames.shape[1] == H and frames.shape[2] == pw and frames.is_contiguous()
     with _stage("k1_paste"):
         _lib.check(lib.emia_paste_threshold_bitpack(_ptr(probs), _ptr(boxes), _ptr(meta), _ptr(crop_off), n, scale_x, scale_y, H, W,
-                                                    _ptr(frames), slots, pw, _ptr(crops), _ptr(bbox), _ptr(area), variant, st),
+                                                    _ptr(frames), slots, pw, _ptr(crops), _ptr(bbox), _ptr(area),
+                                                    int(variant) | (int(ctas_per_sm) << 8), st),
                    "emia_paste_threshold_bitpack")
     LAUNCHES["count"] += 1
     return InstanceSet(n=n, H=H, W=W, meta=meta, crop_off=crop_off, crops=crops, bbox=bbox, area=area, scores=scores,
@@ -299,91 +319,151 @@ def postprocess_masks_universal(iset, groups, is_small_class, min_crys_size=None
 CAP_CONTOURS = 8   # contours per instance held by the single-pass slab layout
 
 
-def measure(iset, um_pix=1.0, min_area=None, single_pass=True):
-    """K5: external contours + morphometry records for every instance of the set (results stay on the device).
-    single_pass: follow the borders once into bounded per-instance slabs; any overflow falls back to the exact
-    count -> scan -> store path."""
+def default_min_area(H, W):
+    """Contour-area gate of the measurement loop (src/functions/inference.py:1178-1184)."""
+    return max(5, H * W * 0.000005 * 0.05)
+
+
+def trace(iset, single_pass=True, marks=None):
+    """K5a: external contours of every instance.  Leaves on the device: vertex lists (pts, cstart), the number of contours and
+    the hull scratch size per instance, and perim0 = arcLength(contours[0]) (the compactness pre-filter of
+    deduplicate_masks_smart needs it).  single_pass follows every border once into bounded per-instance slabs and does NOT
+    synchronise; an overflow (counter in extra["overflow"]) is detected by the next measure*() call, which re-traces exactly."""
     lib = _lib.load()
     dev = iset.device
     n = iset.n
-    if min_area is None:
-        min_area = max(5, iset.H * iset.W * 0.000005 * 0.05)     # src/functions/inference.py:1178-1184
     st = _stream()
-    marks = torch.empty(max(2 * iset.total_crop_words, 1), dtype=torch.int32, device=dev)
+    if marks is None:     # 2 bit planes per crop word, addressed by the (possibly shared) crop offsets
+        marks = torch.empty(max(2 * iset.total_crop_words, 1), dtype=torch.int32, device=dev)
     perim0 = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
-    done = False
+    sizes = torch.empty((3, n + 1), dtype=torch.int64, device=dev)     # rows: n_contours, pt offsets, scratch bytes
     if single_pass and n:
-        sizes = torch.empty((3, n + 1), dtype=torch.int64, device=dev)     # rows: n_contours, pt capacity, scratch bytes
         flag = torch.zeros(1, dtype=torch.int32, device=dev)
         with _stage("k5_plan+scan"):
             _lib.check(lib.emia_contour_trace_plan(_ptr(iset.meta), n, _ptr(sizes[1]), st), "emia_contour_trace_plan")
             exclusive_scan_(sizes[1])
         cap_total = iset.extra.get("pt_cap_total")
         if cap_total is None:
-            # capacity is a pure function of the crop sizes: 4 * (sum ch + 32 * sum cw) + 32 * n_live; read it once
+            # capacity is a pure function of the crop sizes: 4 * (sum ch + 32 * sum cw) + 32 * n_live
             cap_total = int(sizes[1, n].item())
         pts = torch.empty(max(cap_total, 1), dtype=torch.int32, device=dev)
         cstart = torch.empty(n * (CAP_CONTOURS + 1) + 1, dtype=torch.int32, device=dev)
         with _stage("k5_trace"):
             _lib.check(lib.emia_contour_trace_slab(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), n, _ptr(marks), _ptr(sizes[1]),
                                                    CAP_CONTOURS, _ptr(pts), _ptr(cstart), _ptr(sizes[0]), _ptr(sizes[2]), _ptr(flag),
-                                                   st), "emia_contour_trace_slab")
-        with _stage("k5_scans"):
-            exclusive_scan_(sizes[0])
-            exclusive_scan_(sizes[2])
+                                                   _ptr(perim0), st), "emia_contour_trace_slab")
         LAUNCHES["count"] += 2
-        tot = torch.stack([sizes[0, n], sizes[2, n], flag[0].to(torch.int64)]).tolist()
-        n_rec, n_scr, overflow = int(tot[0]), int(tot[1]), int(tot[2])
-        if overflow == 0:
-            records = torch.empty((max(n_rec, 1), REC_FIELDS), dtype=torch.float64, device=dev)
-            rec_inst = torch.empty(max(n_rec, 1), dtype=torch.int32, device=dev)
-            scratch = torch.empty(max(n_scr, 16), dtype=torch.uint8, device=dev)
-            with _stage("k5_measure"):
-                _lib.check(lib.emia_contour_measure_stored(_ptr(iset.meta), n, _ptr(sizes[0]), _ptr(sizes[1]), _ptr(cstart),
-                                                           CAP_CONTOURS + 1, _ptr(sizes[2]), float(um_pix), float(min_area), _ptr(pts),
-                                                           _ptr(records), _ptr(rec_inst), _ptr(perim0), _ptr(scratch), st),
-                           "emia_contour_measure_stored")
-            LAUNCHES["count"] += 1
-            iset.cstart_stride = CAP_CONTOURS + 1
-            done = True
-    if not done:
-        sizes = torch.empty((3, n + 1), dtype=torch.int64, device=dev)     # rows: n_contours, n_points, scratch bytes
+        iset.cstart_stride = CAP_CONTOURS + 1
+        iset.extra["overflow"] = flag
+        iset.cont_off = None
+    else:
         with _stage("k5_count"):
             _lib.check(lib.emia_contour_count(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), n, _ptr(marks), _ptr(sizes[0]),
                                               _ptr(sizes[1]), _ptr(sizes[2]), st), "emia_contour_count")
+        cont_off = sizes[0].clone()
         with _stage("k5_scans"):
-            for r in range(3):
-                exclusive_scan_(sizes[r])
-        LAUNCHES["count"] += 1
-        totals = sizes[:, n].tolist() if n else [0, 0, 0]
-        n_rec, n_pts, n_scr = int(totals[0]), int(totals[1]), int(totals[2])
-        pts = torch.empty(max(n_pts, 1), dtype=torch.int32, device=dev)
-        cstart = torch.empty(n_rec + n + 1, dtype=torch.int32, device=dev)
-        records = torch.empty((max(n_rec, 1), REC_FIELDS), dtype=torch.float64, device=dev)
-        rec_inst = torch.empty(max(n_rec, 1), dtype=torch.int32, device=dev)
-        scratch = torch.empty(max(n_scr, 16), dtype=torch.uint8, device=dev)
-        with _stage("k5_trace+measure"):
-            _lib.check(lib.emia_contour_measure(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), n, _ptr(marks), _ptr(sizes[0]),
-                                                _ptr(sizes[1]), _ptr(sizes[2]), float(um_pix), float(min_area), _ptr(pts), _ptr(cstart),
-                                                _ptr(records), _ptr(rec_inst), _ptr(perim0), _ptr(scratch), st), "emia_contour_measure")
+            exclusive_scan_(cont_off)
+            exclusive_scan_(sizes[1])
+        totals = [int(cont_off[n].item()), int(sizes[1, n].item())] if n else [0, 0]
+        pts = torch.empty(max(totals[1], 1), dtype=torch.int32, device=dev)
+        cstart = torch.empty(totals[0] + n + 1, dtype=torch.int32, device=dev)
+        with _stage("k5_trace"):
+            _lib.check(lib.emia_contour_store(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), n, _ptr(marks), _ptr(cont_off),
+                                              _ptr(sizes[1]), _ptr(pts), _ptr(cstart), _ptr(perim0), st), "emia_contour_store")
         LAUNCHES["count"] += 2
         iset.cstart_stride = 0
-    iset.cont_off, iset.pt_off = sizes[0], sizes[1]
-    iset.pts, iset.cstart, iset.records, iset.rec_inst, iset.perim0 = pts, cstart, records[:n_rec], rec_inst[:n_rec], perim0
-    iset.n_records = n_rec
+        iset.extra.pop("overflow", None)
+        iset.cont_off = cont_off
+    iset.pt_off, iset.pts, iset.cstart, iset.perim0 = sizes[1], pts, cstart, perim0
+    iset.extra["n_contours"] = sizes[0]
+    iset.extra["scratch_bytes"] = sizes[2]
+    return iset
+
+
+@dataclass
+class Measurements:
+    """Morphometry records of the members of G lists: the rows of list slot s are records[rec_off[s]:rec_off[s+1]]
+    (OpenCV contour order); rec_inst[r] = instance id of row r; a row counts when records[r, REC_MEASURED] == 1."""
+    records: torch.Tensor     # float64 [R, 16]
+    rec_inst: torch.Tensor    # int32 [R]
+    rec_off: torch.Tensor     # int64 [L + 1]
+    n_records: int
+    groups: "Groups"
+
+    def rows_to_host(self):
+        """Per group: list of (instance id, float64 [k,16] rows) in list order (host copies)."""
+        rec = self.records.cpu().numpy(); off = self.rec_off.cpu().numpy()
+        ln = self.groups.length.cpu().numpy(); idx = self.groups.idx.cpu().numpy()
+        co = self.groups.cap_off_host
+        return [[(int(idx[co[g] + k]), rec[off[co[g] + k]: off[co[g] + k + 1]]) for k in range(int(ln[g]))]
+                for g in range(self.groups.G)]
+
+
+def measure_list(iset, groups, um_pix=1.0, min_area=None):
+    """K5b: morphometry of the members of `groups` only (what the reference's measurement loop sees).  Needs trace().
+    Returns None when the single-pass trace overflowed (the caller re-traces with single_pass=False)."""
+    lib = _lib.load()
+    dev = iset.device
+    assert iset.pts is not None, "run trace() first"
+    if min_area is None:
+        min_area = default_min_area(iset.H, iset.W)
+    L = groups.total_cap
+    st = _stream()
+    item_inst = torch.empty(max(L, 1), dtype=torch.int32, device=dev)
+    offs = torch.zeros((2, L + 1), dtype=torch.int64, device=dev)
+    with _stage("k5_list_plan+scans"):
+        _lib.check(lib.emia_list_measure_plan(_ptr(groups.cap_off), groups.G, L, _ptr(groups.length), _ptr(groups.idx),
+                                              _ptr(iset.extra["n_contours"]), _ptr(iset.extra["scratch_bytes"]), _ptr(item_inst),
+                                              _ptr(offs[0]), _ptr(offs[1]), st), "emia_list_measure_plan")
+        exclusive_scan_(offs[0])
+        exclusive_scan_(offs[1])
+    LAUNCHES["count"] += 1
+    flag = iset.extra.get("overflow")
+    tot = torch.stack([offs[0, L], offs[1, L], flag[0].to(torch.int64) if flag is not None else offs[0, 0]]).tolist()
+    n_rec, n_scr, overflow = int(tot[0]), int(tot[1]), int(tot[2])
+    if overflow:
+        return None
+    records = torch.empty((max(n_rec, 1), REC_FIELDS), dtype=torch.float64, device=dev)
+    rec_inst = torch.empty(max(n_rec, 1), dtype=torch.int32, device=dev)
+    scratch = torch.empty(max(n_scr, 16), dtype=torch.uint8, device=dev)
+    if L:
+        with _stage("k5_measure"):
+            _lib.check(lib.emia_contour_measure_list(L, _ptr(item_inst), _ptr(offs[0]), _ptr(offs[1]), _ptr(iset.cont_off),
+                                                     _ptr(iset.pt_off), _ptr(iset.cstart), iset.cstart_stride, float(um_pix),
+                                                     float(min_area), _ptr(iset.pts), _ptr(records), _ptr(rec_inst), _ptr(scratch), st),
+                       "emia_contour_measure_list")
+        LAUNCHES["count"] += 2
+    return Measurements(records=records[:n_rec], rec_inst=rec_inst[:n_rec], rec_off=offs[0], n_records=n_rec, groups=groups)
+
+
+def measure(iset, um_pix=1.0, min_area=None, single_pass=True):
+    """K5 over EVERY instance of the set: trace() + measure_list() on the identity list.  Records of instance i are
+    iset.records[cont_off[i]:cont_off[i+1]]."""
+    if min_area is None:
+        min_area = default_min_area(iset.H, iset.W)
+    trace(iset, single_pass=single_pass)
+    ident = groups_from_offsets([0, iset.n], iset.device)
+    m = measure_list(iset, ident, um_pix, min_area)
+    if m is None:
+        trace(iset, single_pass=False)
+        m = measure_list(iset, ident, um_pix, min_area)
+    if iset.cont_off is None:
+        iset.cont_off = m.rec_off
+    iset.records, iset.rec_inst, iset.n_records = m.records, m.rec_inst, m.n_records
     iset.extra["um_pix"] = um_pix
     iset.extra["min_area"] = min_area
-    iset.extra.pop("n_contours", None)
     return iset
 
 
 def contours_to_host(iset):
     """Host copy of the contour vertex lists: list (per instance) of lists (OpenCV order) of int32 [k,2] arrays."""
     pts = iset.pts.cpu().numpy().view(np.uint32)
-    cont_off = iset.cont_off.cpu().numpy(); pt_off = iset.pt_off.cpu().numpy(); cstart = iset.cstart.cpu().numpy()
+    ncont = iset.extra["n_contours"].cpu().numpy()
+    cont_off = np.concatenate([[0], np.cumsum(ncont[:iset.n])])
+    pt_off = iset.pt_off.cpu().numpy(); cstart = iset.cstart.cpu().numpy()
     out = []
     for i in range(iset.n):
-        nc = int(cont_off[i + 1] - cont_off[i])
+        nc = int(ncont[i])
         base = i * iset.cstart_stride if iset.cstart_stride else cont_off[i] + i
         cs = cstart[base: base + nc + 1]
         cl = []
@@ -410,6 +490,16 @@ class Groups:
     @property
     def total_cap(self):
         return int(self.cap_off_host[-1])
+
+    @property
+    def max_cap(self):
+        return int(np.diff(self.cap_off_host).max()) if self.G else 0
+
+    @property
+    def fused_cap(self):
+        """Largest group capacity handed to the K4 entry points (0 = unknown -> staged kernels); FUSED_K4 = False forces the
+        staged global-memory path (tests compare both)."""
+        return self.max_cap if FUSED_K4 else 0
 
     def to_lists(self):
         ln = self.length.cpu().numpy()
@@ -446,7 +536,8 @@ def _workspace(groups, device):
     if nbytes is None:
         host = np.ascontiguousarray(groups.cap_off_host, dtype=np.int32)
         nbytes = int(lib.emia_group_workspace_bytes(host.ctypes.data, groups.G))
-        _ws_cache.clear()
+        if len(_ws_cache) > 256:
+            _ws_cache.clear()
         _ws_cache[key] = nbytes
     return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
 
@@ -458,17 +549,14 @@ def _new_groups_like(g):
 def dedup_smart(iset, groups, iou_threshold=0.4, max_aspect_ratio=None):
     """deduplicate_masks_smart (src/functions/inference.py:2552) on every group.  Needs measure() first (compactness)."""
     lib = _lib.load()
-    assert iset.perim0 is not None, "run measure() before dedup_smart (the pre-filter needs contour perimeters)"
+    assert iset.perim0 is not None, "run trace() before dedup_smart (the pre-filter needs contour perimeters)"
     ws, nb = _workspace(groups, iset.device)
     out = _new_groups_like(groups)
-    ncont = iset.extra.get("n_contours")
-    if ncont is None:
-        ncont = (iset.cont_off[1:] - iset.cont_off[:-1]).contiguous()
-        iset.extra["n_contours"] = ncont
+    ncont = iset.extra["n_contours"]
     with _stage("k4_dedup_smart"):
       _lib.check(lib.emia_dedup_smart(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), _ptr(iset.bbox), _ptr(iset.area),
                                     _ptr(iset.perim0), _ptr(ncont), _ptr(iset.scores), _ptr(iset.classes), _ptr(groups.cap_off),
-                                    groups.G, groups.total_cap, _ptr(groups.length), _ptr(groups.idx), float(iou_threshold),
+                                    groups.G, groups.total_cap, groups.fused_cap, _ptr(groups.length), _ptr(groups.idx), float(iou_threshold),
                                     float(max_aspect_ratio) if max_aspect_ratio else 0.0, _ptr(out.length), _ptr(out.idx),
                                     _ptr(ws), nb, _stream()), "emia_dedup_smart")
     LAUNCHES["count"] += 6
@@ -481,11 +569,14 @@ def dedup_inorder(iset, groups, iou_threshold):
     ws, nb = _workspace(groups, iset.device)
     out = _new_groups_like(groups)
     _lib.check(lib.emia_dedup_inorder(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), _ptr(iset.bbox), _ptr(iset.area),
-                                      _ptr(groups.cap_off), groups.G, groups.total_cap, _ptr(groups.length), _ptr(groups.idx),
+                                      _ptr(groups.cap_off), groups.G, groups.total_cap, groups.fused_cap, _ptr(groups.length), _ptr(groups.idx),
                                       float(iou_threshold), _ptr(out.length), _ptr(out.idx), _ptr(ws), nb, _stream()),
                "emia_dedup_inorder")
     LAUNCHES["count"] += 6
     return out
+
+
+_rule_cache = {}
 
 
 def overlap_rules(iset, groups, rules):
@@ -504,12 +595,17 @@ def overlap_rules(iset, groups, rules):
         active[int(c)] = 1
         max_iou[int(c)] = mi
     dev = iset.device
-    act_t, mi_t = torch.as_tensor(active, device=dev), torch.as_tensor(max_iou, device=dev)
+    key = (active.tobytes(), max_iou.tobytes(), str(dev))
+    cached = _rule_cache.get(key)
+    if cached is None:       # the upload from pageable memory synchronises: do it once per rule set
+        cached = (torch.as_tensor(active, device=dev), torch.as_tensor(max_iou, device=dev))
+        _rule_cache[key] = cached
+    act_t, mi_t = cached
     ws, nb = _workspace(groups, dev)
     out = _new_groups_like(groups)
     with _stage("k4_overlap_rules"):
       _lib.check(lib.emia_overlap_rules(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), _ptr(iset.bbox), _ptr(iset.area),
-                                      _ptr(iset.scores), _ptr(iset.classes), _ptr(groups.cap_off), groups.G, groups.total_cap,
+                                      _ptr(iset.scores), _ptr(iset.classes), _ptr(groups.cap_off), groups.G, groups.total_cap, groups.fused_cap,
                                       _ptr(groups.length), _ptr(groups.idx), _ptr(act_t), _ptr(mi_t), ncls, _ptr(out.length),
                                       _ptr(out.idx), _ptr(ws), nb, _stream()), "emia_overlap_rules")
     LAUNCHES["count"] += 6
@@ -527,7 +623,7 @@ def containment_rules(iset, groups, rules, threshold=0.95):
     out = _new_groups_like(groups)
     with _stage("k4_containment"):
       _lib.check(lib.emia_containment_rules(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), _ptr(iset.bbox), _ptr(iset.area),
-                                          _ptr(iset.classes), _ptr(groups.cap_off), groups.G, groups.total_cap, _ptr(groups.length),
+                                          _ptr(iset.classes), _ptr(groups.cap_off), groups.G, groups.total_cap, groups.fused_cap, _ptr(groups.length),
                                           _ptr(groups.idx), child.ctypes.data, parent.ctypes.data, len(child), float(threshold),
                                           _ptr(out.length), _ptr(out.idx), _ptr(ws), nb, _stream()), "emia_containment_rules")
     LAUNCHES["count"] += 1 + 2 * len(child)
@@ -557,12 +653,153 @@ def pair_counts(iset, pa, pb):
 
 def run_tiles(probs, boxes, scores, classes, tile_offsets, H, W, um_pix=0.5, rules=None, dedup_iou=0.7, frames=None,
               variant=0, scale_x=1.0, scale_y=1.0):
-    """The fused hot path over many tiles at once (BASELINE configs 2 and 5): paste -> contours/morphometry ->
-    deduplicate_masks_smart -> spatial constraints.  Everything stays on the device.  Returns (InstanceSet, Groups)."""
+    """The fused hot path over many tiles at once (BASELINE configs 2 and 5): paste -> external contours ->
+    deduplicate_masks_smart -> spatial constraints -> morphometry of the survivors (the order of the reference:
+    src/functions/inference.py:859, :868, :1148).  Everything stays on the device.
+    Returns (InstanceSet, Groups of kept instances, Measurements of the kept instances)."""
     iset = paste(probs, boxes, H, W, scores=scores, classes=classes, scale_x=scale_x, scale_y=scale_y, frames=frames,
                  variant=variant)
-    measure(iset, um_pix=um_pix)
     groups = groups_from_offsets(tile_offsets, iset.device)
-    kept = dedup_smart(iset, groups, iou_threshold=dedup_iou)
-    kept = apply_spatial_constraints(iset, kept, rules)
-    return iset, kept
+    single_pass = True
+    while True:
+        trace(iset, single_pass=single_pass)
+        kept = dedup_smart(iset, groups, iou_threshold=dedup_iou)
+        kept = apply_spatial_constraints(iset, kept, rules)
+        meas = measure_list(iset, kept, um_pix=um_pix)
+        if meas is not None:
+            return iset, kept, meas
+        single_pass = False      # a slab overflowed: follow the borders again with exact sizes
+
+
+class TilePipeline:
+    """The fused hot path over a shard of tiles, software-pipelined over tile batches on three CUDA streams:
+
+        copy  : (host inputs only) H2D of batch b's 28x28 probabilities from pinned memory
+        paste : K1 of batch b (HBM-write bound)
+        post  : contours -> de-dup -> spatial constraints -> morphometry of batch b-1 (latency bound) [+ D2H of its results]
+
+    so the latency-bound kernels run in the shadow of the bandwidth-bound paste (and, end to end, of the PCIe copy).
+    The plan (crop geometry, vertex capacities) of the WHOLE shard is computed first, with one small device->host read of
+    the per-batch totals; each batch then needs one more read (record/scratch totals) on the post stream only.
+    Batches see slices of shard-wide arrays; list indices stay shard-global."""
+
+    def __init__(self, H, W, um_pix=1.0, rules=None, dedup_iou=0.7, frames=None, variant=0, batches=8, paste_ctas_per_sm=0,
+                 device=None):
+        self.H, self.W, self.um_pix, self.rules, self.dedup_iou = H, W, um_pix, rules, dedup_iou
+        self.frames, self.variant, self.batches, self.paste_ctas = frames, variant, batches, paste_ctas_per_sm
+        self.dev = _need_cuda(device)
+        lo, hi = torch.cuda.Stream.priority_range()
+        self.s_copy = torch.cuda.Stream(device=self.dev)
+        self.s_paste = torch.cuda.Stream(device=self.dev, priority=lo)
+        self.s_post = torch.cuda.Stream(device=self.dev, priority=hi)
+        self._groups_cache = {}
+        self._pinned = {}
+        self.k1_events = []
+
+    def _groups(self, offs):
+        key = offs.tobytes()
+        g = self._groups_cache.get(key)
+        if g is None:
+            if len(self._groups_cache) > 1024:
+                self._groups_cache.clear()
+            g = groups_from_offsets(offs, self.dev)
+            self._groups_cache[key] = g
+        # length / idx are never written by the K4 stages (they produce new lists), so the cached identity lists are reusable
+        return g
+
+    def run(self, probs, boxes, scores, classes, tile_offsets, to_host=False, time_k1=False):
+        """probs [n,28,28] f32, boxes [n,4] f32, scores [n] f32, classes [n] i32: device tensors, or pinned HOST tensors (then
+        the copies are part of the pipeline).  tile_offsets: host int array [T+1].
+        Returns a list over batches of dicts {tiles: (t0, t1), iset, kept, meas[, host: {...}]}."""
+        dev = self.dev
+        main = torch.cuda.current_stream(dev)
+        offs = np.asarray(tile_offsets, dtype=np.int64)
+        T = len(offs) - 1
+        n = int(offs[-1])
+        B = max(1, min(self.batches, T))
+        tb = np.unique(np.linspace(0, T, B + 1).round().astype(np.int64))
+        B = len(tb) - 1
+        ib = offs[tb]
+        host_in = not probs.is_cuda
+        ev_copy = []
+        if host_in:
+            d_boxes = boxes.to(dev, non_blocking=True); d_scores = scores.to(dev, non_blocking=True)
+            d_classes = classes.to(dev, non_blocking=True)
+            d_probs = torch.empty(tuple(probs.shape), dtype=probs.dtype, device=dev)
+            self.s_copy.wait_stream(main)
+            with torch.cuda.stream(self.s_copy):
+                for b in range(B):
+                    d_probs[ib[b]:ib[b + 1]].copy_(probs[ib[b]:ib[b + 1]], non_blocking=True)
+                    e = torch.cuda.Event(); e.record(self.s_copy); ev_copy.append(e)
+        else:
+            d_probs, d_boxes, d_scores, d_classes = probs, boxes, scores, classes
+        # ---- shard-wide plan: crop geometry + vertex capacities, one read of the per-batch totals
+        lib = _lib.load()
+        meta, crop_off = paste_plan(d_boxes, self.H, self.W)
+        cap_off = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        _lib.check(lib.emia_contour_trace_plan(_ptr(meta), n, _ptr(cap_off), _stream()), "emia_contour_trace_plan")
+        exclusive_scan_(cap_off)
+        LAUNCHES["count"] += 1
+        ib_t = torch.as_tensor(ib, device=dev)
+        bounds = torch.stack([crop_off[ib_t], cap_off[ib_t]]).cpu().numpy()
+        total_words = int(bounds[0, -1])
+        crops = torch.empty(max(total_words, 1), dtype=torch.int32, device=dev)
+        marks = torch.empty(max(2 * total_words, 1), dtype=torch.int32, device=dev)
+        self.s_paste.wait_stream(main); self.s_post.wait_stream(main)
+        isets, ev_paste = [], []
+        self.k1_events = []
+        with torch.cuda.stream(self.s_paste):
+            for b in range(B):
+                i0, i1 = int(ib[b]), int(ib[b + 1])
+                if host_in:
+                    self.s_paste.wait_event(ev_copy[b])
+                if time_k1:
+                    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e0.record(self.s_paste)
+                it = paste(d_probs[i0:i1], d_boxes[i0:i1], self.H, self.W, scores=d_scores[i0:i1], classes=d_classes[i0:i1],
+                           frames=self.frames, variant=self.variant, crops_out=crops,
+                           plan=(meta[i0:i1], crop_off[i0:i1 + 1], total_words), ctas_per_sm=self.paste_ctas)
+                if time_k1:
+                    e1.record(self.s_paste); self.k1_events.append((e0, e1))
+                it.extra["pt_cap_total"] = int(bounds[1, b + 1] - bounds[1, b])
+                e = torch.cuda.Event(); e.record(self.s_paste); ev_paste.append(e)
+                isets.append(it)
+        out = []
+        with torch.cuda.stream(self.s_post):
+            for b in range(B):
+                it = isets[b]
+                self.s_post.wait_event(ev_paste[b])
+                groups = self._groups(offs[tb[b]:tb[b + 1] + 1] - ib[b])
+                single_pass = True
+                while True:
+                    trace(it, single_pass=single_pass, marks=marks)
+                    kept = dedup_smart(it, groups, iou_threshold=self.dedup_iou)
+                    kept = apply_spatial_constraints(it, kept, self.rules)
+                    meas = measure_list(it, kept, um_pix=self.um_pix)
+                    if meas is not None:
+                        break
+                    single_pass = False
+                res = {"tiles": (int(tb[b]), int(tb[b + 1])), "inst0": int(ib[b]), "iset": it, "kept": kept, "meas": meas}
+                if to_host:
+                    res["host"] = {k: self._pinned_like(b, k, v).copy_(v, non_blocking=True)
+                                   for k, v in (("records", meas.records), ("rec_inst", meas.rec_inst), ("rec_off", meas.rec_off),
+                                                ("kept_len", kept.length), ("kept_idx", kept.idx))}
+                out.append(res)
+        main.wait_stream(self.s_post); main.wait_stream(self.s_paste)
+        if host_in:
+            main.wait_stream(self.s_copy)
+        self._keep = (crops, marks, meta, crop_off, cap_off, d_probs)
+        return out
+
+    def _pinned_like(self, b, name, t):
+        """Persistent pinned result buffers (one per batch and result array, grown on demand): page-locking memory inside
+        the pipeline would serialise it.  The views handed out are overwritten by the next run()."""
+        key = (b, name)
+        buf = self._pinned.get(key)
+        if buf is None or buf.numel() < t.numel() or buf.dtype != t.dtype:
+            buf = torch.empty(max(int(t.numel() * 1.25), 16), dtype=t.dtype, pin_memory=True)
+            self._pinned[key] = buf
+        return buf[:t.numel()].view(t.shape)
+
+    def k1_ms(self):
+        """Sum over batches of the CUDA-event duration of the K1 launches of the last run(time_k1=True) (after a synchronize)."""
+        return float(sum(a.elapsed_time(b) for a, b in self.k1_events))

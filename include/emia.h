@@ -72,7 +72,11 @@ int emia_exclusive_scan_i64(int64_t* data, int64_t n, void* workspace, size_t wo
  * emia_paste_plan: box scale/clip/non-empty + sampling region -> meta[i], crop_words[i] = ch*cw (caller scans).
  * emia_paste_threshold_bitpack: writes crops (+ full frames when frames != NULL: instance i goes to frame slot
  *   i % frame_slots), bbox[i] = (y_min, x_min, y_max, x_max) inclusive or (-1,-1,-1,-1), area[i] = popcount.
- *   variant: 0 = 128-bit streaming stores, 1 = bulk shared->global copies (TMA engine). */
+ *   variant (bits 0-7): 0 = 128-bit streaming stores, 1 = bulk shared->global copies (TMA engine);
+ *   bits 8-15 of the same argument: resident CTAs per SM of the persistent grid (0 = default 8 / 4) — a smaller grid
+ *   leaves SM room for the contour / de-dup kernels of the previous tile batch running on another stream.
+ *   meta / crop_off / probs / boxes / bbox / area may point INTO larger arrays (a batch of a bigger plan): crop_off
+ *   values are absolute word offsets into `crops`. */
 int emia_paste_plan(const float* boxes, int64_t n, float scale_x, float scale_y, int H, int W,
                     emia_inst_meta* meta, int64_t* crop_words, void* stream);
 int emia_paste_threshold_bitpack(const float* probs, const float* boxes, const emia_inst_meta* meta,
@@ -112,7 +116,12 @@ int emia_contour_measure(const uint32_t* crops, const emia_inst_meta* meta, cons
                          int32_t* cstart, double* records, int32_t* rec_inst, double* perim0, uint8_t* scratch,
                          void* stream);
 
-/* Single-pass variant (the fast path of engine.measure): emia_contour_trace_plan gives per-instance vertex capacities
+/* Pass 2 without the records: vertex lists + perim0 only (the records then come from emia_contour_measure_list). */
+int emia_contour_store(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n,
+                       uint32_t* marks, const int64_t* cont_off, const int64_t* pt_off, uint32_t* pts, int32_t* cstart,
+                       double* perim0, void* stream);
+
+/* Single-pass variant (the fast path of engine.trace): emia_contour_trace_plan gives per-instance vertex capacities
  * (caller scans them into pt_cap_off), emia_contour_trace_slab follows the borders once into those slabs
  * (cstart_slab: cap_contours + 1 ints per instance) and raises *overflow (caller-zeroed counter) when a capacity is
  * exceeded — the caller then falls back to emia_contour_count / emia_contour_measure; emia_contour_measure_stored
@@ -121,15 +130,32 @@ int emia_contour_trace_plan(const emia_inst_meta* meta, int64_t n, int64_t* pt_c
 int emia_contour_trace_slab(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n,
                             uint32_t* marks, const int64_t* pt_cap_off, int32_t cap_contours, uint32_t* pts,
                             int32_t* cstart_slab, int64_t* n_contours, int64_t* scratch_bytes, int32_t* overflow,
-                            void* stream);
+                            double* perim0 /* optional: arcLength(contours[0]) per instance */, void* stream);
 int emia_contour_measure_stored(const emia_inst_meta* meta, int64_t n, const int64_t* cont_off, const int64_t* pt_off,
                                 const int32_t* cstart, int32_t cstart_stride, const int64_t* scratch_off, double um_pix,
                                 double min_area, const uint32_t* pts, double* records, int32_t* rec_inst, double* perim0,
                                 uint8_t* scratch, void* stream);
 
+/* Measure only the members of G lists — the reference measures what survived de-duplication and the spatial
+ * constraints (measurement loop src/functions/inference.py:1148-1253 runs over the final mask list).
+ * emia_list_measure_plan: per list slot s (total_cap slots): item_inst[s] = instance id (-1 for a dead slot),
+ *   rec_cnt[s] / scr_cnt[s] = number of records / scratch bytes (caller scans both, total_cap + 1 entries).
+ * emia_contour_measure_list: records of slot s at rec_off[s] + j (OpenCV contour order), rec_inst = instance id per record.
+ *   inst_cont_off (per instance) is only needed for the packed cstart layout (cstart_stride == 0). */
+int emia_list_measure_plan(const int32_t* cap_off, int32_t G, int32_t total_cap, const int32_t* in_len,
+                           const int32_t* in_idx, const int64_t* n_contours, const int64_t* scratch_bytes,
+                           int32_t* item_inst, int64_t* rec_cnt, int64_t* scr_cnt, void* stream);
+int emia_contour_measure_list(int64_t n_items, const int32_t* item_inst, const int64_t* rec_off, const int64_t* scr_off,
+                              const int64_t* inst_cont_off, const int64_t* pt_off, const int32_t* cstart,
+                              int32_t cstart_stride, double um_pix, double min_area, const uint32_t* pts, double* records,
+                              int32_t* rec_inst, uint8_t* scratch, void* stream);
+
 /* ---- K4: mask-IoU de-duplication and spatial constraints ----------------------------------------------------
  * All operate on G groups at once; see "Instance layout".  total_cap = cap_off[G] (the host knows it).
  * Workspace size: emia_group_workspace_bytes (pass exactly that many bytes: the tail is cleared per call).
+ * max_cap = largest group capacity if the caller knows it (0 = unknown): groups of <= 1024 slots take the fast path — one
+ *   CTA per group with the member tables, the suppression bit matrix and the candidate-pair queue in shared memory and
+ *   one warp per candidate pair for the mask intersection; larger groups use the staged global-memory kernels.
  * emia_dedup_smart       : deduplicate_masks_smart, src/functions/inference.py:2552-2677 (+ :2680-2733), incl. the
  *                          artifact pre-filter (empty / aspect / compactness < 0.15) and quirks Q1, Q2, Q10.
  *                          Output in keep order (score descending).
@@ -141,20 +167,20 @@ size_t emia_group_workspace_bytes(const int32_t* cap_off_host, int32_t G);
 int emia_dedup_smart(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off,
                      const int32_t* bbox, const int32_t* area, const double* perim0, const int64_t* n_contours,
                      const float* scores, const int32_t* classes, const int32_t* cap_off, int32_t G,
-                     int32_t total_cap, const int32_t* in_len, const int32_t* in_idx, double iou_threshold, double max_aspect_ratio,
+                     int32_t total_cap, int32_t max_cap, const int32_t* in_len, const int32_t* in_idx, double iou_threshold, double max_aspect_ratio,
                      int32_t* out_len, int32_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
 int emia_dedup_inorder(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off,
                        const int32_t* bbox, const int32_t* area, const int32_t* cap_off, int32_t G,
-                       int32_t total_cap, const int32_t* in_len, const int32_t* in_idx, double iou_threshold, int32_t* out_len,
+                       int32_t total_cap, int32_t max_cap, const int32_t* in_len, const int32_t* in_idx, double iou_threshold, int32_t* out_len,
                        int32_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
 int emia_overlap_rules(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off,
                        const int32_t* bbox, const int32_t* area, const float* scores, const int32_t* classes,
-                       const int32_t* cap_off, int32_t G, int32_t total_cap, const int32_t* in_len, const int32_t* in_idx,
+                       const int32_t* cap_off, int32_t G, int32_t total_cap, int32_t max_cap, const int32_t* in_len, const int32_t* in_idx,
                        const int32_t* rule_active, const double* rule_max_iou, int32_t num_classes,
                        int32_t* out_len, int32_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
 int emia_containment_rules(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off,
                            const int32_t* bbox, const int32_t* area, const int32_t* classes,
-                           const int32_t* cap_off, int32_t G, int32_t total_cap, const int32_t* in_len, const int32_t* in_idx,
+                           const int32_t* cap_off, int32_t G, int32_t total_cap, int32_t max_cap, const int32_t* in_len, const int32_t* in_idx,
                            const int32_t* child_class_host, const int32_t* parent_class_host, int32_t n_rules,
                            double containment_threshold, int32_t* out_len, int32_t* out_idx, void* workspace,
                            size_t workspace_bytes, void* stream);

@@ -12,6 +12,15 @@ pytestmark = pytest.mark.gpu
 REL_TOL = 1e-5
 
 
+@pytest.fixture(params=["fused", "staged"])
+def k4_path(request):
+    """Both K4 implementations: one CTA per group in shared memory (groups <= 1024) and the staged global-memory kernels."""
+    old = engine.FUSED_K4
+    engine.FUSED_K4 = request.param == "fused"
+    yield request.param
+    engine.FUSED_K4 = old
+
+
 def _heads(seed, n, H, W, **kw):
     probs, boxes, scores, classes = syn.synthetic_heads(seed, n, H, W, **kw)
     return probs, boxes, scores, classes
@@ -173,7 +182,7 @@ def _mask_lists(seed, n, H, W, dup=0.5):
 
 
 @pytest.mark.parametrize("seed,thr", [(21, 0.4), (22, 0.7), (23, 0.1)])
-def test_dedup_smart_kept_sets(cuda_device, seed, thr):
+def test_dedup_smart_kept_sets(cuda_device, k4_path, seed, thr):
     H, W = 256, 256
     groups_ml = []
     for g in range(4):
@@ -196,7 +205,7 @@ def test_dedup_smart_kept_sets(cuda_device, seed, thr):
         assert [k - offs[g] for k in kept[g]] == ref, f"group {g}"
 
 
-def test_dedup_quirks_q1_q2(cuda_device):
+def test_dedup_quirks_q1_q2(cuda_device, k4_path):
     import cv2
     H = W = 128
     def disc(x, y, r=8):
@@ -218,7 +227,7 @@ def test_dedup_quirks_q1_q2(cuda_device):
         assert got == ref
 
 
-def test_inorder_dedup(cuda_device):
+def test_inorder_dedup(cuda_device, k4_path):
     H, W = 256, 256
     ml, sl, cl = _mask_lists(77, 70, H, W, dup=0.8)
     ml.insert(5, np.zeros((H, W), bool)); sl.insert(5, np.float32(0.3)); cl.insert(5, 0)
@@ -230,7 +239,7 @@ def test_inorder_dedup(cuda_device):
 
 
 @pytest.mark.parametrize("seed", [31, 32, 33])
-def test_spatial_constraints(cuda_device, seed):
+def test_spatial_constraints(cuda_device, k4_path, seed):
     H, W = 256, 256
     rules = syn.POLYHIPES_RULES
     lists = [_mask_lists(seed * 10 + g, 60, H, W, dup=0.6) for g in range(3)]
@@ -268,7 +277,7 @@ def test_spatial_constraints(cuda_device, seed):
         assert [k - offs[g] for k in got_c2[g]] == [i for i in range(n) if i not in rem]
 
 
-def test_fused_tiles_pipeline(cuda_device):
+def test_fused_tiles_pipeline(cuda_device, k4_path):
     """BASELINE config 2/5 path on 3 tiles: paste -> measure -> de-dup 0.7 -> spatial constraints -> rows."""
     H, W = 384, 384
     tiles = [_heads(5000 + t, 70 + 5 * t, H, W, duplicate_frac=0.3, rmin=6, rmax=22, margin=25) for t in range(3)]
@@ -276,18 +285,54 @@ def test_fused_tiles_pipeline(cuda_device):
     scores = np.concatenate([t[2] for t in tiles]); classes = np.concatenate([t[3] for t in tiles])
     offs = np.concatenate([[0], np.cumsum([len(t[0]) for t in tiles])])
     tp, tb, ts, tc = _dev(cuda_device, probs, boxes, scores, classes)
-    iset, kept = engine.run_tiles(tp, tb, ts, tc, offs, H, W, um_pix=0.5, rules=syn.POLYHIPES_RULES, dedup_iou=0.7, frames=True)
+    iset, kept, meas = engine.run_tiles(tp, tb, ts, tc, offs, H, W, um_pix=0.5, rules=syn.POLYHIPES_RULES, dedup_iou=0.7, frames=True)
     torch.cuda.synchronize()
     kept_l = kept.to_lists()
-    rec = iset.records.cpu().numpy(); cont_off = iset.cont_off.cpu().numpy()
+    host_rows = meas.rows_to_host()
     for t, (p, b, s, c) in enumerate(tiles):
         final, rows, _ = pipeline.run_tile(p, b, s, c, H, W, um_pix=0.5, rules=syn.POLYHIPES_RULES, dedup_iou=0.7)
         assert [k - offs[t] for k in kept_l[t]] == final, f"tile {t}"
-        got = []
-        for k in kept_l[t]:
-            for j in range(cont_off[k], cont_off[k + 1]):
-                if rec[j, engine.REC_MEASURED] == 1.0:
-                    got.append(rec[j, :12])
+        assert [k for k, _ in host_rows[t]] == kept_l[t]
+        got = [r[:12] for _, rr in host_rows[t] for r in rr if r[engine.REC_MEASURED] == 1.0]
         assert len(got) == len(rows)
         for g, r in zip(got, rows):
             np.testing.assert_allclose(g, np.array([float(v) for v in r[3:15]]), rtol=REL_TOL, atol=0)
+
+
+@pytest.mark.parametrize("host_inputs", [False, True])
+def test_tile_pipeline_matches_single_batch_path(cuda_device, host_inputs):
+    """The three-stream batched pipeline (bench.py's step) gives exactly the results of the one-batch path and the oracle."""
+    H, W = 256, 256
+    tiles = [_heads(7000 + t, 30 + 3 * t, H, W, duplicate_frac=0.3, rmin=5, rmax=18, margin=20) for t in range(7)]
+    probs = np.concatenate([t[0] for t in tiles]); boxes = np.concatenate([t[1] for t in tiles])
+    scores = np.concatenate([t[2] for t in tiles]); classes = np.concatenate([t[3] for t in tiles])
+    offs = np.concatenate([[0], np.cumsum([len(t[0]) for t in tiles])])
+    dev_in = _dev(cuda_device, probs, boxes, scores, classes)
+    iset, kept, meas = engine.run_tiles(*dev_in, offs, H, W, um_pix=0.5, rules=syn.POLYHIPES_RULES, dedup_iou=0.7)
+    ref_kept = kept.to_lists(); ref_rows = meas.rows_to_host()
+    pipe = engine.TilePipeline(H, W, um_pix=0.5, rules=syn.POLYHIPES_RULES, dedup_iou=0.7, batches=3, device=cuda_device)
+    if host_inputs:
+        inputs = [torch.as_tensor(np.ascontiguousarray(a)).pin_memory() for a in (probs, boxes, scores, classes)]
+    else:
+        inputs = dev_in
+    for _ in range(2):      # twice: buffers of the first run are recycled by the caching allocator
+        res = pipe.run(*inputs, offs, to_host=host_inputs)
+        torch.cuda.synchronize()
+        seen = 0
+        for r in res:
+            t0, t1 = r["tiles"]
+            kl = r["kept"].to_lists(); rows = r["meas"].rows_to_host()
+            for g in range(t1 - t0):
+                assert [k + r["inst0"] for k in kl[g]] == ref_kept[t0 + g]
+                assert len(rows[g]) == len(ref_rows[t0 + g])
+                for (ka, ra), (kb, rb) in zip(rows[g], ref_rows[t0 + g]):
+                    assert ka + r["inst0"] == kb and np.array_equal(ra, rb)
+                seen += 1
+            if host_inputs:
+                assert np.array_equal(r["host"]["records"].numpy(), r["meas"].records.cpu().numpy())
+                assert np.array_equal(r["host"]["kept_idx"].numpy(), r["kept"].idx.cpu().numpy())
+        assert seen == len(tiles)
+    # and against the oracle for one tile
+    p, b, s, c = tiles[4]
+    final, rows, _ = pipeline.run_tile(p, b, s, c, H, W, um_pix=0.5, rules=syn.POLYHIPES_RULES, dedup_iou=0.7)
+    assert [k - offs[4] for k in ref_kept[4]] == final
