@@ -163,7 +163,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--tiles", type=int, default=N_TILES)
-    ap.add_argument("--variant", type=int, default=int(os.environ.get("EMIA_PASTE_VARIANT", "0")))
+    ap.add_argument("--variant", type=int, default=int(os.environ.get("EMIA_PASTE_VARIANT", "2")))
     ap.add_argument("--arena-gb", type=float, default=32.0)
     ap.add_argument("--ref-tiles", type=int, default=8)
     ap.add_argument("--batches", type=int, default=8, help="tile batches of the three-stream pipeline")

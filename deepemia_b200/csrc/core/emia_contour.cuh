@@ -86,10 +86,11 @@ EMIA_HD uint32_t emia_nbr8(const EmiaBitView& v, int lx, int ly) {
 // Written as ONE flat loop over a two-phase state machine (scan for the next start pixel / one border-following step)
 // so that the 32 instances of a warp share the instruction stream: a lane in the "follow" phase executes the same
 // branch-free step (3x3 neighbour mask -> rotate -> count-trailing-zeros picks the next direction) whatever the shape.
-EMIA_HD_NOINLINE void emia_find_external_contours(const EmiaBitView& v, uint32_t* mk, uint32_t* ng, EmiaContourOut& o) {
+// marks_zeroed != 0: the caller cleared both planes already (the kernels clear the whole buffer with coalesced stores).
+EMIA_HD_NOINLINE void emia_find_external_contours(const EmiaBitView& v, uint32_t* mk, uint32_t* ng, EmiaContourOut& o, int marks_zeroed = 0) {
     const int ww = v.wwords;
     const int nw = v.h * ww;
-    for (int i = 0; i < nw; ++i) { mk[i] = 0u; ng[i] = 0u; }
+    if (!marks_zeroed) for (int i = 0; i < nw; ++i) { mk[i] = 0u; ng[i] = 0u; }
     o.n_contours = 0; o.n_pts = 0; o.overflow = 0; o.max_len = 0;
     if (o.store) o.cstart[0] = 0;
     int y = 0, c = 0;
@@ -188,16 +189,29 @@ EMIA_HD double emia_contour_area(const uint32_t* pts, int n) {
 
 // cv2.arcLength(c, closed=True): per-segment float32 sqrt of float32 (dx*dx+dy*dy), accumulated in double,
 // starting with the closing segment (last -> first).
-EMIA_HD double emia_arc_length_closed(const uint32_t* pts, int n) {
+// The segments of a CHAIN_APPROX_SIMPLE contour are runs in one of the 8 chain directions, so almost every term is
+// either an axial run (sqrtf(k*k) == k exactly for k < 4096) or a diagonal run (fl32(sqrt(2 k^2)), taken from `diag`
+// when the caller provides the table: diag[k] = sqrtf((float)(2*k*k)), k < EMIA_DIAG_TABLE); anything else goes through
+// sqrtf, so the result is bit-identical to the plain loop for ANY vertex list.
+#define EMIA_DIAG_TABLE 128
+EMIA_HD double emia_arc_length_closed(const uint32_t* pts, int n, const float* diag = nullptr) {
     if (n <= 1) return 0.0;
     double per = 0.0;
-    float px = (float)EMIA_PT_X(pts[n - 1]), py = (float)EMIA_PT_Y(pts[n - 1]);
+    int px = EMIA_PT_X(pts[n - 1]), py = EMIA_PT_Y(pts[n - 1]);
     for (int i = 0; i < n; ++i) {
-        const float x = (float)EMIA_PT_X(pts[i]), y = (float)EMIA_PT_Y(pts[i]);
-        const float dx = x - px, dy = y - py;
-        const float dx2 = dx * dx;
-        const float dy2 = dy * dy;
-        per += (double)sqrtf(dx2 + dy2);
+        const int x = EMIA_PT_X(pts[i]), y = EMIA_PT_Y(pts[i]);
+        int dx = x - px, dy = y - py;
+        dx = dx < 0 ? -dx : dx; dy = dy < 0 ? -dy : dy;
+        float seg;
+        if ((dx == 0 || dy == 0) && (dx | dy) < 4096) seg = (float)(dx | dy);
+        else if (diag && dx == dy && dx < EMIA_DIAG_TABLE) seg = diag[dx];
+        else {
+            const float fx = (float)dx, fy = (float)dy;
+            const float dx2 = fx * fx;
+            const float dy2 = fy * fy;
+            seg = sqrtf(dx2 + dy2);
+        }
+        per += (double)seg;
         px = x; py = y;
     }
     return per;

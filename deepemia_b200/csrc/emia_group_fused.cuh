@@ -334,18 +334,49 @@ __global__ void __launch_bounds__(EMIA_FUSED_THREADS) k_containment_fused(
     if (__any_sync(0xffffffffu, any) && lane == 0) s_any_parent = 1;
     __syncthreads();
     const int any_parent = s_any_parent;
-    for (int c = tid; c < len; c += EMIA_FUSED_THREADS) {
-        if (role[c] != 1) continue;
-        if (!any_parent) { rem_out[base + c] = 1; role[c] = 0; continue; }
-        const int ac = S.area[c];
-        const int4 bc4 = S.bb[c];
-        if (ac <= 0 || bc4.x < 0) { rem_out[base + c] = 1; role[c] = 0; continue; }
-        const int bc[4] = {bc4.x, bc4.y, bc4.z, bc4.w};
-        for (int p = 0; p < len; ++p) {
-            if (role[p] != 2) continue;
-            const int4 bp4 = S.bb[p];
-            const int bp[4] = {bp4.x, bp4.y, bp4.z, bp4.w};
-            if (!emia_bbox_overlap(bc, bp)) continue;
+    // children that cannot be judged by intersection are decided here; the others and the live parents are sorted by x_min
+    int P = 32;
+    while (P < len) P <<= 1;
+    for (int k = tid; k < P; k += EMIA_FUSED_THREADS) {
+        uint32_t xk = 0xFFFFFFFFu;
+        if (k < len) {
+            if (role[k] == 1) {
+                if (!any_parent || S.area[k] <= 0 || S.bb[k].x < 0) { rem_out[base + k] = 1; role[k] = 0; }
+                else xk = ((uint32_t)S.bb[k].y << 16) | (uint32_t)k;
+            } else if (role[k] == 2 && S.bb[k].x >= 0) xk = ((uint32_t)S.bb[k].y << 16) | (uint32_t)k;
+        }
+        S.xs[k] = xk;
+    }
+    __syncthreads();
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int st = size >> 1; st > 0; st >>= 1) {
+            for (int t = tid; t < (P >> 1); t += EMIA_FUSED_THREADS) {
+                const int lo = ((t / st) * (st << 1)) + (t % st);
+                const int hi = lo + st;
+                const bool up = ((lo & size) == 0);
+                const uint32_t xa = S.xs[lo], xb = S.xs[hi];
+                if ((xa > xb) == up) { S.xs[lo] = xb; S.xs[hi] = xa; }
+            }
+            __syncthreads();
+        }
+    }
+    // sweep: every bbox-overlapping (child, parent) pair is met once, from the member with the smaller x_min
+    for (int i = tid; i < len; i += EMIA_FUSED_THREADS) {
+        const uint32_t xi = S.xs[i];
+        if (xi == 0xFFFFFFFFu) continue;
+        const int a = (int)(xi & 0xFFFFu);
+        const int ra = role[a];
+        const int4 ba4 = S.bb[a];
+        const int ba[4] = {ba4.x, ba4.y, ba4.z, ba4.w};
+        for (int j = i + 1; j < len; ++j) {
+            const uint32_t xj = S.xs[j];
+            if (xj == 0xFFFFFFFFu || (int)(xj >> 16) > ba4.w) break;
+            const int b = (int)(xj & 0xFFFFu);
+            if (role[b] == ra) continue;
+            const int4 bb4 = S.bb[b];
+            const int bb[4] = {bb4.x, bb4.y, bb4.z, bb4.w};
+            if (!emia_bbox_overlap(ba, bb)) continue;
+            const int c = (ra == 1) ? a : b, p = (ra == 1) ? b : a;
             const int q = atomicAdd(&s_qn, 1);
             if (q < EMIA_FUSED_QUEUE) S.queue[q] = (uint32_t)c | ((uint32_t)p << 16);
             else {

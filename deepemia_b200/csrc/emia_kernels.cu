@@ -476,6 +476,188 @@ __global__ void __launch_bounds__(EMIA_PASTE_THREADS) k_paste_bulk(
     if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// ---- variant 2 (default): latency-hiding order + 256-bit stores + oversubscribed grid -------------------------------
+// ncu on variant 0 (profiles/): 23 % of the stall samples sit on the global->shared copy of the 28x28 probabilities at
+// the top of every instance (a DRAM read queued behind the kernel's own write stream) and 11 % of the instructions are
+// the integer division of the (row, word) work split; a write-bandwidth probe (scripts/wbw_probe.cu) shows 256-bit
+// stores from a grid 4-8x larger than the resident CTA count reach 7.0-7.2 TB/s where a persistent 128-bit grid stops
+// at 6.1-6.3.  Hence:
+//   1. cp.async (LDGSTS) the probabilities into a zero-padded 32 x 36 tile FIRST, then zero-fill the frame outside the
+//      crop rows with st.global.v4.b64 while the copy is in flight, and only then wait for it;
+//   2. per-column AND per-row sampling taps in shared memory, padded tile => no bounds tests, no per-pixel division;
+//   3. grid = min(n, SMs x 32) CTAs of 256 threads, instance = blockIdx.x + k * gridDim.x.
+// Needs 32-byte aligned frame rows (pitch_words % 8 == 0); other shapes use variant 0.
+#define EMIA_P2_PAD_STRIDE 36                 // floats per padded tile row: data at columns 4..31, zeros elsewhere
+#define EMIA_P2_PAD_ROWS 32                   // tile rows -2..29
+#define EMIA_P2_BAND_ROWS 128                 // row taps staged per band
+#define EMIA_P2_MAX_COLS 2112                 // W <= 2048 (+ one word of slack, multiple of 32)
+
+__device__ __forceinline__ void emia_st256_zero(void* p) {
+    asm volatile("st.global.v4.b64 [%0], {%1, %1, %1, %1};" ::"l"(p), "l"(0ull) : "memory");
+}
+__device__ __forceinline__ void emia_st256(void* p, uint4 a, uint4 b) {
+    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(((unsigned long long)a.y << 32) | a.x),
+                 "l"(((unsigned long long)a.w << 32) | a.z), "l"(((unsigned long long)b.y << 32) | b.x),
+                 "l"(((unsigned long long)b.w << 32) | b.z)
+                 : "memory");
+}
+__device__ __forceinline__ void emia_cp_async16(void* sdst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ int emia_clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__global__ void __launch_bounds__(EMIA_PASTE_THREADS) k_paste_v2(
+    const float* __restrict__ probs, const float4* __restrict__ boxes, const emia_inst_meta* __restrict__ meta,
+    const int64_t* __restrict__ crop_off, int64_t n, float sx, float sy, int H, int W, uint32_t* __restrict__ frames,
+    int64_t frame_slots, int pitch_words, uint32_t* __restrict__ crops, int32_t* __restrict__ bbox, int32_t* __restrict__ area) {
+    __shared__ __align__(16) float s_pp[EMIA_P2_PAD_ROWS * EMIA_P2_PAD_STRIDE];   // padded probabilities
+    __shared__ __align__(32) uint32_t s_tile[EMIA_PASTE_TILE_WORDS];              // one band of frame rows (chunk span)
+    __shared__ short s_ci0[EMIA_P2_MAX_COLS];
+    __shared__ float s_cw1[EMIA_P2_MAX_COLS];
+    __shared__ short s_ri0[EMIA_P2_BAND_ROWS];
+    __shared__ float s_rw1[EMIA_P2_BAND_ROWS];
+    __shared__ int s_red[5];   // area, ymin, xmin, ymax, xmax
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int nwarps = EMIA_PASTE_THREADS / 32;
+    const int cpr = pitch_words >> 3;               // 32-byte chunks per frame row
+    for (int k = tid; k < EMIA_P2_PAD_ROWS * EMIA_P2_PAD_STRIDE; k += EMIA_PASTE_THREADS) s_pp[k] = 0.f;
+    __syncthreads();
+
+    for (int64_t inst = blockIdx.x; inst < n; inst += gridDim.x) {
+        const emia_inst_meta m = meta[inst];
+        const float4 bx = boxes[inst];
+        const EmiaPasteBox pb = emia_paste_prepare(bx.x, bx.y, bx.z, bx.w, sx, sy, W, H);
+        const bool live = m.valid && m.ch > 0 && m.cw > 0;
+        if (tid < 5) s_red[tid] = (tid == 0) ? 0 : ((tid == 1 || tid == 2) ? 0x7fffffff : -1);
+        // ---- 1. start the copy of the probabilities (28 rows x 7 chunks of 16 bytes -> padded tile rows 2..29, columns 4..31)
+        if (live && tid < EMIA_MASK_SIDE * 7) {
+            const int r = tid / 7, q = tid - r * 7;
+            emia_cp_async16(&s_pp[(r + 2) * EMIA_P2_PAD_STRIDE + 4 + q * 4], probs + inst * (EMIA_MASK_SIDE * EMIA_MASK_SIDE) + r * EMIA_MASK_SIDE + q * 4);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        // ---- 2. zero-fill the frame outside the crop's rows / chunk span while the copy is in flight
+        const int cc0 = live ? (m.wc0 >> 3) : 0;
+        const int cc1 = live ? ((m.wc0 + m.cw - 1) >> 3) : -1;   // inclusive
+        unsigned char* frame = nullptr;
+        if (frames) {
+            frame = (unsigned char*)(frames + (size_t)(inst % frame_slots) * (size_t)H * (size_t)pitch_words);
+            const int total = H * cpr;
+            const int top = live ? m.ry0 * cpr : total;
+            const int bot0 = live ? (m.ry0 + m.ch) * cpr : total;
+            for (int q = tid; q < top; q += EMIA_PASTE_THREADS) emia_st256_zero(frame + (size_t)q * 32);
+            for (int q = bot0 + tid; q < total; q += EMIA_PASTE_THREADS) emia_st256_zero(frame + (size_t)q * 32);
+            if (live && cc1 - cc0 + 1 < cpr) {
+                for (int r = tid; r < m.ch; r += EMIA_PASTE_THREADS) {
+                    unsigned char* row = frame + (size_t)(m.ry0 + r) * cpr * 32;
+                    for (int c = 0; c < cc0; ++c) emia_st256_zero(row + c * 32);
+                    for (int c = cc1 + 1; c < cpr; ++c) emia_st256_zero(row + c * 32);
+                }
+            }
+        }
+        if (live) {
+            // ---- 3. column taps (independent of the probabilities)
+            const int ncols = m.cw * 32;
+            for (int k = tid; k < ncols; k += EMIA_PASTE_THREADS) {
+                const EmiaAxisTap a = emia_paste_axis(m.wc0 * 32 + k, pb.x0, pb.x1);
+                s_ci0[k] = (short)emia_clampi(a.i0, -2, EMIA_MASK_SIDE);
+                s_cw1[k] = a.w1;
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        if (live) {
+            const int span_chunks = cc1 - cc0 + 1;
+            const int span_words = span_chunks * 8;             // staged row width (32-byte chunk aligned)
+            const int woff = m.wc0 - cc0 * 8;                   // crop word 0 sits at this word of the staged row
+            const int rows_per_band = emia_min(EMIA_P2_BAND_ROWS, emia_max(1, EMIA_PASTE_TILE_WORDS / span_words));
+            const int step_r = nwarps / m.cw, step_c = nwarps - step_r * m.cw;
+            uint32_t* crop = crops + crop_off[inst];
+            int l_area = 0, l_ymin = 0x7fffffff, l_xmin = 0x7fffffff, l_ymax = -1, l_xmax = -1;
+            for (int r0 = 0; r0 < m.ch; r0 += rows_per_band) {
+                const int nr = emia_min(rows_per_band, m.ch - r0);
+                for (int k = tid; k < nr * span_words; k += EMIA_PASTE_THREADS) s_tile[k] = 0u;
+                for (int k = tid; k < nr; k += EMIA_PASTE_THREADS) {
+                    const EmiaAxisTap a = emia_paste_axis(m.ry0 + r0 + k, pb.y0, pb.y1);
+                    s_ri0[k] = (short)emia_clampi(a.i0, -2, EMIA_MASK_SIDE);
+                    s_rw1[k] = a.w1;
+                }
+                __syncthreads();
+                // one warp per (row, word): 32 lanes sample 32 pixels, ballot -> word
+                int r = warp / m.cw, c = warp - r * m.cw;
+                while (r < nr) {
+                    const int y = m.ry0 + r0 + r;
+                    const int k = c * 32 + lane;
+                    const int x = m.wc0 * 32 + k;
+                    bool bit = false;
+                    if (x >= m.rx0 && x < m.rx1) {
+                        const int ix = s_ci0[k], iy = s_ri0[r];
+                        const float xw1 = s_cw1[k], yw1 = s_rw1[r];
+                        const float xw0 = 1.f - xw1, yw0 = 1.f - yw1;
+                        const float* t = &s_pp[(iy + 2) * EMIA_P2_PAD_STRIDE + ix + 4];
+                        const float nw = yw0 * xw0;
+                        const float ne = yw0 * xw1;
+                        const float sw = yw1 * xw0;
+                        const float se = yw1 * xw1;
+                        float acc = t[0] * nw;
+                        acc = emia_fmaf(t[1], ne, acc);
+                        acc = emia_fmaf(t[EMIA_P2_PAD_STRIDE], sw, acc);
+                        acc = emia_fmaf(t[EMIA_P2_PAD_STRIDE + 1], se, acc);
+                        bit = acc >= 0.5f;
+                    }
+                    const uint32_t word = __ballot_sync(0xffffffffu, bit);
+                    if (lane == 0 && word) {
+                        s_tile[r * span_words + woff + c] = word;
+                        l_area += __popc(word);
+                        l_ymin = min(l_ymin, y); l_ymax = max(l_ymax, y);
+                        l_xmin = min(l_xmin, (m.wc0 + c) * 32 + (__ffs((int)word) - 1));
+                        l_xmax = max(l_xmax, (m.wc0 + c) * 32 + (31 - __clz((int)word)));
+                    }
+                    r += step_r; c += step_c;
+                    if (c >= m.cw) { c -= m.cw; ++r; }
+                }
+                __syncthreads();
+                // write the band: crop words, then the frame chunk span (256-bit stores)
+                {
+                    int rr = tid / m.cw, cc = tid - rr * m.cw;
+                    const int sr = EMIA_PASTE_THREADS / m.cw, scw = EMIA_PASTE_THREADS - sr * m.cw;
+                    while (rr < nr) {
+                        crop[(size_t)(r0 + rr) * m.cw + cc] = s_tile[rr * span_words + woff + cc];
+                        rr += sr; cc += scw;
+                        if (cc >= m.cw) { cc -= m.cw; ++rr; }
+                    }
+                }
+                if (frames) {
+                    const uint4* s4 = (const uint4*)s_tile;
+                    int rr = tid / span_chunks, cc = tid - rr * span_chunks;
+                    const int sr = EMIA_PASTE_THREADS / span_chunks, sc = EMIA_PASTE_THREADS - sr * span_chunks;
+                    while (rr < nr) {
+                        const int si = (rr * span_chunks + cc) * 2;
+                        emia_st256(frame + ((size_t)(m.ry0 + r0 + rr) * cpr + cc0 + cc) * 32, s4[si], s4[si + 1]);
+                        rr += sr; cc += sc;
+                        if (cc >= span_chunks) { cc -= span_chunks; ++rr; }
+                    }
+                }
+                __syncthreads();
+            }
+            if (lane == 0 && l_area) {
+                atomicAdd(&s_red[0], l_area);
+                atomicMin(&s_red[1], l_ymin); atomicMin(&s_red[2], l_xmin);
+                atomicMax(&s_red[3], l_ymax); atomicMax(&s_red[4], l_xmax);
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            const int a = live ? s_red[0] : 0;
+            area[inst] = a;
+            ((int4*)bbox)[inst] = a > 0 ? make_int4(s_red[1], s_red[2], s_red[3], s_red[4]) : make_int4(-1, -1, -1, -1);
+        }
+        __syncthreads();
+    }
+}
+
 extern "C" int emia_paste_threshold_bitpack(const float* probs, const float* boxes, const emia_inst_meta* meta,
                                             const int64_t* crop_off, int64_t n, float scale_x, float scale_y, int H,
                                             int W, uint32_t* frames, int64_t frame_slots, int pitch_words,
@@ -495,6 +677,14 @@ extern "C" int emia_paste_threshold_bitpack(const float* probs, const float* box
     const int max_cols = ((W + 31) / 32 + 1) * 32;
     cudaStream_t st = (cudaStream_t)stream;
     const int sms = emia_num_sms();
+    if (variant == 2 && max_cols <= EMIA_P2_MAX_COLS && ((uintptr_t)probs & 15) == 0 &&
+        (!frames || ((pitch_words & 7) == 0 && ((uintptr_t)frames & 31) == 0))) {
+        const int64_t per_sm = ctas_req ? ctas_req : 32;
+        const unsigned grid = (unsigned)(n < (int64_t)sms * per_sm ? n : (int64_t)sms * per_sm);
+        k_paste_v2<<<grid, EMIA_PASTE_THREADS, 0, st>>>(probs, (const float4*)boxes, meta, crop_off, n, scale_x, scale_y, H, W, frames,
+                                                        frames ? frame_slots : 1, pitch_words, crops, bbox, area);
+        return emia_check_launch("emia_paste_threshold_bitpack (v2) launch: %s");
+    }
     if (variant == 1 && frames) {
         if (pitch_words * 4 > EMIA_BULK_BYTES) return emia_fail(EMIA_ERR_UNSUPPORTED, "emia_paste_threshold_bitpack: %s", "variant 1 needs a frame row <= 16 KB");
         const size_t smem = 2 * EMIA_BULK_BYTES + EMIA_MASK_SIDE * EMIA_MASK_SIDE * 4 + (size_t)max_cols * 12;

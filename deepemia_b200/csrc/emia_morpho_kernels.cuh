@@ -13,12 +13,43 @@ __device__ __forceinline__ EmiaBitView emia_make_view(const uint32_t* crops, con
 // ---- border following: one THREAD per instance ---------------------------------------------------------------------
 #define EMIA_TRACE_THREADS 128
 
+// diag[k] = sqrtf(2 k^2): the diagonal-run terms of cv2.arcLength (see emia_arc_length_closed), per CTA in shared memory
+__device__ __forceinline__ void emia_fill_diag_table(float* diag) {
+    for (int k = threadIdx.x; k < EMIA_DIAG_TABLE; k += blockDim.x) {
+        const float f = (float)k;
+        const float f2 = f * f;
+        diag[k] = sqrtf(f2 + f2);
+    }
+    __syncthreads();
+}
+
+// clear the two mark planes of the instances [0, n): words [2 * crop_off[0], 2 * crop_off[n]) of `marks`, coalesced
+__global__ void __launch_bounds__(256) k_clear_marks(uint32_t* __restrict__ marks, const int64_t* __restrict__ crop_off, int64_t n) {
+    const int64_t lo = 2 * crop_off[0], hi = 2 * crop_off[n];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // head up to a 16-byte boundary, then 128-bit stores, then the tail
+    const int64_t lo4 = (lo + 3) & ~(int64_t)3, hi4 = hi & ~(int64_t)3;
+    if (lo4 >= hi4) { for (; i < hi; i += stride) marks[i] = 0u; return; }
+    if (i < lo4) marks[i] = 0u;
+    uint4* m4 = (uint4*)(marks + lo4);
+    const int64_t n4 = (hi4 - lo4) >> 2;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) m4[q] = make_uint4(0u, 0u, 0u, 0u);
+    const int64_t t = hi4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < hi) marks[t] = 0u;
+}
+static void emia_launch_clear_marks(uint32_t* marks, const int64_t* crop_off, int64_t n, cudaStream_t st) {
+    k_clear_marks<<<emia_num_sms() * 8, 256, 0, st>>>(marks, crop_off, n);
+}
+
 template <bool kStore>
 __global__ void __launch_bounds__(EMIA_TRACE_THREADS) k_contour_trace(
     const uint32_t* __restrict__ crops, const emia_inst_meta* __restrict__ meta, const int64_t* __restrict__ crop_off, int64_t n,
     uint32_t* __restrict__ marks, int64_t* __restrict__ n_contours, int64_t* __restrict__ n_points,
     int64_t* __restrict__ scratch_bytes, const int64_t* __restrict__ cont_off, const int64_t* __restrict__ pt_off,
     uint32_t* __restrict__ pts, int32_t* __restrict__ cstart, double* __restrict__ perim0) {
+    __shared__ float s_diag[EMIA_DIAG_TABLE];
+    if (kStore) emia_fill_diag_table(s_diag);
     const int64_t i = (int64_t)blockIdx.x * EMIA_TRACE_THREADS + threadIdx.x;
     if (i >= n) return;
     const emia_inst_meta m = meta[i];
@@ -39,7 +70,7 @@ __global__ void __launch_bounds__(EMIA_TRACE_THREADS) k_contour_trace(
     } else {
         o.pts = nullptr; o.cap_pts = 0; o.cstart = nullptr; o.cap_contours = 0; o.store = 0;
     }
-    emia_find_external_contours(v, mk, ng, o);
+    emia_find_external_contours(v, mk, ng, o, 1);
     if (!kStore) {
         n_contours[i] = o.n_contours;
         n_points[i] = o.n_pts;
@@ -47,7 +78,7 @@ __global__ void __launch_bounds__(EMIA_TRACE_THREADS) k_contour_trace(
     } else if (perim0) {
         // arcLength of contours[0] in OpenCV order = the LAST discovered contour (deduplicate_masks_smart's compactness, Q10)
         const int nc = o.n_contours;
-        perim0[i] = nc ? emia_arc_length_closed(o.pts + o.cstart[nc - 1], o.cstart[nc] - o.cstart[nc - 1]) : 0.0;
+        perim0[i] = nc ? emia_arc_length_closed(o.pts + o.cstart[nc - 1], o.cstart[nc] - o.cstart[nc - 1], s_diag) : 0.0;
     }
 }
 #define EMIA_TRACE_SMEM_BYTES ((size_t)0)
@@ -193,6 +224,7 @@ extern "C" int emia_contour_count(const uint32_t* crops, const emia_inst_meta* m
     if (!crops || !meta || !crop_off || !marks || !n_contours || !n_points || !scratch_bytes)
         return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_count: %s", "null pointer");
     const unsigned grid = (unsigned)((n + EMIA_TRACE_THREADS - 1) / EMIA_TRACE_THREADS);
+    emia_launch_clear_marks(marks, crop_off, n, (cudaStream_t)stream);
     k_contour_trace<false><<<grid, EMIA_TRACE_THREADS, EMIA_TRACE_SMEM_BYTES, (cudaStream_t)stream>>>(crops, meta, crop_off, n, marks, n_contours, n_points,
                                                                                   scratch_bytes, nullptr, nullptr, nullptr, nullptr, nullptr);
     return emia_check_launch("emia_contour_count launch: %s");
@@ -209,6 +241,7 @@ extern "C" int emia_contour_measure(const uint32_t* crops, const emia_inst_meta*
         !rec_inst || !perim0 || !scratch)
         return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_measure: %s", "null pointer");
     const unsigned gridt = (unsigned)((n + EMIA_TRACE_THREADS - 1) / EMIA_TRACE_THREADS);
+    emia_launch_clear_marks(marks, crop_off, n, (cudaStream_t)stream);
     k_contour_trace<true><<<gridt, EMIA_TRACE_THREADS, EMIA_TRACE_SMEM_BYTES, (cudaStream_t)stream>>>(crops, meta, crop_off, n, marks, nullptr, nullptr, nullptr,
                                                                                   cont_off, pt_off, pts, cstart, nullptr);
     const unsigned grid = (unsigned)((n + 127) / 128);
@@ -229,6 +262,7 @@ extern "C" int emia_contour_store(const uint32_t* crops, const emia_inst_meta* m
     if (!crops || !meta || !crop_off || !marks || !cont_off || !pt_off || !pts || !cstart)
         return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_store: %s", "null pointer");
     const unsigned gridt = (unsigned)((n + EMIA_TRACE_THREADS - 1) / EMIA_TRACE_THREADS);
+    emia_launch_clear_marks(marks, crop_off, n, (cudaStream_t)stream);
     k_contour_trace<true><<<gridt, EMIA_TRACE_THREADS, EMIA_TRACE_SMEM_BYTES, (cudaStream_t)stream>>>(crops, meta, crop_off, n, marks, nullptr, nullptr, nullptr,
                                                                                   cont_off, pt_off, pts, cstart, perim0);
     return emia_check_launch("emia_contour_store launch: %s");
@@ -249,6 +283,8 @@ __global__ void __launch_bounds__(EMIA_TRACE_THREADS) k_contour_trace_slab(
     uint32_t* __restrict__ marks, const int64_t* __restrict__ pt_cap_off, int capc, uint32_t* __restrict__ pts,
     int32_t* __restrict__ cstart_slab, int64_t* __restrict__ n_contours, int64_t* __restrict__ scratch_bytes,
     int32_t* __restrict__ overflow, double* __restrict__ perim0) {
+    __shared__ float s_diag[EMIA_DIAG_TABLE];
+    emia_fill_diag_table(s_diag);
     const int64_t i = (int64_t)blockIdx.x * EMIA_TRACE_THREADS + threadIdx.x;
     if (i >= n) return;
     const emia_inst_meta m = meta[i];
@@ -263,13 +299,13 @@ __global__ void __launch_bounds__(EMIA_TRACE_THREADS) k_contour_trace_slab(
     EmiaContourOut o;
     o.pts = pts + pt_cap_off[i]; o.cap_pts = (int)(pt_cap_off[i + 1] - pt_cap_off[i]);
     o.cstart = cs; o.cap_contours = capc; o.store = 1;
-    emia_find_external_contours(v, mk, ng, o);
+    emia_find_external_contours(v, mk, ng, o, 1);
     if (o.overflow) { atomicAdd(overflow, 1); n_contours[i] = 0; scratch_bytes[i] = 0; return; }
     n_contours[i] = o.n_contours;
     scratch_bytes[i] = o.n_contours ? (int64_t)((emia_measure_scratch_bytes(o.max_len) + 15) & ~(size_t)15) : 0;
     if (perim0 && o.n_contours) {
         const int nc = o.n_contours;
-        perim0[i] = emia_arc_length_closed(o.pts + cs[nc - 1], cs[nc] - cs[nc - 1]);
+        perim0[i] = emia_arc_length_closed(o.pts + cs[nc - 1], cs[nc] - cs[nc - 1], s_diag);
     }
 }
 
@@ -290,6 +326,7 @@ extern "C" int emia_contour_trace_slab(const uint32_t* crops, const emia_inst_me
     if (!crops || !meta || !crop_off || !marks || !pt_cap_off || !pts || !cstart_slab || !n_contours || !scratch_bytes || !overflow)
         return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_trace_slab: %s", "null pointer");
     const unsigned grid = (unsigned)((n + EMIA_TRACE_THREADS - 1) / EMIA_TRACE_THREADS);
+    emia_launch_clear_marks(marks, crop_off, n, (cudaStream_t)stream);
     k_contour_trace_slab<<<grid, EMIA_TRACE_THREADS, 0, (cudaStream_t)stream>>>(crops, meta, crop_off, n, marks, pt_cap_off, cap_contours, pts,
                                                                              cstart_slab, n_contours, scratch_bytes, overflow, perim0);
     return emia_check_launch("emia_contour_trace_slab launch: %s");

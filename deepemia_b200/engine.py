@@ -128,7 +128,7 @@ def paste_plan(boxes, H, W, scale_x=1.0, scale_y=1.0):
 
 
 def paste(probs, boxes, H, W, scores=None, classes=None, scale_x=1.0, scale_y=1.0, frames=None, frame_slots=0,
-          variant=0, crops_out=None, plan=None, ctas_per_sm=0):
+          variant=2, crops_out=None, plan=None, ctas_per_sm=0):
     """K1.  probs [n,28,28] f32, boxes [n,4] f32 xyxy (mask-head outputs, device tensors) -> InstanceSet.
     frames: None (crops only), True (allocate n full frames) or a preallocated int32 [slots, H, pitch_words] ring.
     plan: (meta, crop_off, total_crop_words) from paste_plan() — possibly a slice of a larger plan whose crop offsets index
@@ -652,7 +652,7 @@ def pair_counts(iset, pa, pb):
 
 
 def run_tiles(probs, boxes, scores, classes, tile_offsets, H, W, um_pix=0.5, rules=None, dedup_iou=0.7, frames=None,
-              variant=0, scale_x=1.0, scale_y=1.0):
+              variant=2, scale_x=1.0, scale_y=1.0):
     """The fused hot path over many tiles at once (BASELINE configs 2 and 5): paste -> external contours ->
     deduplicate_masks_smart -> spatial constraints -> morphometry of the survivors (the order of the reference:
     src/functions/inference.py:859, :868, :1148).  Everything stays on the device.
@@ -683,7 +683,7 @@ class TilePipeline:
     the per-batch totals; each batch then needs one more read (record/scratch totals) on the post stream only.
     Batches see slices of shard-wide arrays; list indices stay shard-global."""
 
-    def __init__(self, H, W, um_pix=1.0, rules=None, dedup_iou=0.7, frames=None, variant=0, batches=8, paste_ctas_per_sm=0,
+    def __init__(self, H, W, um_pix=1.0, rules=None, dedup_iou=0.7, frames=None, variant=2, batches=8, paste_ctas_per_sm=0,
                  device=None):
         self.H, self.W, self.um_pix, self.rules, self.dedup_iou = H, W, um_pix, rules, dedup_iou
         self.frames, self.variant, self.batches, self.paste_ctas = frames, variant, batches, paste_ctas_per_sm

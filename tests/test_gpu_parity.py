@@ -37,7 +37,7 @@ def _unpack_frames(frames, W):
     return bits.reshape(f.shape[0], f.shape[1], -1)[:, :, :W]
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("shape", [(256, 320), (300, 333), (128, 1100)])
 def test_paste_matches_detectron2_oracle(cuda_device, variant, shape):
     H, W = shape
