@@ -491,6 +491,9 @@ __global__ void __launch_bounds__(EMIA_PASTE_THREADS) k_paste_bulk(
 #define EMIA_P2_PAD_ROWS 32                   // tile rows -2..29
 #define EMIA_P2_BAND_ROWS 128                 // row taps staged per band
 #define EMIA_P2_MAX_COLS 2112                 // W <= 2048 (+ one word of slack, multiple of 32)
+#ifndef EMIA_P2_MIN_CTAS
+#define EMIA_P2_MIN_CTAS 4
+#endif
 
 __device__ __forceinline__ void emia_st256_zero(void* p) {
     asm volatile("st.global.v4.b64 [%0], {%1, %1, %1, %1};" ::"l"(p), "l"(0ull) : "memory");
@@ -506,16 +509,14 @@ __device__ __forceinline__ void emia_cp_async16(void* sdst, const void* gsrc) {
 }
 __device__ __forceinline__ int emia_clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-__global__ void __launch_bounds__(EMIA_PASTE_THREADS) k_paste_v2(
+__global__ void __launch_bounds__(EMIA_PASTE_THREADS, EMIA_P2_MIN_CTAS) k_paste_v2(
     const float* __restrict__ probs, const float4* __restrict__ boxes, const emia_inst_meta* __restrict__ meta,
     const int64_t* __restrict__ crop_off, int64_t n, float sx, float sy, int H, int W, uint32_t* __restrict__ frames,
     int64_t frame_slots, int pitch_words, uint32_t* __restrict__ crops, int32_t* __restrict__ bbox, int32_t* __restrict__ area) {
     __shared__ __align__(16) float s_pp[EMIA_P2_PAD_ROWS * EMIA_P2_PAD_STRIDE];   // padded probabilities
     __shared__ __align__(32) uint32_t s_tile[EMIA_PASTE_TILE_WORDS];              // one band of frame rows (chunk span)
-    __shared__ short s_ci0[EMIA_P2_MAX_COLS];
-    __shared__ float s_cw1[EMIA_P2_MAX_COLS];
-    __shared__ short s_ri0[EMIA_P2_BAND_ROWS];
-    __shared__ float s_rw1[EMIA_P2_BAND_ROWS];
+    __shared__ int2 s_ctap[EMIA_P2_MAX_COLS];     // per column: (tile offset of tap i0, bits of w1); columns outside [rx0, rx1) read zeros
+    __shared__ int2 s_rtap[EMIA_P2_BAND_ROWS];    // per row of the band: (tile offset of tap row, bits of w1)
     __shared__ int s_red[5];   // area, ymin, xmin, ymax, xmax
 
     const int tid = threadIdx.x;
@@ -561,9 +562,11 @@ __global__ void __launch_bounds__(EMIA_PASTE_THREADS) k_paste_v2(
             // ---- 3. column taps (independent of the probabilities)
             const int ncols = m.cw * 32;
             for (int k = tid; k < ncols; k += EMIA_PASTE_THREADS) {
-                const EmiaAxisTap a = emia_paste_axis(m.wc0 * 32 + k, pb.x0, pb.x1);
-                s_ci0[k] = (short)emia_clampi(a.i0, -2, EMIA_MASK_SIDE);
-                s_cw1[k] = a.w1;
+                const int x = m.wc0 * 32 + k;
+                const EmiaAxisTap a = emia_paste_axis(x, pb.x0, pb.x1);
+                // a column outside the sampling region reads the zero padding (taps -2, -1): its bits come out 0
+                const int i0 = (x >= m.rx0 && x < m.rx1) ? emia_clampi(a.i0, -2, EMIA_MASK_SIDE) : -2;
+                s_ctap[k] = make_int2(i0 + 4, __float_as_int(a.w1));
             }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -581,50 +584,44 @@ __global__ void __launch_bounds__(EMIA_PASTE_THREADS) k_paste_v2(
                 for (int k = tid; k < nr * span_words; k += EMIA_PASTE_THREADS) s_tile[k] = 0u;
                 for (int k = tid; k < nr; k += EMIA_PASTE_THREADS) {
                     const EmiaAxisTap a = emia_paste_axis(m.ry0 + r0 + k, pb.y0, pb.y1);
-                    s_ri0[k] = (short)emia_clampi(a.i0, -2, EMIA_MASK_SIDE);
-                    s_rw1[k] = a.w1;
+                    s_rtap[k] = make_int2((emia_clampi(a.i0, -2, EMIA_MASK_SIDE) + 2) * EMIA_P2_PAD_STRIDE, __float_as_int(a.w1));
                 }
                 __syncthreads();
                 // one warp per (row, word): 32 lanes sample 32 pixels, ballot -> word
                 int r = warp / m.cw, c = warp - r * m.cw;
                 while (r < nr) {
-                    const int y = m.ry0 + r0 + r;
-                    const int k = c * 32 + lane;
-                    const int x = m.wc0 * 32 + k;
-                    bool bit = false;
-                    if (x >= m.rx0 && x < m.rx1) {
-                        const int ix = s_ci0[k], iy = s_ri0[r];
-                        const float xw1 = s_cw1[k], yw1 = s_rw1[r];
-                        const float xw0 = 1.f - xw1, yw0 = 1.f - yw1;
-                        const float* t = &s_pp[(iy + 2) * EMIA_P2_PAD_STRIDE + ix + 4];
-                        const float nw = yw0 * xw0;
-                        const float ne = yw0 * xw1;
-                        const float sw = yw1 * xw0;
-                        const float se = yw1 * xw1;
-                        float acc = t[0] * nw;
-                        acc = emia_fmaf(t[1], ne, acc);
-                        acc = emia_fmaf(t[EMIA_P2_PAD_STRIDE], sw, acc);
-                        acc = emia_fmaf(t[EMIA_P2_PAD_STRIDE + 1], se, acc);
-                        bit = acc >= 0.5f;
-                    }
-                    const uint32_t word = __ballot_sync(0xffffffffu, bit);
-                    if (lane == 0 && word) {
-                        s_tile[r * span_words + woff + c] = word;
-                        l_area += __popc(word);
-                        l_ymin = min(l_ymin, y); l_ymax = max(l_ymax, y);
-                        l_xmin = min(l_xmin, (m.wc0 + c) * 32 + (__ffs((int)word) - 1));
-                        l_xmax = max(l_xmax, (m.wc0 + c) * 32 + (31 - __clz((int)word)));
-                    }
+                    const int2 ct = s_ctap[c * 32 + lane], rt = s_rtap[r];
+                    const float xw1 = __int_as_float(ct.y), yw1 = __int_as_float(rt.y);
+                    const float xw0 = 1.f - xw1, yw0 = 1.f - yw1;
+                    const float* t = &s_pp[rt.x + ct.x];
+                    const float nw = yw0 * xw0;
+                    const float ne = yw0 * xw1;
+                    const float sw = yw1 * xw0;
+                    const float se = yw1 * xw1;
+                    float acc = t[0] * nw;
+                    acc = emia_fmaf(t[1], ne, acc);
+                    acc = emia_fmaf(t[EMIA_P2_PAD_STRIDE], sw, acc);
+                    acc = emia_fmaf(t[EMIA_P2_PAD_STRIDE + 1], se, acc);
+                    const uint32_t word = __ballot_sync(0xffffffffu, acc >= 0.5f);
+                    if (lane == 0) s_tile[r * span_words + woff + c] = word;
                     r += step_r; c += step_c;
                     if (c >= m.cw) { c -= m.cw; ++r; }
                 }
                 __syncthreads();
-                // write the band: crop words, then the frame chunk span (256-bit stores)
+                // write the band: crop words (+ bbox / area from the same words), then the frame chunk span (256-bit stores)
                 {
                     int rr = tid / m.cw, cc = tid - rr * m.cw;
                     const int sr = EMIA_PASTE_THREADS / m.cw, scw = EMIA_PASTE_THREADS - sr * m.cw;
                     while (rr < nr) {
-                        crop[(size_t)(r0 + rr) * m.cw + cc] = s_tile[rr * span_words + woff + cc];
+                        const uint32_t word = s_tile[rr * span_words + woff + cc];
+                        crop[(size_t)(r0 + rr) * m.cw + cc] = word;
+                        if (word) {
+                            const int y = m.ry0 + r0 + rr;
+                            l_area += __popc(word);
+                            l_ymin = min(l_ymin, y); l_ymax = max(l_ymax, y);
+                            l_xmin = min(l_xmin, (m.wc0 + cc) * 32 + (__ffs((int)word) - 1));
+                            l_xmax = max(l_xmax, (m.wc0 + cc) * 32 + (31 - __clz((int)word)));
+                        }
                         rr += sr; cc += scw;
                         if (cc >= m.cw) { cc -= m.cw; ++rr; }
                     }
@@ -641,6 +638,11 @@ __global__ void __launch_bounds__(EMIA_PASTE_THREADS) k_paste_v2(
                     }
                 }
                 __syncthreads();
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                l_area += __shfl_xor_sync(0xffffffffu, l_area, o);
+                l_ymin = min(l_ymin, __shfl_xor_sync(0xffffffffu, l_ymin, o)); l_xmin = min(l_xmin, __shfl_xor_sync(0xffffffffu, l_xmin, o));
+                l_ymax = max(l_ymax, __shfl_xor_sync(0xffffffffu, l_ymax, o)); l_xmax = max(l_xmax, __shfl_xor_sync(0xffffffffu, l_xmax, o));
             }
             if (lane == 0 && l_area) {
                 atomicAdd(&s_red[0], l_area);
