@@ -99,6 +99,9 @@ __global__ void __launch_bounds__(EMIA_FUSED_THREADS) k_group_fused(
     const int nwarps = EMIA_FUSED_THREADS / 32;
     const int base = cap_off[g], cap = cap_off[g + 1] - base;
     const int len = in_len[g];
+    // mode 3 (score-sorted iou() de-dup): visit order of mode 0, pair relation of mode 1
+    const int rank_mode = (mode == 3) ? 0 : mode;
+    const int pair_mode = (mode == 3) ? 1 : mode;
     if (tid == 0) { s_qn = 0; s_nok = 0; }
     // ---- load + select
     for (int k = tid; k < cap; k += EMIA_FUSED_THREADS) {
@@ -112,8 +115,8 @@ __global__ void __launch_bounds__(EMIA_FUSED_THREADS) k_group_fused(
             S.coff[k] = crop_off[inst];
             a = area[inst];
             b = ((const int4*)bbox)[inst];
-            if (mode != 1) cl = classes[inst];
-            if (mode != 1) sc = scores[inst];
+            if (pair_mode != 1) cl = classes[inst];
+            if (rank_mode != 1) sc = scores[inst];
             ok = 1;
             if (mode == 0) {
                 if (a <= 0) ok = 0;
@@ -162,11 +165,11 @@ __global__ void __launch_bounds__(EMIA_FUSED_THREADS) k_group_fused(
         uint64_t key = ~0ull;
         uint32_t xk = 0xFFFFFFFFu;
         if (k < cap && S.fidx[k] >= 0) {
-            if (mode == 1) key = (uint64_t)k;
+            if (rank_mode == 1) key = (uint64_t)k;
             else {
                 const uint32_t bits = __float_as_uint(S.score[k]);
                 const uint32_t u = bits ^ ((bits >> 31) ? 0xFFFFFFFFu : 0x80000000u);      // order-preserving
-                if (mode == 0) key = ((uint64_t)(~u) << 16) | (uint64_t)(0xFFFFu - (uint32_t)k);
+                if (rank_mode == 0) key = ((uint64_t)(~u) << 16) | (uint64_t)(0xFFFFu - (uint32_t)k);
                 else key = ((uint64_t)((uint32_t)(S.cls[k] + 0x8000) & 0xFFFFu) << 48) | ((uint64_t)(~u) << 16) | (uint64_t)k;
             }
             // takes part in the pair sweep?
@@ -196,7 +199,7 @@ __global__ void __launch_bounds__(EMIA_FUSED_THREADS) k_group_fused(
     for (int k = tid; k < cap; k += EMIA_FUSED_THREADS) if (S.fidx[k] < 0) S.pos[k] = -1;
     for (int r = tid; r < nok; r += EMIA_FUSED_THREADS) {
         const uint32_t low = (uint32_t)(rk[r] & 0xFFFFu);
-        const int k = (mode == 0) ? (int)(0xFFFFu - low) : (int)low;
+        const int k = (rank_mode == 0) ? (int)(0xFFFFu - low) : (int)low;
         S.pos[k] = r;
         S.order[r] = k;
     }
@@ -217,10 +220,10 @@ __global__ void __launch_bounds__(EMIA_FUSED_THREADS) k_group_fused(
             const uint32_t xj = S.xs[j];
             if (xj == 0xFFFFFFFFu || (int)(xj >> 16) > ba4.w) break;   // end of the list / starts right of a's x_max
             const int b = (int)(xj & 0xFFFFu);
-            if (mode != 1 && S.cls[b] != ca) continue;
+            if (pair_mode != 1 && S.cls[b] != ca) continue;
             const int4 bb4 = S.bb[b];
             const int bb[4] = {bb4.x, bb4.y, bb4.z, bb4.w};
-            if (mode == 0) { if (!emia_bbox_overlap_q1(ba, bb)) continue; }
+            if (pair_mode == 0) { if (!emia_bbox_overlap_q1(ba, bb)) continue; }
             if (!emia_bbox_overlap(ba, bb)) continue;
             const int q = atomicAdd(&s_qn, 1);
             if (q < EMIA_FUSED_QUEUE) S.queue[q] = (uint32_t)a | ((uint32_t)b << 16);

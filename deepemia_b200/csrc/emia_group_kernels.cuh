@@ -421,8 +421,9 @@ static int emia_group_pipeline(int mode, const uint32_t* crops, const emia_inst_
     k_group_offsets<<<1, 1, 0, st>>>(cap_off, G, ws.bm_off, ws.rm_off);
     k_group_select<<<gl, T, 0, st>>>(cap_off, G, in_len, in_idx, L, mode == 0 ? 0 : 1, bbox, area, perim0, n_contours, max_aspect, ws.ok);
     k_group_fidx<<<gw, T, 0, st>>>(cap_off, G, ws.ok, ws.fidx, ws.nok);
-    k_group_rank<<<gl, T, 0, st>>>(cap_off, G, in_idx, L, mode, scores, classes, ws.ok, ws.fidx, ws.pos, ws.order);
-    k_group_pairs<<<gl, T, 0, st>>>(crops, meta, crop_off, bbox, area, classes, cap_off, G, in_idx, L, mode, thr, rule_active,
+    const int rank_mode = (mode == 3) ? 0 : mode, pair_mode = (mode == 3) ? 1 : mode;
+    k_group_rank<<<gl, T, 0, st>>>(cap_off, G, in_idx, L, rank_mode, scores, classes, ws.ok, ws.fidx, ws.pos, ws.order);
+    k_group_pairs<<<gl, T, 0, st>>>(crops, meta, crop_off, bbox, area, classes, cap_off, G, in_idx, L, pair_mode, thr, rule_active,
                                     rule_max_iou, num_classes, ws.ok, ws.pos, ws.bm_off, ws.bm);
     k_group_greedy<<<gw, T, 0, st>>>(cap_off, G, in_idx, ws.nok, ws.order, ws.fidx, ws.ok, ws.pos, ws.bm_off, ws.bm, ws.rm_off,
                                      ws.rm, mode == 0 ? 1 : 0, mode == 2 ? 0 : 1, out_len, out_idx);
@@ -457,6 +458,23 @@ extern "C" int emia_dedup_inorder(const uint32_t* crops, const emia_inst_meta* m
     const int L = total_cap;
     if (L == 0) { cudaMemsetAsync(out_len, 0, (size_t)G * 4, (cudaStream_t)stream); return EMIA_OK; }
     return emia_group_pipeline(1, crops, meta, crop_off, bbox, area, nullptr, nullptr, nullptr, nullptr, cap_off, G, in_len, in_idx,
+                               iou_threshold, 0.0, nullptr, nullptr, 0, out_len, out_idx, workspace, workspace_bytes,
+                               (cudaStream_t)stream, L, max_cap);
+}
+
+// score-sorted greedy de-dup with iou() (run_adaptive_multiscale_inference, src/functions/inference.py:1964-1978):
+// visit in np.argsort(scores)[::-1] order, keep unless iou > thr with an already kept mask (any class); keep order out.
+extern "C" int emia_dedup_sorted(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off,
+                                 const int32_t* bbox, const int32_t* area, const float* scores, const int32_t* cap_off, int32_t G,
+                                 int32_t total_cap, int32_t max_cap, const int32_t* in_len, const int32_t* in_idx, double iou_threshold,
+                                 int32_t* out_len, int32_t* out_idx, void* workspace, size_t workspace_bytes, void* stream) {
+    if (G < 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_dedup_sorted: %s", "bad G");
+    if (G == 0) return EMIA_OK;
+    if (!crops || !meta || !crop_off || !bbox || !area || !scores || !cap_off || !in_len || !in_idx || !out_len || !out_idx || !workspace)
+        return emia_fail(EMIA_ERR_BAD_ARG, "emia_dedup_sorted: %s", "null pointer");
+    const int L = total_cap;
+    if (L == 0) { cudaMemsetAsync(out_len, 0, (size_t)G * 4, (cudaStream_t)stream); return EMIA_OK; }
+    return emia_group_pipeline(3, crops, meta, crop_off, bbox, area, nullptr, nullptr, scores, nullptr, cap_off, G, in_len, in_idx,
                                iou_threshold, 0.0, nullptr, nullptr, 0, out_len, out_idx, workspace, workspace_bytes,
                                (cudaStream_t)stream, L, max_cap);
 }

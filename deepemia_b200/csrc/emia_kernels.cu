@@ -716,3 +716,4 @@ extern "C" int emia_paste_threshold_bitpack(const float* probs, const float* box
 #include "emia_morpho_kernels.cuh"
 #include "emia_group_kernels.cuh"
 #include "emia_morph_kernels.cuh"
+#include "emia_tile_kernels.cuh"

@@ -576,6 +576,134 @@ def dedup_inorder(iset, groups, iou_threshold):
     return out
 
 
+def dedup_sorted(iset, groups, iou_threshold):
+    """Score-sorted greedy de-dup with iou() (run_adaptive_multiscale_inference, src/functions/inference.py:1964-1978)."""
+    lib = _lib.load()
+    ws, nb = _workspace(groups, iset.device)
+    out = _new_groups_like(groups)
+    _lib.check(lib.emia_dedup_sorted(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), _ptr(iset.bbox), _ptr(iset.area),
+                                     _ptr(iset.scores), _ptr(groups.cap_off), groups.G, groups.total_cap, groups.fused_cap,
+                                     _ptr(groups.length), _ptr(groups.idx), float(iou_threshold), _ptr(out.length), _ptr(out.idx),
+                                     _ptr(ws), nb, _stream()), "emia_dedup_sorted")
+    LAUNCHES["count"] += 1 if groups.fused_cap and groups.fused_cap <= 1024 else 6
+    return out
+
+
+def filter_flag(groups, flag, keep_value=0):
+    """List members whose flag[inst] == keep_value (e.g. the edge filter of the tile pipeline)."""
+    lib = _lib.load()
+    out = _new_groups_like(groups)
+    _lib.check(lib.emia_group_filter_flag(_ptr(groups.cap_off), groups.G, _ptr(groups.length), _ptr(groups.idx), _ptr(flag),
+                                          int(keep_value), _ptr(out.length), _ptr(out.idx), _stream()), "emia_group_filter_flag")
+    LAUNCHES["count"] += 1
+    return out
+
+
+def resize_place(iset, th, tw, Hd, Wd, off_xy=None, tile_size=None, overlap_ratio=None):
+    """K3: cv2.resize(mask, (tw, th), INTER_NEAREST) of every instance of `iset` (frame iset.H x iset.W), placed at
+    off_xy[i] = (x_offset, y_offset) of an Hd x Wd frame with the reference's clipping (src/functions/inference.py:2399-2420;
+    :2044-2054 with th, tw = Hd, Wd and no offsets).  Returns (InstanceSet in the destination frame, edge_flag or None):
+    edge_flag[i] = is_edge_mask(resized mask, tile_size, overlap_ratio) (inference.py:2522-2549)."""
+    lib = _lib.load()
+    dev = iset.device
+    n = iset.n
+    meta = torch.empty((n, 8), dtype=torch.int32, device=dev)
+    crop_off = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    if off_xy is not None:
+        off_xy = torch.as_tensor(off_xy, dtype=torch.int32, device=dev).contiguous()
+        assert off_xy.shape == (n, 2)
+    st = _stream()
+    _lib.check(lib.emia_resize_place_plan(_ptr(iset.bbox), n, iset.H, iset.W, th, tw, _ptr(off_xy), Hd, Wd, _ptr(meta), _ptr(crop_off), st),
+               "emia_resize_place_plan")
+    exclusive_scan_(crop_off)
+    total = int(crop_off[n].item()) if n else 0
+    crops = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    bbox = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    area = torch.empty(n, dtype=torch.int32, device=dev)
+    edge = None
+    edge_width = ts = 0
+    if tile_size is not None:
+        edge = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        ts = int(tile_size)
+        edge_width = int(tile_size * overlap_ratio / 2)
+    _lib.check(lib.emia_resize_nearest_place(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), _ptr(iset.bbox), n, iset.H, iset.W,
+                                             th, tw, _ptr(off_xy), Hd, Wd, edge_width, ts, _ptr(meta), _ptr(crop_off), _ptr(crops),
+                                             _ptr(bbox), _ptr(area), _ptr(edge), st), "emia_resize_nearest_place")
+    LAUNCHES["count"] += 2
+    out = InstanceSet(n=n, H=Hd, W=Wd, meta=meta, crop_off=crop_off, crops=crops, bbox=bbox, area=area, scores=iset.scores,
+                      classes=iset.classes, total_crop_words=total)
+    return out, edge
+
+
+def select(iset, idx):
+    """A new InstanceSet holding instances idx (device or host int array) of `iset`, crops re-packed (device gathers only)."""
+    dev = iset.device
+    idx = torch.as_tensor(idx, dtype=torch.int64, device=dev)
+    k = int(idx.numel())
+    meta = iset.meta[idx].contiguous()
+    words = (meta[:, 2].to(torch.int64) * meta[:, 3].to(torch.int64))
+    crop_off = torch.zeros(k + 1, dtype=torch.int64, device=dev)
+    if k:
+        crop_off[1:] = torch.cumsum(words, 0)
+    total = int(crop_off[k].item()) if k else 0
+    crops = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    if total:
+        # word j of the new buffer comes from old_off[inst(j)] + (j - new_off[inst(j)])
+        owner = torch.repeat_interleave(torch.arange(k, device=dev), words)
+        src = iset.crop_off[idx][owner] + (torch.arange(total, device=dev) - crop_off[:-1][owner])
+        crops[:total] = iset.crops[src]
+    pick = lambda t: None if t is None else t[idx].contiguous()
+    return InstanceSet(n=k, H=iset.H, W=iset.W, meta=meta, crop_off=crop_off, crops=crops, bbox=pick(iset.bbox), area=pick(iset.area),
+                       scores=pick(iset.scores), classes=pick(iset.classes), total_crop_words=total)
+
+
+def concat(isets):
+    """Concatenate InstanceSets of the same frame size (e.g. full-image pass + every tile, src/functions/inference.py:2452-2454)."""
+    isets = [s for s in isets if s is not None]
+    assert isets and all(s.H == isets[0].H and s.W == isets[0].W for s in isets)
+    dev = isets[0].device
+    n = sum(s.n for s in isets)
+    total = sum(s.total_crop_words for s in isets)
+    crop_off = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    pos, base = 0, 0
+    for s in isets:
+        crop_off[pos:pos + s.n] = s.crop_off[:s.n] + base
+        pos += s.n; base += s.total_crop_words
+    crop_off[n] = base
+    crops = torch.cat([s.crops[:s.total_crop_words] for s in isets]) if total else torch.empty(1, dtype=torch.int32, device=dev)
+    cat = lambda name: (torch.cat([getattr(s, name)[:s.n] for s in isets]) if all(getattr(s, name) is not None for s in isets) else None)
+    return InstanceSet(n=n, H=isets[0].H, W=isets[0].W, meta=torch.cat([s.meta for s in isets]), crop_off=crop_off, crops=crops,
+                       bbox=cat("bbox"), area=cat("area"), scores=cat("scores"), classes=cat("classes"), total_crop_words=total)
+
+
+def rle_encode(iset, idx=None):
+    """K6: rle_encoding (src/utils/mask_utils.py:17-35) of every instance: (run_off int64 [n+1], runs int64 [R, 2]) on the device;
+    runs[run_off[i]:run_off[i+1]] are the (start, length) pairs of instance i (column-major, 1-indexed)."""
+    lib = _lib.load()
+    dev = iset.device
+    n = iset.n
+    run_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    st = _stream()
+    _lib.check(lib.emia_rle_count(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), _ptr(iset.bbox), n, iset.H, _ptr(run_off), st),
+               "emia_rle_count")
+    exclusive_scan_(run_off)
+    R = int(run_off[n].item()) if n else 0
+    runs = torch.empty((max(R, 1), 2), dtype=torch.int64, device=dev)
+    _lib.check(lib.emia_rle_encode(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), _ptr(iset.bbox), n, iset.H, _ptr(run_off),
+                                   _ptr(runs), st), "emia_rle_encode")
+    LAUNCHES["count"] += 2
+    return run_off, runs[:R]
+
+
+def moments01(iset):
+    """(m00, m10, m01) int64 [n,3]: cv2.moments of the 0/1 mask (src/functions/inference.py:1101-1104)."""
+    lib = _lib.load()
+    out = torch.empty((max(iset.n, 1), 3), dtype=torch.int64, device=iset.device)
+    _lib.check(lib.emia_moments01(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), iset.n, _ptr(out), _stream()), "emia_moments01")
+    LAUNCHES["count"] += 1
+    return out[:iset.n]
+
+
 _rule_cache = {}
 
 

@@ -173,6 +173,11 @@ int emia_dedup_inorder(const uint32_t* crops, const emia_inst_meta* meta, const 
                        const int32_t* bbox, const int32_t* area, const int32_t* cap_off, int32_t G,
                        int32_t total_cap, int32_t max_cap, const int32_t* in_len, const int32_t* in_idx, double iou_threshold, int32_t* out_len,
                        int32_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
+/* emia_dedup_sorted: score-sorted greedy de-dup with iou() (run_adaptive_multiscale_inference, inference.py:1964-1978) */
+int emia_dedup_sorted(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, const int32_t* bbox,
+                      const int32_t* area, const float* scores, const int32_t* cap_off, int32_t G, int32_t total_cap,
+                      int32_t max_cap, const int32_t* in_len, const int32_t* in_idx, double iou_threshold, int32_t* out_len,
+                      int32_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
 int emia_overlap_rules(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off,
                        const int32_t* bbox, const int32_t* area, const float* scores, const int32_t* classes,
                        const int32_t* cap_off, int32_t G, int32_t total_cap, int32_t max_cap, const int32_t* in_len, const int32_t* in_idx,
@@ -215,6 +220,37 @@ int emia_group_filter_area(const int32_t* cap_off, int32_t G, const int32_t* in_
 int emia_column_gate(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, const int32_t* cap_off,
                      int32_t G, const int32_t* in_len, const int32_t* in_idx, int W, int32_t min_size, int32_t* out_len,
                      int32_t* out_idx, void* stream);
+
+/* ---- K3: nearest-neighbour back-projection of instances into a (larger) frame ------------------------------------------
+ * Replaces the per-instance cv2.resize(mask, INTER_NEAREST) + is_edge_mask + zero-frame placement of the tile pipeline
+ * (src/functions/inference.py:2399-2420, :2522-2549) and of the multi-scale pass (:2044-2054, offsets 0).
+ * Source instances live in an Hs x Ws frame (the upscaled tile / scaled image); they are resized to th x tw (the tile /
+ * original image) and placed at off_xy[i] = (x_offset, y_offset) (NULL: 0,0) of the Hd x Wd destination frame, clipped
+ * like `global_mask[y:y_end, x:x_end] = downscaled[:y_end - y, :x_end - x]`.
+ * emia_resize_place_plan: destination geometry + crop sizes (caller scans).  emia_resize_nearest_place: destination crops,
+ * bbox, area and (optional) edge_flag[i] = is_edge_mask(downscaled mask, tile_size, overlap) with edge_width =
+ * int(tile_size * overlap_ratio / 2) — evaluated on the UNCLIPPED tile-sized mask; empty => 1. */
+int emia_resize_place_plan(const int32_t* src_bbox, int64_t n, int Hs, int Ws, int th, int tw, const int32_t* off_xy,
+                           int Hd, int Wd, emia_inst_meta* dst_meta, int64_t* dst_crop_words, void* stream);
+int emia_resize_nearest_place(const uint32_t* src_crops, const emia_inst_meta* src_meta, const int64_t* src_crop_off,
+                              const int32_t* src_bbox, int64_t n, int Hs, int Ws, int th, int tw, const int32_t* off_xy,
+                              int Hd, int Wd, int edge_width, int tile_size, const emia_inst_meta* dst_meta,
+                              const int64_t* dst_crop_off, uint32_t* dst_crops, int32_t* dst_bbox, int32_t* dst_area,
+                              int32_t* edge_flag, void* stream);
+/* list members whose flag[inst] == keep_value, list order kept */
+int emia_group_filter_flag(const int32_t* cap_off, int32_t G, const int32_t* in_len, const int32_t* in_idx,
+                           const int32_t* flag, int32_t keep_value, int32_t* out_len, int32_t* out_idx, void* stream);
+
+/* ---- K6: RLE wire format (rle_encoding, src/utils/mask_utils.py:17-35; R50_flip_results.csv "EncodedPixels") -----------
+ * Column-major, 1-indexed (start, length) pairs.  emia_rle_count: runs per instance (caller scans);
+ * emia_rle_encode: runs[2 * (run_off[i] + k)] = start, [.. + 1] = length.  H = frame height. */
+int emia_rle_count(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, const int32_t* bbox,
+                   int64_t n, int H, int64_t* n_runs, void* stream);
+int emia_rle_encode(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, const int32_t* bbox,
+                    int64_t n, int H, const int64_t* run_off, int64_t* runs, void* stream);
+/* raw moments (m00, m10, m01) of every instance as exact integers: cv2.moments(mask) of src/functions/inference.py:1101-1104 */
+int emia_moments01(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n, int64_t* out,
+                   void* stream);
 
 /* pairwise helpers (drop-in for iou / calculate_iou / calculate_containment on explicit pairs):
  * out[k] = {intersection, area_a, area_b} for pairs (pa[k], pb[k]). */
