@@ -317,3 +317,43 @@ extern "C" int emia_moments01(const uint32_t* crops, const emia_inst_meta* meta,
     k_moments01<<<(unsigned)((n * 32 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(crops, meta, crop_off, n, out);
     return emia_check_launch("emia_moments01 launch: %s");
 }
+
+// ---- masked grey-level histogram (contrast d10 / d50 / d90, src/utils/measurements.py:195-215) ---------------------------
+// gray = cv2.cvtColor(BGR2GRAY) for 8-bit images: (B * 1868 + G * 9617 + R * 4899 + 8192) >> 14; np.histogram(bins = 256,
+// range = (0, 255)) puts the integer level v into bin v.  One CTA per instance, 256-bin histogram in shared memory.
+__global__ void __launch_bounds__(128) k_gray_hist(const uint32_t* __restrict__ crops, const emia_inst_meta* __restrict__ meta,
+                                                   const int64_t* __restrict__ crop_off, int64_t n, const uint8_t* __restrict__ image,
+                                                   int H, int W, int channels, int32_t* __restrict__ hist) {
+    __shared__ int s_h[256];
+    for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+        for (int k = threadIdx.x; k < 256; k += blockDim.x) s_h[k] = 0;
+        __syncthreads();
+        const emia_inst_meta m = meta[i];
+        const uint32_t* crop = crops + crop_off[i];
+        for (int k = threadIdx.x; k < m.ch * m.cw; k += blockDim.x) {
+            uint32_t w = crop[k];
+            const int r = k / m.cw, c = k - r * m.cw;
+            const int y = m.ry0 + r;
+            while (w) {
+                const int b = __ffs((int)w) - 1;
+                w &= w - 1;
+                const int x = (m.wc0 + c) * 32 + b;
+                if (x >= W || y >= H) continue;
+                const uint8_t* px = image + ((size_t)y * W + x) * channels;
+                const int g = (channels == 3) ? ((px[0] * 1868 + px[1] * 9617 + px[2] * 4899 + 8192) >> 14) : px[0];
+                atomicAdd(&s_h[g], 1);
+            }
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < 256; k += blockDim.x) hist[i * 256 + k] = s_h[k];
+        __syncthreads();
+    }
+}
+extern "C" int emia_gray_hist(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n,
+                              const uint8_t* image, int H, int W, int channels, int32_t* hist, void* stream) {
+    if (n < 0 || H <= 0 || W <= 0 || (channels != 1 && channels != 3)) return emia_fail(EMIA_ERR_BAD_ARG, "emia_gray_hist: %s", "bad argument");
+    if (n == 0) return EMIA_OK;
+    if (!crops || !meta || !crop_off || !image || !hist) return emia_fail(EMIA_ERR_BAD_ARG, "emia_gray_hist: %s", "null pointer");
+    k_gray_hist<<<(unsigned)(n < 65535 ? n : 65535), 128, 0, (cudaStream_t)stream>>>(crops, meta, crop_off, n, image, H, W, channels, hist);
+    return emia_check_launch("emia_gray_hist launch: %s");
+}

@@ -455,6 +455,38 @@ def measure(iset, um_pix=1.0, min_area=None, single_pass=True):
     return iset
 
 
+def measure_contours(contours, um_pix=1.0, device=None):
+    """Morphometry records [n,16] (float64, device) of n explicit contours (each an int array [K,2] or OpenCV's [K,1,2]):
+    the kernel behind calculate_measurements (src/utils/measurements.py:114-233) for callers that hold contours."""
+    lib = _lib.load()
+    dev = _need_cuda(device)
+    n = len(contours)
+    lens = np.array([len(c) for c in contours], np.int64)
+    pt_off = np.zeros(n + 1, np.int64); pt_off[1:] = np.cumsum(lens)
+    flat = (np.concatenate([np.asarray(c).reshape(-1, 2) for c in contours]) if n and pt_off[-1] else np.zeros((0, 2), np.int64))
+    if flat.size and (flat.min() < 0 or flat.max() > 0xFFFF):
+        raise _lib.EmiaError("contour coordinates must lie in [0, 65535]")
+    packed = (flat[:, 0].astype(np.uint32) | (flat[:, 1].astype(np.uint32) << 16)).astype(np.uint32)
+    cont_off = np.arange(n + 1, dtype=np.int64)
+    cstart = np.zeros(2 * n + 1, np.int32)
+    cstart[1:2 * n:2] = lens.astype(np.int32)           # instance i: entries (0, len_i) at cont_off[i] + i = 2 i
+    scr = ((28 * lens + 64 + 15) // 16) * 16
+    scr_off = np.zeros(n + 1, np.int64); scr_off[1:] = np.cumsum(scr)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
+    d_pts = t(packed.view(np.int32)) if packed.size else torch.zeros(1, dtype=torch.int32, device=dev)
+    d_cont, d_pt, d_cs, d_scr = t(cont_off), t(pt_off), t(cstart), t(scr_off)
+    records = torch.empty((max(n, 1), REC_FIELDS), dtype=torch.float64, device=dev)
+    rec_inst = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    perim0 = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
+    scratch = torch.empty(max(int(scr_off[-1]), 16), dtype=torch.uint8, device=dev)
+    dummy_meta = torch.zeros((max(n, 1), 8), dtype=torch.int32, device=dev)
+    _lib.check(lib.emia_contour_measure_stored(_ptr(dummy_meta), n, _ptr(d_cont), _ptr(d_pt), _ptr(d_cs), 0, _ptr(d_scr), float(um_pix), 0.0,
+                                               _ptr(d_pts), _ptr(records), _ptr(rec_inst), _ptr(perim0), _ptr(scratch), _stream()),
+               "emia_contour_measure_stored")
+    LAUNCHES["count"] += 2
+    return records[:n]
+
+
 def contours_to_host(iset):
     """Host copy of the contour vertex lists: list (per instance) of lists (OpenCV order) of int32 [k,2] arrays."""
     pts = iset.pts.cpu().numpy().view(np.uint32)
@@ -693,6 +725,19 @@ def rle_encode(iset, idx=None):
                                    _ptr(runs), st), "emia_rle_encode")
     LAUNCHES["count"] += 2
     return run_off, runs[:R]
+
+
+def gray_hist(iset, image):
+    """int32 [n,256] grey-level histograms of the image pixels under every instance (image: H x W x 3 BGR or H x W uint8)."""
+    lib = _lib.load()
+    img = torch.as_tensor(np.ascontiguousarray(image), device=iset.device)
+    assert img.dtype == torch.uint8 and img.shape[0] == iset.H and img.shape[1] == iset.W
+    ch = 1 if img.dim() == 2 else int(img.shape[2])
+    out = torch.empty((max(iset.n, 1), 256), dtype=torch.int32, device=iset.device)
+    _lib.check(lib.emia_gray_hist(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), iset.n, _ptr(img), iset.H, iset.W, ch, _ptr(out),
+                                  _stream()), "emia_gray_hist")
+    LAUNCHES["count"] += 1
+    return out[:iset.n]
 
 
 def moments01(iset):

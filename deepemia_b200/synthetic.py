@@ -79,3 +79,46 @@ POLYHIPES_RULES = {
     'overlap_rules': {0: {'allow_overlap': False, 'allow_touch': True, 'max_iou_threshold': 0.30},
                       1: {'allow_overlap': False, 'allow_touch': True, 'max_iou_threshold': 0.50}},
 }
+
+
+class FakeHeadPredictor:
+    """A deterministic stand-in for the Mask R-CNN heads (Detectron2 is absent): the head outputs of an image are a
+    pure function of the image bytes (CRC32 -> seed), so the reference functions (fed the Detectron2-paste oracle of these heads)
+    and the CUDA mirror (fed the raw heads) see the same detections for every image, tile, and rescaled image they derive.
+    Test / golden-vector infrastructure."""
+
+    def __init__(self, base_seed=0, n=28, duplicate_frac=0.35, rmin=5.0, rmax=15.0, margin=6, input_scale=1.0, zero_score=False):
+        self.base_seed, self.n, self.dup, self.rmin, self.rmax, self.margin = base_seed, n, duplicate_frac, rmin, rmax, margin
+        self.input_scale, self.zero_score = input_scale, zero_score
+        self.calls = 0
+
+    def raw_heads(self, image):
+        """(probs [n,28,28] f32, boxes [n,4] f32 in model-input coordinates, scores, classes int64, (in_h, in_w))."""
+        import zlib
+        H, W = image.shape[:2]
+        seed = (zlib.crc32(np.ascontiguousarray(image).tobytes()) ^ (self.base_seed * 2654435761)) & 0x7FFFFFFF
+        n = self.n + int(seed % 7)
+        r_hi = min(self.rmax, max(self.rmin + 1.0, min(H, W) / 6.0))
+        probs, boxes, scores, classes = synthetic_heads(seed, n, H, W, duplicate_frac=self.dup, rmin=self.rmin, rmax=r_hi,
+                                                        margin=self.margin)
+        rng = np.random.default_rng(seed + 1)
+        # a few degenerate / out-of-frame boxes exercise Boxes.nonempty() and the clipping
+        boxes[0] = [W + 5.0, 3.0, W + 20.0, 18.0]
+        boxes[1, 2] = boxes[1, 0]
+        boxes[2] += np.array([-boxes[2, 0] - 4.0, 0.0, -boxes[2, 0] - 4.0, 0.0], np.float32)      # hangs over the left edge
+        if self.zero_score:
+            scores[3] = 0.0
+        in_h, in_w = int(round(H * self.input_scale)), int(round(W * self.input_scale))
+        boxes = boxes * np.array([in_w / W, in_h / H, in_w / W, in_h / H], np.float32)
+        _ = rng
+        self.calls += 1
+        return probs, boxes.astype(np.float32), scores.astype(np.float32), classes.astype(np.int64), (in_h, in_w)
+
+    def heads(self, image):
+        """The pre-paste hook of deepemia_b200.functions.inference (CUDA tensors)."""
+        import torch
+        from .functions.inference import HeadOutputs
+        probs, boxes, scores, classes, in_size = self.raw_heads(image)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
+        return HeadOutputs(t(probs), t(boxes), t(scores), t(classes), in_size)

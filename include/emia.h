@@ -252,6 +252,11 @@ int emia_rle_encode(const uint32_t* crops, const emia_inst_meta* meta, const int
 int emia_moments01(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n, int64_t* out,
                    void* stream);
 
+/* 256-bin grey-level histogram of the image pixels under every instance (contrast d10/d50/d90, src/utils/measurements.py:
+ * 195-215): image = H x W x channels bytes (3: BGR -> cv2's 8-bit BGR2GRAY fixed-point formula; 1: grey), hist[n][256]. */
+int emia_gray_hist(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n,
+                   const uint8_t* image, int H, int W, int channels, int32_t* hist, void* stream);
+
 /* pairwise helpers (drop-in for iou / calculate_iou / calculate_containment on explicit pairs):
  * out[k] = {intersection, area_a, area_b} for pairs (pa[k], pb[k]). */
 int emia_pair_counts(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off,
