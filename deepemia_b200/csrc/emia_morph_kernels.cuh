@@ -121,6 +121,7 @@ __device__ void emia_cross_op(const EmiaPad& dst, const EmiaPad& src, int dilate
 __global__ void __launch_bounds__(32) k_morph(const uint32_t* __restrict__ crops, const emia_inst_meta* __restrict__ meta,
                                               const int64_t* __restrict__ crop_off, int64_t n, int H, int W, int op0, int op1, int op2,
                                               int op3, const int64_t* __restrict__ pad_off, uint32_t* __restrict__ work,
+                                              const emia_inst_meta* __restrict__ meta_out, const int64_t* __restrict__ crop_off_out,
                                               uint32_t* __restrict__ crops_out) {
     const int lane = threadIdx.x;
     const int64_t inst = blockIdx.x;
@@ -165,10 +166,13 @@ __global__ void __launch_bounds__(32) k_morph(const uint32_t* __restrict__ crops
         }
         EmiaPad t = cur; cur = other; other = t;
     }
-    uint32_t* out = crops_out + crop_off[inst];
-    for (int k = lane; k < m.ch * m.cw; k += 32) {
-        const int r = k / m.cw, c = k - r * m.cw;
-        out[k] = emia_pad_at(cur, r + 1, c + 1);
+    // output geometry: the input's, or (a chain that dilates first) the crop grown by one pixel towards every frame border —
+    // out-of-frame neighbours are ignored by the erosion, so a closing can grow a mask that ends one pixel short of the border
+    const emia_inst_meta mo = meta_out[inst];
+    uint32_t* out = crops_out + crop_off_out[inst];
+    for (int k = lane; k < mo.ch * mo.cw; k += 32) {
+        const int r = k / mo.cw, c = k - r * mo.cw;
+        out[k] = emia_pad_at(cur, mo.ry0 + r - (m.ry0 - 1), mo.wc0 + c - (m.wc0 - 1));
     }
 }
 
@@ -272,6 +276,29 @@ __global__ void k_morph_plan(const emia_inst_meta* __restrict__ meta, int64_t n,
     const emia_inst_meta m = meta[i];
     pad_words[i] = (m.ch > 0 && m.cw > 0) ? (int64_t)(m.ch + 2) * (m.cw + 2) : 0;
 }
+// geometry of the result of a chain that may grow the mask by one pixel (see k_morph)
+__global__ void k_morph_grow_plan(const emia_inst_meta* __restrict__ meta, int64_t n, int H, int W, emia_inst_meta* __restrict__ meta_out,
+                                  int64_t* __restrict__ crop_words) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    emia_inst_meta m = meta[i];
+    if (m.ch > 0 && m.cw > 0) {
+        const int y0 = max(m.ry0 - 1, 0), y1 = min(m.ry0 + m.ch + 1, H);
+        const int x0 = max(m.rx0 - 1, 0), x1 = min(m.rx1 + 1, W);
+        m.ry0 = y0; m.ch = y1 - y0; m.rx0 = x0; m.rx1 = x1;
+        m.wc0 = x0 >> 5; m.cw = ((x1 - 1) >> 5) - m.wc0 + 1;
+    }
+    meta_out[i] = m;
+    crop_words[i] = (int64_t)m.ch * m.cw;
+}
+extern "C" int emia_morph_grow_plan(const emia_inst_meta* meta, int64_t n, int H, int W, emia_inst_meta* meta_out, int64_t* crop_words,
+                                    void* stream) {
+    if (n < 0 || H <= 0 || W <= 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_morph_grow_plan: %s", "bad argument");
+    if (n == 0) return EMIA_OK;
+    if (!meta || !meta_out || !crop_words) return emia_fail(EMIA_ERR_BAD_ARG, "emia_morph_grow_plan: %s", "null pointer");
+    k_morph_grow_plan<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(meta, n, H, W, meta_out, crop_words);
+    return emia_check_launch("emia_morph_grow_plan launch: %s");
+}
 
 extern "C" int emia_morph_plan(const emia_inst_meta* meta, int64_t n, int64_t* pad_words, void* stream) {
     if (n < 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_morph_plan: %s", "bad n");
@@ -281,17 +308,20 @@ extern "C" int emia_morph_plan(const emia_inst_meta* meta, int64_t n, int64_t* p
     return emia_check_launch("emia_morph_plan launch: %s");
 }
 extern "C" int emia_morph(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n, int H, int W,
-                          const int32_t* ops_host, int32_t n_ops, const int64_t* pad_off, uint32_t* work, uint32_t* crops_out,
-                          void* stream) {
+                          const int32_t* ops_host, int32_t n_ops, const int64_t* pad_off, uint32_t* work,
+                          const emia_inst_meta* meta_out, const int64_t* crop_off_out, uint32_t* crops_out, void* stream) {
     if (n < 0 || n_ops < 1 || n_ops > 4 || !ops_host) return emia_fail(EMIA_ERR_BAD_ARG, "emia_morph: %s", "bad argument");
     if (n == 0) return EMIA_OK;
     if (!crops || !meta || !crop_off || !pad_off || !work || !crops_out) return emia_fail(EMIA_ERR_BAD_ARG, "emia_morph: %s", "null pointer");
+    if (!meta_out) { meta_out = meta; crop_off_out = crop_off; }
+    if (!crop_off_out) return emia_fail(EMIA_ERR_BAD_ARG, "emia_morph: %s", "meta_out without crop_off_out");
     int ops[4] = {0, 0, 0, 0};
     for (int i = 0; i < n_ops; ++i) {
         if (ops_host[i] < 1 || ops_host[i] > 3) return emia_fail(EMIA_ERR_BAD_ARG, "emia_morph: %s", "unknown operator");
         ops[i] = ops_host[i];
     }
-    k_morph<<<(unsigned)n, 32, 0, (cudaStream_t)stream>>>(crops, meta, crop_off, n, H, W, ops[0], ops[1], ops[2], ops[3], pad_off, work, crops_out);
+    k_morph<<<(unsigned)n, 32, 0, (cudaStream_t)stream>>>(crops, meta, crop_off, n, H, W, ops[0], ops[1], ops[2], ops[3], pad_off, work,
+                                                          meta_out, crop_off_out, crops_out);
     return emia_check_launch("emia_morph launch: %s");
 }
 extern "C" int emia_overlap_first_come(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, const int32_t* bbox,

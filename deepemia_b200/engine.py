@@ -229,17 +229,19 @@ def _pad_plan(iset):
     return pad_off, work
 
 
-def _derived(iset, crops):
-    """A new InstanceSet with the geometry (meta, crop_off) of `iset` and new crop bits; bbox/area recomputed."""
+def _derived(iset, crops, geometry=None):
+    """A new InstanceSet with new crop bits in the geometry (meta, crop_off, total words) of `iset` or the given one; bbox/area
+    recomputed."""
     lib = _lib.load()
+    meta, crop_off, total = geometry if geometry is not None else (iset.meta, iset.crop_off, iset.total_crop_words)
     bbox = torch.empty_like(iset.bbox)
     area = torch.empty_like(iset.area)
-    _lib.check(lib.emia_crop_stats(_ptr(crops), _ptr(iset.meta), _ptr(iset.crop_off), iset.n, _ptr(bbox), _ptr(area), _stream()),
+    _lib.check(lib.emia_crop_stats(_ptr(crops), _ptr(meta), _ptr(crop_off), iset.n, _ptr(bbox), _ptr(area), _stream()),
                "emia_crop_stats")
     LAUNCHES["count"] += 1
-    out = InstanceSet(n=iset.n, H=iset.H, W=iset.W, meta=iset.meta, crop_off=iset.crop_off, crops=crops, bbox=bbox, area=area,
-                      scores=iset.scores, classes=iset.classes, total_crop_words=iset.total_crop_words)
-    if "pad_plan" in iset.extra:
+    out = InstanceSet(n=iset.n, H=iset.H, W=iset.W, meta=meta, crop_off=crop_off, crops=crops, bbox=bbox, area=area,
+                      scores=iset.scores, classes=iset.classes, total_crop_words=total)
+    if geometry is None and "pad_plan" in iset.extra:
         out.extra["pad_plan"] = iset.extra["pad_plan"]
     return out
 
@@ -250,13 +252,30 @@ def morph(iset, ops):
     lib = _lib.load()
     ops = np.ascontiguousarray(ops, dtype=np.int32)
     pad_off, work = _pad_plan(iset)
-    crops = torch.empty_like(iset.crops)
+    structuring = [int(o) for o in ops if int(o) != MORPH_FILL]
+    grows = bool(structuring) and structuring[0] == MORPH_DILATE
+    geometry = None
+    meta_out = crop_off_out = None
+    if grows and iset.n:
+        # closing / dilation: the result may be one pixel larger (always for a dilation; for a closing next to the frame border)
+        meta_out = torch.empty_like(iset.meta)
+        crop_off_out = torch.empty(iset.n + 1, dtype=torch.int64, device=iset.device)
+        _lib.check(lib.emia_morph_grow_plan(_ptr(iset.meta), iset.n, iset.H, iset.W, _ptr(meta_out), _ptr(crop_off_out), _stream()),
+                   "emia_morph_grow_plan")
+        exclusive_scan_(crop_off_out)
+        LAUNCHES["count"] += 1
+        total = int(crop_off_out[iset.n].item())
+        geometry = (meta_out, crop_off_out, total)
+        crops = torch.empty(max(total, 1), dtype=torch.int32, device=iset.device)
+    else:
+        crops = torch.empty_like(iset.crops)
     if iset.n:
         with _stage("k2_morph"):
             _lib.check(lib.emia_morph(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), iset.n, iset.H, iset.W, ops.ctypes.data,
-                                      len(ops), _ptr(pad_off), _ptr(work), _ptr(crops), _stream()), "emia_morph")
+                                      len(ops), _ptr(pad_off), _ptr(work), _ptr(meta_out), _ptr(crop_off_out), _ptr(crops), _stream()),
+                       "emia_morph")
         LAUNCHES["count"] += 1
-    return _derived(iset, crops)
+    return _derived(iset, crops, geometry)
 
 
 def overlap_first_come(iset, groups):

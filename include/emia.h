@@ -203,9 +203,14 @@ int emia_containment_rules(const uint32_t* crops, const emia_inst_meta* meta, co
 #define EMIA_MORPH_ERODE 2
 #define EMIA_MORPH_DILATE 3
 int emia_morph_plan(const emia_inst_meta* meta, int64_t n, int64_t* pad_words, void* stream);
+/* meta_out / crop_off_out (NULL: the input geometry): geometry of the result.  A chain whose first structuring operator is a
+ * dilation (closing, plain dilation) can grow a mask by one pixel — also a closing, next to the frame border, where the
+ * erosion ignores out-of-frame neighbours — so its result needs the grown geometry of emia_morph_grow_plan (caller scans). */
+int emia_morph_grow_plan(const emia_inst_meta* meta, int64_t n, int H, int W, emia_inst_meta* meta_out, int64_t* crop_words,
+                         void* stream);
 int emia_morph(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n, int H, int W,
-               const int32_t* ops_host, int32_t n_ops, const int64_t* pad_off, uint32_t* work, uint32_t* crops_out,
-               void* stream);
+               const int32_t* ops_host, int32_t n_ops, const int64_t* pad_off, uint32_t* work,
+               const emia_inst_meta* meta_out, const int64_t* crop_off_out, uint32_t* crops_out, void* stream);
 int emia_overlap_first_come(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off,
                             const int32_t* bbox, const int32_t* cap_off, int32_t G, int32_t total_cap,
                             const int32_t* in_len, const int32_t* in_idx, const int64_t* pad_off, uint32_t* work,

@@ -136,3 +136,32 @@ def test_postprocess_masks_column_gate(cuda_device):
     ref = morphology.postprocess_masks(np.stack(ms), np.ones(len(ms), np.float32), (H, W), min_crys_size=1000)
     _, gated = engine.postprocess_masks(iset, engine.groups_from_offsets([0, len(ms)], cuda_device), min_crys_size=1000)
     assert ref == [] and gated.to_lists()[0] == []
+
+
+def test_closing_grows_next_to_the_frame_border(cuda_device):
+    """Out-of-frame neighbours are ignored by the erosion, so the closing of a mask that ends ONE pixel short of the frame border
+    reaches the border (regression: the result does not fit the input's bbox crop)."""
+    from scipy import ndimage as ndi
+    H, W = 64, 96
+    ms = []
+    for (y0, y1, x0, x1) in ((1, 20, 30, 50), (40, H - 1, 30, 50), (20, 40, 1, 20), (20, 40, 70, W - 1), (1, H - 1, 1, W - 1),
+                             (1, 10, 31, 33), (50, H - 1, 63, 65)):
+        m = np.zeros((H, W), np.uint8); cv2.ellipse(m, ((x0 + x1) // 2, (y0 + y1) // 2), ((x1 - x0) // 2, (y1 - y0) // 2), 0, 0, 360, 1, -1)
+        m[:y0] = 0; m[y1:] = 0; m[:, :x0] = 0; m[:, x1:] = 0
+        ms.append(m)
+    iset = engine.from_masks(torch.as_tensor(np.stack(ms), device=cuda_device))
+    got = _bits(engine.morph(iset, [engine.MORPH_FILL, engine.MORPH_DILATE, engine.MORPH_ERODE]))
+    grew = 0
+    for i, m in enumerate(ms):
+        ref = morphology.erosion(morphology.dilation(ndi.binary_fill_holes(m).astype(np.uint8)))
+        assert np.array_equal(got[i], ref), f"mask {i}"
+        grew += int(ref.sum() > 0 and (dedup_bbox(ref) != dedup_bbox(m)))
+    assert grew > 0
+    got = _bits(engine.morph(iset, [engine.MORPH_DILATE]))
+    for i, m in enumerate(ms):
+        assert np.array_equal(got[i], morphology.dilation(m)), f"dilation of mask {i}"
+
+
+def dedup_bbox(m):
+    ys, xs = np.nonzero(m)
+    return (ys.min(), xs.min(), ys.max(), xs.max())
