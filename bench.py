@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--paste-ctas", type=int, default=0, help="resident paste CTAs per SM (0 = kernel default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="extra untimed pass with per-stage CUDA events (stderr)")
+    ap.add_argument("--device-pass-only", action="store_true", help="profiling aid: run only the warm-up + timed device-resident steps")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -248,6 +249,14 @@ def main():
     per_step_ms = [step_ev[i].elapsed_time(step_ev[i + 1]) for i in range(args.steps)]
     launches = engine.LAUNCHES["count"] - l0
     ms_total = ev[0].elapsed_time(ev[1])
+    if args.device_pass_only:
+        if sampler is not None:
+            sampler.terminate()
+        if rank == 0:
+            print(json.dumps({"device_pass_only": True, "ms_per_step": ms_total / args.steps, "instances": n_local}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if args.breakdown and rank == 0:
         # un-overlapped pass (one batch, one stream) with per-stage CUDA events
         engine.STAGE_TIMING["enabled"] = True
@@ -301,6 +310,12 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
+        traffic = None
+        try:     # DRAM bytes per instance of the paste kernel from the committed ncu --set full capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "k1_dram_traffic.json")))
+            traffic = float(tj["dram_bytes_per_instance"]) * n_local
+        except Exception:
+            pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)"
         crop_bytes = 4.0 * total_crop_words
@@ -324,12 +339,13 @@ def main():
             "e2e": {"value": e2e_val, "unit": "instances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_paste (K1 paste+threshold+bitpack)", "achieved": k1_gbs, "peak": peak,
-                         "unit": "GB/s", "frac": k1_gbs / peak, "traffic": None, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": "k_paste_v2 (K1 paste+threshold+bitpack)", "achieved": k1_gbs, "peak": peak,
+                         "unit": "GB/s", "frac": k1_gbs / peak, "traffic": traffic, "algorithmic_bytes": k1_bytes, "peak_source": peak_src,
                          "k1_ms_per_step": k1, "k1_launches_per_step": len(res), "k1_share_of_step": k1 / ms_step,
                          "k1_alone_ms": float(np.median(k1_alone)), "k1_alone_gbs": k1_bytes / (float(np.median(k1_alone)) * 1e-3) / 1e9,
-                         "note": "achieved = K1 algorithmic bytes / sum of its CUDA-event durations on the paste stream while the "
-                                 "contour / de-dup / morphometry kernels of the previous tile batch run on the post stream",
+                         "note": "achieved = K1 algorithmic bytes of rank 0 per step / its CUDA-event duration on the stream it is launched on "
+                                 "(one launch per tile batch; tile_batches = 1: nothing overlaps it); traffic = dram__bytes_read+write "
+                                 "of the same kernel from profiles/k1_dram_traffic.json (ncu --set full), scaled to this step",
                          "path_achieved_gbs": path_bytes / (ms_step * 1e-3) / 1e9,
                          "path_frac": path_bytes / (ms_step * 1e-3) / 1e9 / peak},
         }
