@@ -56,7 +56,7 @@ int sim_min_area_rect(const uint32_t* pts, int n, int clockwise, float* rect, fl
 
 // out[5] = cx, cy, w, h, angle
 int sim_fit_ellipse(const uint32_t* pts, int n, float* out) {
-    EmiaEllipse e = emia_fit_ellipse_general(pts, n);
+    EmiaEllipse e = emia_fit_ellipse(pts, n);
     out[0] = e.cx; out[1] = e.cy; out[2] = e.w; out[3] = e.h; out[4] = e.angle;
     return e.ok;
 }

@@ -94,7 +94,7 @@ def test_fit_ellipse_axes(L):
     tot = exact = 0
     for m in _shapes(rng, 1500):
         for c in cv2.findContours(m, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)[0]:
-            if len(c) < 6 or cv2.contourArea(c) < 5:     # n == 5 takes OpenCV's "direct" solver (known gap)
+            if len(c) < 5 or cv2.contourArea(c) < 5:
                 continue
             p = _pack(c); out = np.zeros(5, np.float32)
             L.sim_fit_ellipse(_p(p), len(p), _p(out))
@@ -104,6 +104,37 @@ def test_fit_ellipse_axes(L):
             exact += np.array_equal(ref, out[2:4])
             np.testing.assert_allclose(out[2:4], ref, rtol=1e-5)
     assert exact >= 0.99 * tot
+
+
+def test_fit_ellipse_small_and_degenerate_shapes(L):
+    """Tiny / thin blobs: 5-vertex contours (OpenCV's direct solver), two-pixel-wide strips (degenerate conic: the centre system
+    is singular -> minimum-norm solve), shapes with |dx| == |dy| for every vertex (rank-deficient stage 2).  cv2.fitEllipse
+    itself is non-reproducible on inputs where it perturbs the points with an RNG (call it twice: two answers) — those are
+    skipped; of the rest at most 1 % may differ (axes that are pure rounding noise, e.g. 3.7e7 px for a two-row strip)."""
+    rng = np.random.default_rng(0)
+    tot = bad = nondet = n5 = 0
+    for _ in range(6000):
+        m = np.zeros((16, 24), np.uint8)
+        h, w, y, x = rng.integers(1, 5), rng.integers(2, 12), rng.integers(2, 8), rng.integers(2, 8)
+        m[y:y + h, x:x + w] = 1
+        for _ in range(rng.integers(0, 5)):
+            m[rng.integers(y, y + h), rng.integers(x, x + w)] = rng.integers(0, 2)
+        for c in cv2.findContours(m * 255, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)[0]:
+            if len(c) < 5 or cv2.contourArea(c) < 5:
+                continue
+            ref, ref2 = cv2.fitEllipse(c), cv2.fitEllipse(c)
+            if ref != ref2:
+                nondet += 1
+                continue
+            if not np.all(np.isfinite(ref[1])):
+                continue
+            p = _pack(c); out = np.zeros(5, np.float32)
+            L.sim_fit_ellipse(_p(p), len(p), _p(out))
+            tot += 1
+            n5 += len(c) == 5
+            bad += not np.allclose(out[2:4], np.array(ref[1], np.float32), rtol=1e-5, atol=1e-9)
+    assert tot > 1000 and n5 > 50
+    assert bad <= 0.01 * tot, (bad, tot, nondet)
 
 
 def test_measure_contour_vs_reference_golden(L):
