@@ -292,14 +292,33 @@ def main():
     ev[1].record()
     barrier()
     ms_e2e = ev[0].elapsed_time(ev[1])
+    # the same with the head probabilities as fp16 (what the mask head emits under the reference's default AMP autocast;
+    # the synthetic probabilities are fp16-representable, K1 widens them exactly): half the H2D bytes
+    h_probs16 = h_probs.to(torch.float16).pin_memory()
+    assert torch.equal(h_probs16.to(torch.float32), h_probs)
+    def e2e16_step():
+        r = pipe_e2e.run(h_probs16, h_boxes, h_scores, h_classes, offs, to_host=True)
+        torch.cuda.current_stream().synchronize()
+        return r
+    for _ in range(2):
+        res_h16 = e2e16_step()
+    barrier()
+    ev[0].record()
+    for _ in range(args.steps):
+        res_h16 = e2e16_step()
+    ev[1].record()
+    barrier()
+    ms_e2e16 = ev[0].elapsed_time(ev[1])
+    same16 = all(torch.equal(a["host"]["records"], b["host"]["records"]) and torch.equal(a["host"]["kept_idx"], b["host"]["kept_idx"])
+                 for a, b in zip(res_h, res_h16))
     if sampler is not None:
         sampler.terminate()
-    t = torch.tensor([ms_total, ms_e2e, float(np.mean(k1_ms))], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, ms_e2e, float(np.mean(k1_ms)), ms_e2e16], dtype=torch.float64, device=dev)
     cnt = torch.tensor([float(n_local)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms_total, ms_e2e, k1 = t.tolist()
+    ms_total, ms_e2e, k1, ms_e2e16 = t.tolist()
     n_global = cnt.item()
     if rank == 0:
         ms_step = ms_total / args.steps
@@ -338,6 +357,10 @@ def main():
             "clocks": _clock_summary(clk_path, local),
             "e2e": {"value": e2e_val, "unit": "instances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
+            "e2e_fp16_heads": {"value": n_global / (ms_e2e16 / args.steps * 1e-3), "unit": "instances/s",
+                               "h2d_bytes_per_step": int(h_probs16.numel() * 2 + h_boxes.numel() * 4 + h_scores.numel() * 4 + h_classes.numel() * 4),
+                               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e16 / args.steps, "identical_results_to_f32": bool(same16),
+                               "note": "extra: same step with the 28x28 probabilities transported as fp16 (AMP head output), widened exactly in K1"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_paste_v2 (K1 paste+threshold+bitpack)", "achieved": k1_gbs, "peak": peak,
                          "unit": "GB/s", "frac": k1_gbs / peak, "traffic": traffic, "algorithmic_bytes": k1_bytes, "peak_source": peak_src,

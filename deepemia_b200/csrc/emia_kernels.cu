@@ -2,6 +2,7 @@
 // Build: nvcc -O3 -lineinfo -fmad=false -gencode arch=compute_100a,code=sm_100a -shared -Xcompiler -fPIC
 // (-fmad=false: no implicit FMA contraction; see core/emia_common.cuh).
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -509,11 +510,15 @@ __device__ __forceinline__ void emia_cp_async16(void* sdst, const void* gsrc) {
 }
 __device__ __forceinline__ int emia_clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+template <bool kHalf>
 __global__ void __launch_bounds__(EMIA_PASTE_THREADS, EMIA_P2_MIN_CTAS) k_paste_v2(
-    const float* __restrict__ probs, const float4* __restrict__ boxes, const emia_inst_meta* __restrict__ meta,
+    const void* __restrict__ probs_raw, const float4* __restrict__ boxes, const emia_inst_meta* __restrict__ meta,
     const int64_t* __restrict__ crop_off, int64_t n, float sx, float sy, int H, int W, uint32_t* __restrict__ frames,
     int64_t frame_slots, int pitch_words, uint32_t* __restrict__ crops, int32_t* __restrict__ bbox, int32_t* __restrict__ area) {
     __shared__ __align__(16) float s_pp[EMIA_P2_PAD_ROWS * EMIA_P2_PAD_STRIDE];   // padded probabilities
+    __shared__ __align__(16) __half s_half[kHalf ? EMIA_MASK_SIDE * EMIA_MASK_SIDE : 8];   // fp16 head outputs: staged, then widened
+    const float* probs = (const float*)probs_raw;
+    const __half* probs_h = (const __half*)probs_raw;
     __shared__ __align__(32) uint32_t s_tile[EMIA_PASTE_TILE_WORDS];              // one band of frame rows (chunk span)
     __shared__ int2 s_ctap[EMIA_P2_MAX_COLS];     // per column: (tile offset of tap i0, bits of w1); columns outside [rx0, rx1) read zeros
     __shared__ int2 s_rtap[EMIA_P2_BAND_ROWS];    // per row of the band: (tile offset of tap row, bits of w1)
@@ -534,7 +539,11 @@ __global__ void __launch_bounds__(EMIA_PASTE_THREADS, EMIA_P2_MIN_CTAS) k_paste_
         const bool live = m.valid && m.ch > 0 && m.cw > 0;
         if (tid < 5) s_red[tid] = (tid == 0) ? 0 : ((tid == 1 || tid == 2) ? 0x7fffffff : -1);
         // ---- 1. start the copy of the probabilities (28 rows x 7 chunks of 16 bytes -> padded tile rows 2..29, columns 4..31)
-        if (live && tid < EMIA_MASK_SIDE * 7) {
+        if (kHalf) {
+            // 784 halves = 98 chunks of 16 bytes; exact widening to float happens after the wait (AMP heads emit fp16)
+            if (live && tid < (EMIA_MASK_SIDE * EMIA_MASK_SIDE) / 8)
+                emia_cp_async16(&s_half[tid * 8], probs_h + inst * (EMIA_MASK_SIDE * EMIA_MASK_SIDE) + tid * 8);
+        } else if (live && tid < EMIA_MASK_SIDE * 7) {
             const int r = tid / 7, q = tid - r * 7;
             emia_cp_async16(&s_pp[(r + 2) * EMIA_P2_PAD_STRIDE + 4 + q * 4], probs + inst * (EMIA_MASK_SIDE * EMIA_MASK_SIDE) + r * EMIA_MASK_SIDE + q * 4);
         }
@@ -571,6 +580,14 @@ __global__ void __launch_bounds__(EMIA_PASTE_THREADS, EMIA_P2_MIN_CTAS) k_paste_
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
+        if (kHalf) {
+            if (live)
+                for (int k = tid; k < EMIA_MASK_SIDE * EMIA_MASK_SIDE; k += EMIA_PASTE_THREADS) {
+                    const int r = k / EMIA_MASK_SIDE, c = k - r * EMIA_MASK_SIDE;
+                    s_pp[(r + 2) * EMIA_P2_PAD_STRIDE + 4 + c] = __half2float(s_half[k]);
+                }
+            __syncthreads();
+        }
         if (live) {
             const int span_chunks = cc1 - cc0 + 1;
             const int span_words = span_chunks * 8;             // staged row width (32-byte chunk aligned)
@@ -667,6 +684,7 @@ extern "C" int emia_paste_threshold_bitpack(const float* probs, const float* box
     // bits 0-7: variant; bits 8-15: resident CTAs per SM (0 = default) — a smaller grid leaves SM room for other streams
     const int variant = variant_and_grid & 0xff;
     const int ctas_req = (variant_and_grid >> 8) & 0xff;
+    const bool probs_f16 = (variant_and_grid >> 16) & 1;      // EMIA_PASTE_PROBS_F16
     if (n < 0 || H <= 0 || W <= 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_paste_threshold_bitpack: %s", "bad shape");
     if (n == 0) return EMIA_OK;
     if (!probs || !boxes || !meta || !crop_off || !crops || !bbox || !area)
@@ -683,10 +701,15 @@ extern "C" int emia_paste_threshold_bitpack(const float* probs, const float* box
         (!frames || ((pitch_words & 7) == 0 && ((uintptr_t)frames & 31) == 0))) {
         const int64_t per_sm = ctas_req ? ctas_req : 32;
         const unsigned grid = (unsigned)(n < (int64_t)sms * per_sm ? n : (int64_t)sms * per_sm);
-        k_paste_v2<<<grid, EMIA_PASTE_THREADS, 0, st>>>(probs, (const float4*)boxes, meta, crop_off, n, scale_x, scale_y, H, W, frames,
-                                                        frames ? frame_slots : 1, pitch_words, crops, bbox, area);
+        if (probs_f16)
+            k_paste_v2<true><<<grid, EMIA_PASTE_THREADS, 0, st>>>(probs, (const float4*)boxes, meta, crop_off, n, scale_x, scale_y, H, W, frames,
+                                                                  frames ? frame_slots : 1, pitch_words, crops, bbox, area);
+        else
+            k_paste_v2<false><<<grid, EMIA_PASTE_THREADS, 0, st>>>(probs, (const float4*)boxes, meta, crop_off, n, scale_x, scale_y, H, W, frames,
+                                                                   frames ? frame_slots : 1, pitch_words, crops, bbox, area);
         return emia_check_launch("emia_paste_threshold_bitpack (v2) launch: %s");
     }
+    if (probs_f16) return emia_fail(EMIA_ERR_UNSUPPORTED, "emia_paste_threshold_bitpack: %s", "fp16 probabilities need variant 2 (W <= 2048, 32-byte frame rows)");
     if (variant == 1 && frames) {
         if (pitch_words * 4 > EMIA_BULK_BYTES) return emia_fail(EMIA_ERR_UNSUPPORTED, "emia_paste_threshold_bitpack: %s", "variant 1 needs a frame row <= 16 KB");
         const size_t smem = 2 * EMIA_BULK_BYTES + EMIA_MASK_SIDE * EMIA_MASK_SIDE * 4 + (size_t)max_cols * 12;

@@ -62,8 +62,9 @@ def _need_cuda(dev):
 
 
 def pitch_words_for(W):
-    """128-bit aligned bit rows: pitch = 16 * ceil(W / 128) bytes."""
-    return 4 * ((W + 127) // 128)
+    """256-bit aligned bit rows (the paste kernel writes frames with 256-bit stores): pitch = 32 * ceil(W / 256) bytes.
+    The ABI accepts any pitch that is a multiple of 4 words; pitches that are not multiples of 8 fall back to 128-bit stores."""
+    return 8 * ((W + 255) // 256)
 
 
 def exclusive_scan_(t):
@@ -129,7 +130,7 @@ def paste_plan(boxes, H, W, scale_x=1.0, scale_y=1.0):
 
 def paste(probs, boxes, H, W, scores=None, classes=None, scale_x=1.0, scale_y=1.0, frames=None, frame_slots=0,
           variant=2, crops_out=None, plan=None, ctas_per_sm=0):
-    """K1.  probs [n,28,28] f32, boxes [n,4] f32 xyxy (mask-head outputs, device tensors) -> InstanceSet.
+    """K1.  probs [n,28,28] f32 (or f16, as an AMP mask head emits them), boxes [n,4] f32 xyxy (device tensors) -> InstanceSet.
     frames: None (crops only), True (allocate n full frames) or a preallocated int32 [slots, H, pitch_words] ring.
     plan: (meta, crop_off, total_crop_words) from paste_plan() — possibly a slice of a larger plan whose crop offsets index
     the shared `crops_out` buffer; given a plan the call does not synchronise.
@@ -138,8 +139,9 @@ def paste(probs, boxes, H, W, scores=None, classes=None, scale_x=1.0, scale_y=1.
     lib = _lib.load()
     dev = probs.device
     n = int(probs.shape[0])
-    assert probs.dtype == torch.float32 and boxes.dtype == torch.float32 and probs.is_contiguous() and boxes.is_contiguous()
+    assert probs.dtype in (torch.float32, torch.float16) and boxes.dtype == torch.float32 and probs.is_contiguous() and boxes.is_contiguous()
     st = _stream()
+    f16 = (1 << 16) if probs.dtype == torch.float16 else 0      # EMIA_PASTE_PROBS_F16: AMP heads, widened exactly in the kernel
     if plan is None:
         meta, crop_off = paste_plan(boxes, H, W, scale_x, scale_y)
         total = int(crop_off[n].item()) if n else 0
@@ -163,7 +165,7 @@ def paste(probs, boxes, H, W, scores=None, classes=None, scale_x=1.0, scale_y=1.
     with _stage("k1_paste"):
         _lib.check(lib.emia_paste_threshold_bitpack(_ptr(probs), _ptr(boxes), _ptr(meta), _ptr(crop_off), n, scale_x, scale_y, H, W,
                                                     _ptr(frames), slots, pw, _ptr(crops), _ptr(bbox), _ptr(area),
-                                                    int(variant) | (int(ctas_per_sm) << 8), st),
+                                                    int(variant) | (int(ctas_per_sm) << 8) | f16, st),
                    "emia_paste_threshold_bitpack")
     LAUNCHES["count"] += 1
     return InstanceSet(n=n, H=H, W=W, meta=meta, crop_off=crop_off, crops=crops, bbox=bbox, area=area, scores=scores,

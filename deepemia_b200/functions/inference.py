@@ -205,7 +205,10 @@ def _predict(predictor, image):
     ho = predictor.heads(image)
     H, W = image.shape[:2]
     in_h, in_w = ho.input_size
-    probs = ho.probs.reshape(-1, engine.MASK_SIDE, engine.MASK_SIDE).to(torch.float32).contiguous()
+    probs = ho.probs.reshape(-1, engine.MASK_SIDE, engine.MASK_SIDE)
+    if probs.dtype not in (torch.float16, torch.float32):
+        probs = probs.to(torch.float32)
+    probs = probs.contiguous()                  # fp16 (AMP heads) is widened exactly inside K1
     iset = engine.paste(probs, ho.boxes.to(torch.float32).contiguous(), H, W, scale_x=float(W) / float(in_w),
                         scale_y=float(H) / float(in_h))
     valid = iset.valid.cpu().numpy()

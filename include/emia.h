@@ -35,6 +35,7 @@ extern "C" {
 #define EMIA_ERR_WORKSPACE (-4)
 
 #define EMIA_MASK_SIDE 28   /* Mask R-CNN mask head resolution */
+#define EMIA_PASTE_PROBS_F16 (1 << 16)
 #define EMIA_REC_FIELDS 16  /* doubles per measurement record, see emia_rec_field */
 
 typedef struct emia_inst_meta {
@@ -75,6 +76,8 @@ int emia_exclusive_scan_i64(int64_t* data, int64_t n, void* workspace, size_t wo
  *   variant (bits 0-7): 0 = 128-bit streaming stores, 1 = bulk shared->global copies (TMA engine);
  *   bits 8-15 of the same argument: resident CTAs per SM of the persistent grid (0 = default 8 / 4) — a smaller grid
  *   leaves SM room for the contour / de-dup kernels of the previous tile batch running on another stream.
+ *   bit 16 (EMIA_PASTE_PROBS_F16): `probs` holds IEEE half values (what the mask head emits under the reference's AMP autocast,
+ *   inference.py:1392-1396); they are widened exactly to float32 before sampling, as torch's grid_sample autocast does.
  *   meta / crop_off / probs / boxes / bbox / area may point INTO larger arrays (a batch of a bigger plan): crop_off
  *   values are absolute word offsets into `crops`. */
 int emia_paste_plan(const float* boxes, int64_t n, float scale_x, float scale_y, int H, int W,

@@ -70,6 +70,18 @@ def test_paste_matches_detectron2_oracle(cuda_device, variant, shape):
             k += 1
 
 
+def test_paste_fp16_heads_equal_fp32(cuda_device):
+    """AMP heads emit fp16 probabilities; K1 widens them exactly, so the masks equal those of the same values passed as fp32."""
+    H, W = 300, 333 + 19
+    probs, boxes, _, _ = _heads(77, 60, H, W, rmin=4, rmax=25, margin=10)
+    assert np.array_equal(probs, probs.astype(np.float16).astype(np.float32))
+    tp, tb = _dev(cuda_device, probs, boxes)
+    a = engine.paste(tp, tb, H, W, frames=True)
+    b = engine.paste(tp.to(torch.float16).contiguous(), tb, H, W, frames=True)
+    assert torch.equal(a.crops[:a.total_crop_words], b.crops[:b.total_crop_words]) and torch.equal(a.frames, b.frames)
+    assert torch.equal(a.area, b.area) and torch.equal(a.bbox, b.bbox)
+
+
 def test_exclusive_scan(cuda_device):
     rng = np.random.default_rng(0)
     for n in (0, 1, 5, 4096, 4097, 100_003, 1_022_339, 4_300_000):
