@@ -17,9 +17,11 @@
 #if defined(__CUDACC__)
 #define EMIA_HD __host__ __device__ __forceinline__
 #define EMIA_HD_NOINLINE __host__ __device__
+#define EMIA_HD_COLD __host__ __device__ __noinline__      // rarely taken paths: keep them out of the hot path's register budget
 #else
 #define EMIA_HD inline
 #define EMIA_HD_NOINLINE
+#define EMIA_HD_COLD
 #endif
 
 #ifndef M_PI

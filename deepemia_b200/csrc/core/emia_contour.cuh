@@ -30,7 +30,27 @@ struct EmiaContourOut {
     int overflow;      // set when a capacity was exceeded (results invalid)
     int max_len;       // longest contour (vertices)
     int store;         // 0: count only (pts / cstart untouched, capacities ignored)
+    // optional running cv2.arcLength of the contour being followed (track != 0): perim_last = arcLength(closed) of the most
+    // recently completed contour, i.e. of contours[0] in OpenCV's (reverse discovery) order once the crop is done
+    int track;
+    const float* diag; // table of fl32(sqrt(2 k^2)) or nullptr
+    double per, perim_last;
+    int first_x, first_y, last_x, last_y, cur_n;
 };
+
+#define EMIA_DIAG_TABLE 128
+// length of one closed-polygon segment as cv2.arcLength computes it: sqrtf((float)dx * dx + (float)dy * dy) in float32.
+// Segments of a CHAIN_APPROX_SIMPLE contour are axial runs (exactly k for k < 4096) or diagonal runs (diag[k] when the table
+// is given); every other case goes through sqrtf, so the value is bit-identical to the plain formula for ANY segment.
+EMIA_HD float emia_seg_len(int dx, int dy, const float* diag) {
+    dx = dx < 0 ? -dx : dx; dy = dy < 0 ? -dy : dy;
+    if ((dx == 0 || dy == 0) && (dx | dy) < 4096) return (float)(dx | dy);
+    if (diag && dx == dy && dx < EMIA_DIAG_TABLE) return diag[dx];
+    const float fx = (float)dx, fy = (float)dy;
+    const float dx2 = fx * fx;
+    const float dy2 = fy * fy;
+    return sqrtf(dx2 + dy2);
+}
 
 EMIA_HD void emia_contour_emit(EmiaContourOut& o, int fx, int fy) {
     if (o.store) {
@@ -38,6 +58,21 @@ EMIA_HD void emia_contour_emit(EmiaContourOut& o, int fx, int fy) {
         else o.overflow = 1;
     }
     o.n_pts++;
+    if (o.track) {
+        // every term is a float32 >= 1 (a multiple of 2^-23) and the sum stays below 2^20, so the double accumulation is exact
+        // and independent of the order in which cv2.arcLength adds the same terms
+        if (o.cur_n == 0) { o.first_x = fx; o.first_y = fy; }
+        else o.per += (double)emia_seg_len(fx - o.last_x, fy - o.last_y, o.diag);
+        o.last_x = fx; o.last_y = fy; o.cur_n++;
+    }
+}
+// a contour is complete
+EMIA_HD void emia_contour_close(EmiaContourOut& o) {
+    if (o.track) {
+        if (o.cur_n > 1) o.per += (double)emia_seg_len(o.first_x - o.last_x, o.first_y - o.last_y, o.diag);
+        o.perim_last = o.per;
+        o.per = 0.0; o.cur_n = 0;
+    }
 }
 
 struct EmiaMarks {
@@ -81,96 +116,129 @@ EMIA_HD uint32_t emia_nbr8(const EmiaBitView& v, int lx, int ly) {
 }
 
 // All external contours of the crop, in discovery (raster) order.  OpenCV returns them in REVERSE discovery order;
-// consumers iterate k = n_contours-1 .. 0.  mk/ng must hold h*wwords words each (zeroed here).
+// consumers iterate k = n_contours-1 .. 0.  mk/ng must hold h*wwords words each.
 //
-// Written as ONE flat loop over a two-phase state machine (scan for the next start pixel / one border-following step)
-// so that the 32 instances of a warp share the instruction stream: a lane in the "follow" phase executes the same
-// branch-free step (3x3 neighbour mask -> rotate -> count-trailing-zeros picks the next direction) whatever the shape.
-// marks_zeroed != 0: the caller cleared both planes already (the kernels clear the whole buffer with coalesced stores).
-EMIA_HD_NOINLINE void emia_find_external_contours(const EmiaBitView& v, uint32_t* mk, uint32_t* ng, EmiaContourOut& o, int marks_zeroed = 0) {
+// The algorithm is a two-phase state machine — SCAN for the next start pixel / one border-FOLLOWING step — exposed as
+// resumable step functions, so that a kernel can keep the 32 instances of a warp in ONE flat loop (every lane executes the
+// same branch-free following step: 3x3 neighbour mask -> rotate -> count-trailing-zeros picks the next direction) and hand a
+// lane its next instance inside that same loop (k_contour_trace_slab).  emia_find_external_contours is the plain driver.
+struct EmiaTraceState {
+    EmiaBitView v;
+    uint32_t* mk;
+    uint32_t* ng;
+    EmiaContourOut o;
+    int y, c;                 // scan position (row, word)
+    uint32_t done_mask;       // bits of the current word already examined
+    int x0, y0, x1, y1, x3, y3, s, prev_s, before;
+};
+#define EMIA_TRACE_SCAN 0
+#define EMIA_TRACE_FOLLOW 1
+#define EMIA_TRACE_DONE 2
+
+EMIA_HD void emia_trace_begin(EmiaTraceState& T) {
+    T.o.n_contours = 0; T.o.n_pts = 0; T.o.overflow = 0; T.o.max_len = 0;
+    T.o.per = 0.0; T.o.perim_last = 0.0; T.o.cur_n = 0;
+    if (T.o.store) T.o.cstart[0] = 0;
+    T.y = 0; T.c = 0; T.done_mask = 0u;
+    T.x0 = T.y0 = T.x1 = T.y1 = T.x3 = T.y3 = T.s = T.prev_s = T.before = 0;
+}
+
+// One scan step: walks the rest of the current row for a start candidate.  Returns the next phase.
+EMIA_HD int emia_trace_scan_step(EmiaTraceState& T) {
+    const EmiaBitView& v = T.v;
     const int ww = v.wwords;
-    const int nw = v.h * ww;
-    if (!marks_zeroed) for (int i = 0; i < nw; ++i) { mk[i] = 0u; ng[i] = 0u; }
-    o.n_contours = 0; o.n_pts = 0; o.overflow = 0; o.max_len = 0;
-    if (o.store) o.cstart[0] = 0;
-    int y = 0, c = 0;
-    uint32_t done_mask = 0u;            // bits of the current word already examined
-    int phase = 0;                      // 0: scan, 1: follow
-    int x0 = 0, y0 = 0, x1 = 0, y1 = 0, x3 = 0, y3 = 0, s = 0, prev_s = 0, before = 0;
-    for (;;) {
-        if (phase == 0) {
-            if (y >= v.h) break;
-            const uint32_t* row = v.bits + (size_t)y * v.pitch_words;
-            const uint32_t F = row[c];
-            const uint32_t left = (F << 1) | (c > 0 ? (row[c - 1] >> 31) : 0u);
-            const uint32_t cand = F & ~left & ~mk[y * ww + c] & ~done_mask;
-            if (cand == 0u) {
-                done_mask = 0u;
-                if (++c >= ww) { c = 0; ++y; }
-                continue;
-            }
-            const int b = emia_ctz(cand);
-            done_mask |= (b == 31) ? 0xFFFFFFFFu : ((2u << b) - 1u);
-            const int x = c * 32 + b;
-            // RETR_EXTERNAL: nearest marked pixel strictly left of x on this row must carry a negative label (or not exist)
-            {
-                int cc = c;
-                uint32_t mw = mk[y * ww + cc] & ((b == 0) ? 0u : ((1u << b) - 1u));
-                while (mw == 0u && cc > 0) { --cc; mw = mk[y * ww + cc]; }
-                if (mw != 0u) {
-                    const int hb = emia_msb(mw);
-                    if (!((ng[y * ww + cc] >> hb) & 1u)) continue;   // inside an already-followed outer border
-                }
-            }
-            if (o.store && o.n_contours >= o.cap_contours) { o.overflow = 1; return; }
-            before = o.n_pts;
-            const uint32_t N8 = emia_nbr8(v, x, y);
-            // first neighbour clockwise from W: directions 3,2,1,0,7,6,5 -> bit k of M
-            const uint32_t M = ((N8 >> 3) & 1u) | (((N8 >> 2) & 1u) << 1) | (((N8 >> 1) & 1u) << 2) | ((N8 & 1u) << 3) |
-                               (((N8 >> 7) & 1u) << 4) | (((N8 >> 6) & 1u) << 5) | (((N8 >> 5) & 1u) << 6);
-            const int wi = y * ww + (x >> 5);
-            const uint32_t bit = 1u << (x & 31);
-            if (M == 0u) {   // isolated pixel
-                mk[wi] |= bit; ng[wi] |= bit;
-                emia_contour_emit(o, v.x_origin + x, v.y_origin + y);
-                o.n_contours++;
-                if (o.n_pts - before > o.max_len) o.max_len = o.n_pts - before;
-                if (o.store) o.cstart[o.n_contours] = o.n_pts;
-                if (o.overflow) return;
-                continue;
-            }
-            s = (3 - emia_ctz(M)) & 7;
-            x0 = x; y0 = y; x1 = x + EMIA_DX(s); y1 = y + EMIA_DY(s);
-            x3 = x0; y3 = y0;
-            prev_s = s ^ 4;
-            phase = 1;
-        } else {
-            const uint32_t N8 = emia_nbr8(v, x3, y3);
-            const int s_end = s;
-            const int r = (s_end + 1) & 7;
-            const uint32_t rot = ((N8 >> r) | (N8 << (8 - r))) & 0xFFu;
-            s = (s_end + 1 + emia_ctz(rot)) & 7;                 // next foreground neighbour counter-clockwise
-            const int wi = y3 * ww + (x3 >> 5);
-            const uint32_t bit = 1u << (x3 & 31);
-            mk[wi] |= bit;                                        // label +2 ...
-            if ((unsigned)(s - 1) < (unsigned)s_end) ng[wi] |= bit;   // ... or -126 when the east neighbour was examined empty
-            if (s != prev_s) {
-                emia_contour_emit(o, v.x_origin + x3, v.y_origin + y3);
-                prev_s = s;
-            }
-            const int x4 = x3 + EMIA_DX(s), y4 = y3 + EMIA_DY(s);
-            if (x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) {
-                o.n_contours++;
-                if (o.n_pts - before > o.max_len) o.max_len = o.n_pts - before;
-                if (o.store) o.cstart[o.n_contours] = o.n_pts;
-                if (o.overflow) return;
-                phase = 0;
-                continue;
-            }
-            x3 = x4; y3 = y4;
-            s = (s + 4) & 7;
+    if (T.y >= v.h) return EMIA_TRACE_DONE;
+    const uint32_t* row = v.bits + (size_t)T.y * v.pitch_words;
+    const uint32_t* mrow = T.mk + T.y * ww;
+    uint32_t cand = 0u;
+    for (; T.c < ww; ++T.c, T.done_mask = 0u) {
+        const uint32_t F = row[T.c];
+        const uint32_t left = (F << 1) | (T.c > 0 ? (row[T.c - 1] >> 31) : 0u);
+        cand = F & ~left & ~mrow[T.c] & ~T.done_mask;
+        if (cand) break;
+    }
+    if (!cand) { T.c = 0; ++T.y; T.done_mask = 0u; return EMIA_TRACE_SCAN; }
+    const int c = T.c, y = T.y;
+    const int b = emia_ctz(cand);
+    T.done_mask |= (b == 31) ? 0xFFFFFFFFu : ((2u << b) - 1u);
+    const int x = c * 32 + b;
+    // RETR_EXTERNAL: nearest marked pixel strictly left of x on this row must carry a negative label (or not exist)
+    {
+        int cc = c;
+        uint32_t mw = mrow[cc] & ((b == 0) ? 0u : ((1u << b) - 1u));
+        while (mw == 0u && cc > 0) { --cc; mw = mrow[cc]; }
+        if (mw != 0u) {
+            const int hb = emia_msb(mw);
+            if (!((T.ng[y * ww + cc] >> hb) & 1u)) return EMIA_TRACE_SCAN;   // inside an already-followed outer border
         }
     }
+    EmiaContourOut& o = T.o;
+    if (o.store && o.n_contours >= o.cap_contours) { o.overflow = 1; return EMIA_TRACE_DONE; }
+    T.before = o.n_pts;
+    const uint32_t N8 = emia_nbr8(v, x, y);
+    // first neighbour clockwise from W: directions 3,2,1,0,7,6,5 -> bit k of M
+    const uint32_t M = ((N8 >> 3) & 1u) | (((N8 >> 2) & 1u) << 1) | (((N8 >> 1) & 1u) << 2) | ((N8 & 1u) << 3) |
+                       (((N8 >> 7) & 1u) << 4) | (((N8 >> 6) & 1u) << 5) | (((N8 >> 5) & 1u) << 6);
+    const int wi = y * ww + (x >> 5);
+    const uint32_t bit = 1u << (x & 31);
+    if (M == 0u) {   // isolated pixel
+        T.mk[wi] |= bit; T.ng[wi] |= bit;
+        emia_contour_emit(o, v.x_origin + x, v.y_origin + y);
+        emia_contour_close(o);
+        o.n_contours++;
+        if (o.n_pts - T.before > o.max_len) o.max_len = o.n_pts - T.before;
+        if (o.store) o.cstart[o.n_contours] = o.n_pts;
+        return o.overflow ? EMIA_TRACE_DONE : EMIA_TRACE_SCAN;
+    }
+    T.s = (3 - emia_ctz(M)) & 7;
+    T.x0 = x; T.y0 = y; T.x1 = x + EMIA_DX(T.s); T.y1 = y + EMIA_DY(T.s);
+    T.x3 = x; T.y3 = y;
+    T.prev_s = T.s ^ 4;
+    return EMIA_TRACE_FOLLOW;
+}
+
+// One border-following step.  Returns the next phase.
+EMIA_HD int emia_trace_follow_step(EmiaTraceState& T) {
+    const EmiaBitView& v = T.v;
+    const int ww = v.wwords;
+    EmiaContourOut& o = T.o;
+    const uint32_t N8 = emia_nbr8(v, T.x3, T.y3);
+    const int s_end = T.s;
+    const int r = (s_end + 1) & 7;
+    const uint32_t rot = ((N8 >> r) | (N8 << (8 - r))) & 0xFFu;
+    const int s = (s_end + 1 + emia_ctz(rot)) & 7;                 // next foreground neighbour counter-clockwise
+    const int wi = T.y3 * ww + (T.x3 >> 5);
+    const uint32_t bit = 1u << (T.x3 & 31);
+    T.mk[wi] |= bit;                                                // label +2 ...
+    if ((unsigned)(s - 1) < (unsigned)s_end) T.ng[wi] |= bit;       // ... or -126 when the east neighbour was examined empty
+    if (s != T.prev_s) {
+        emia_contour_emit(o, v.x_origin + T.x3, v.y_origin + T.y3);
+        T.prev_s = s;
+    }
+    const int x4 = T.x3 + EMIA_DX(s), y4 = T.y3 + EMIA_DY(s);
+    if (x4 == T.x0 && y4 == T.y0 && T.x3 == T.x1 && T.y3 == T.y1) {
+        emia_contour_close(o);
+        o.n_contours++;
+        if (o.n_pts - T.before > o.max_len) o.max_len = o.n_pts - T.before;
+        if (o.store) o.cstart[o.n_contours] = o.n_pts;
+        T.s = s;
+        return o.overflow ? EMIA_TRACE_DONE : EMIA_TRACE_SCAN;
+    }
+    T.x3 = x4; T.y3 = y4;
+    T.s = (s + 4) & 7;
+    return EMIA_TRACE_FOLLOW;
+}
+
+// marks_zeroed != 0: the caller cleared both planes already (the kernels clear the whole buffer with coalesced stores).
+EMIA_HD_NOINLINE void emia_find_external_contours(const EmiaBitView& v, uint32_t* mk, uint32_t* ng, EmiaContourOut& o, int marks_zeroed = 0) {
+    const int nw = v.h * v.wwords;
+    if (!marks_zeroed) for (int i = 0; i < nw; ++i) { mk[i] = 0u; ng[i] = 0u; }
+    EmiaTraceState T;
+    T.v = v; T.mk = mk; T.ng = ng; T.o = o;
+    emia_trace_begin(T);
+    int phase = EMIA_TRACE_SCAN;
+    while (phase != EMIA_TRACE_DONE) phase = (phase == EMIA_TRACE_SCAN) ? emia_trace_scan_step(T) : emia_trace_follow_step(T);
+    o = T.o;
 }
 
 // cv2.contourArea on integer vertices: |shoelace| / 2 (exact; OpenCV accumulates integer-valued doubles).
@@ -193,25 +261,13 @@ EMIA_HD double emia_contour_area(const uint32_t* pts, int n) {
 // either an axial run (sqrtf(k*k) == k exactly for k < 4096) or a diagonal run (fl32(sqrt(2 k^2)), taken from `diag`
 // when the caller provides the table: diag[k] = sqrtf((float)(2*k*k)), k < EMIA_DIAG_TABLE); anything else goes through
 // sqrtf, so the result is bit-identical to the plain loop for ANY vertex list.
-#define EMIA_DIAG_TABLE 128
 EMIA_HD double emia_arc_length_closed(const uint32_t* pts, int n, const float* diag = nullptr) {
     if (n <= 1) return 0.0;
     double per = 0.0;
     int px = EMIA_PT_X(pts[n - 1]), py = EMIA_PT_Y(pts[n - 1]);
     for (int i = 0; i < n; ++i) {
         const int x = EMIA_PT_X(pts[i]), y = EMIA_PT_Y(pts[i]);
-        int dx = x - px, dy = y - py;
-        dx = dx < 0 ? -dx : dx; dy = dy < 0 ? -dy : dy;
-        float seg;
-        if ((dx == 0 || dy == 0) && (dx | dy) < 4096) seg = (float)(dx | dy);
-        else if (diag && dx == dy && dx < EMIA_DIAG_TABLE) seg = diag[dx];
-        else {
-            const float fx = (float)dx, fy = (float)dy;
-            const float dx2 = fx * fx;
-            const float dy2 = fy * fy;
-            seg = sqrtf(dx2 + dy2);
-        }
-        per += (double)seg;
+        per += (double)emia_seg_len(x - px, y - py, diag);
         px = x; py = y;
     }
     return per;

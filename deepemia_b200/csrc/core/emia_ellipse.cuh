@@ -89,7 +89,7 @@ EMIA_HD void emia_sv_extremes(const double* R, double* smax, double* smin) {
 // DECOMP_SVD) return, including for rank-deficient systems (e.g. stage 2 when |dx| == |dy| for every vertex: the x^2 and y^2
 // columns coincide and OpenCV answers with the equal split, a circle).  smax / smin: extreme singular values.
 template <int K>
-EMIA_HD void emia_svd_solve(const double* R, const double* qtb, double* x, double* smax, double* smin) {
+EMIA_HD_COLD void emia_svd_solve(const double* R, const double* qtb, double* x, double* smax, double* smin) {
     double M[K * K], V[K * K];
     for (int i = 0; i < K * K; ++i) { M[i] = R[i]; V[i] = 0.0; }
     for (int i = 0; i < K; ++i) V[i * K + i] = 1.0;
@@ -422,7 +422,7 @@ EMIA_HD void emia_mat3_eigvec(const double* m, double lambda, double* v) {
     const double nrm = sqrt(best);
     if (nrm > 0.0) { v[0] /= nrm; v[1] /= nrm; v[2] /= nrm; }
 }
-EMIA_HD_NOINLINE EmiaEllipse emia_fit_ellipse_direct(const uint32_t* pts, int n) {
+EMIA_HD_COLD EmiaEllipse emia_fit_ellipse_direct(const uint32_t* pts, int n) {
     EmiaEllipse box; box.cx = box.cy = box.w = box.h = box.angle = 0.f; box.ok = 0;
     double cx = 0.0, cy = 0.0;
     for (int i = 0; i < n; ++i) { cx += (double)EMIA_PT_X(pts[i]); cy += (double)EMIA_PT_Y(pts[i]); }

@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(EMIA_TRACE_THREADS) k_contour_trace(
     } else {
         o.pts = nullptr; o.cap_pts = 0; o.cstart = nullptr; o.cap_contours = 0; o.store = 0;
     }
+    o.track = 0; o.diag = nullptr;
     emia_find_external_contours(v, mk, ng, o, 1);
     if (!kStore) {
         n_contours[i] = o.n_contours;
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(EMIA_PRESORT_WARPS * 32) k_contour_hull(int64_
 }
 
 // ---- morphometry: one THREAD per instance over the stored vertex lists ---------------------------------------------
-__global__ void __launch_bounds__(128) k_contour_measure(int64_t n, const int32_t* __restrict__ item_inst,
+__global__ void __launch_bounds__(128, 4) k_contour_measure(int64_t n, const int32_t* __restrict__ item_inst,
                                                          const int64_t* __restrict__ rec_off, const int64_t* __restrict__ inst_cont_off,
                                                          const int64_t* __restrict__ pt_off,
                                                          const int64_t* __restrict__ scratch_off, double um_pix, double min_area,
@@ -278,34 +279,64 @@ __global__ void k_trace_caps(const emia_inst_meta* __restrict__ meta, int64_t n,
     cap[i] = (m.ch > 0 && m.cw > 0) ? (int64_t)(4 * (m.ch + 32 * m.cw) + 32) : 0;
 }
 
+// Lanes are PERSISTENT inside a CTA-owned chunk of instances: a lane that finishes its instance takes the next one from a
+// shared-memory counter INSIDE the same flat loop (phase "next"), so the warp keeps executing one instruction stream with
+// most lanes busy — border lengths differ 4x between instances and one-instance-per-thread left 8 of 32 lanes active (ncu).
+#define EMIA_TRACE_CHUNK 1024          // instances per CTA (upper bound; smaller inputs use smaller chunks to fill the GPU)
 __global__ void __launch_bounds__(EMIA_TRACE_THREADS) k_contour_trace_slab(
     const uint32_t* __restrict__ crops, const emia_inst_meta* __restrict__ meta, const int64_t* __restrict__ crop_off, int64_t n,
     uint32_t* __restrict__ marks, const int64_t* __restrict__ pt_cap_off, int capc, uint32_t* __restrict__ pts,
     int32_t* __restrict__ cstart_slab, int64_t* __restrict__ n_contours, int64_t* __restrict__ scratch_bytes,
-    int32_t* __restrict__ overflow, double* __restrict__ perim0) {
+    int32_t* __restrict__ overflow, double* __restrict__ perim0, int chunk) {
     __shared__ float s_diag[EMIA_DIAG_TABLE];
+    __shared__ int s_next;
     emia_fill_diag_table(s_diag);
-    const int64_t i = (int64_t)blockIdx.x * EMIA_TRACE_THREADS + threadIdx.x;
-    if (i >= n) return;
-    const emia_inst_meta m = meta[i];
-    const int words = m.ch * m.cw;
-    int32_t* cs = cstart_slab + (size_t)i * (capc + 1);
-    if (perim0) perim0[i] = 0.0;
-    if (words <= 0) { cs[0] = 0; n_contours[i] = 0; scratch_bytes[i] = 0; return; }
-    const int64_t off = crop_off[i];
-    const EmiaBitView v = emia_make_view(crops, m, off);
-    uint32_t* mk = marks + 2 * off;
-    uint32_t* ng = mk + words;
-    EmiaContourOut o;
-    o.pts = pts + pt_cap_off[i]; o.cap_pts = (int)(pt_cap_off[i + 1] - pt_cap_off[i]);
-    o.cstart = cs; o.cap_contours = capc; o.store = 1;
-    emia_find_external_contours(v, mk, ng, o, 1);
-    if (o.overflow) { atomicAdd(overflow, 1); n_contours[i] = 0; scratch_bytes[i] = 0; return; }
-    n_contours[i] = o.n_contours;
-    scratch_bytes[i] = o.n_contours ? (int64_t)((emia_measure_scratch_bytes(o.max_len) + 15) & ~(size_t)15) : 0;
-    if (perim0 && o.n_contours) {
-        const int nc = o.n_contours;
-        perim0[i] = emia_arc_length_closed(o.pts + cs[nc - 1], cs[nc] - cs[nc - 1], s_diag);
+    const int64_t lo = (int64_t)blockIdx.x * chunk;
+    const int64_t hi = (lo + chunk < n) ? lo + chunk : n;
+    if (threadIdx.x == 0) s_next = EMIA_TRACE_THREADS;
+    __syncthreads();
+    EmiaTraceState T;
+    int64_t i = -1;
+    int32_t* cs = nullptr;
+    int phase = EMIA_TRACE_DONE;
+    int first = 1;
+    for (;;) {
+        if (phase == EMIA_TRACE_DONE) {
+            if (i >= 0) {
+                // epilogue of instance i
+                if (T.o.overflow) { atomicAdd(overflow, 1); n_contours[i] = 0; scratch_bytes[i] = 0; }
+                else {
+                    const int nc = T.o.n_contours;
+                    n_contours[i] = nc;
+                    scratch_bytes[i] = nc ? (int64_t)((emia_measure_scratch_bytes(T.o.max_len) + 15) & ~(size_t)15) : 0;
+                    // arcLength of contours[0] in OpenCV order = the LAST discovered contour (deduplicate_masks_smart, Q10),
+                    // accumulated while the border was followed
+                    if (perim0 && nc) perim0[i] = T.o.perim_last;
+                }
+            }
+            // next instance of this CTA's chunk
+            const int k = first ? (int)threadIdx.x : atomicAdd(&s_next, 1);
+            first = 0;
+            i = lo + k;
+            if (i >= hi) break;
+            const emia_inst_meta m = meta[i];
+            cs = cstart_slab + (size_t)i * (capc + 1);
+            if (perim0) perim0[i] = 0.0;
+            if (m.ch * m.cw <= 0) { cs[0] = 0; n_contours[i] = 0; scratch_bytes[i] = 0; i = -1; continue; }
+            const int64_t off = crop_off[i];
+            T.v = emia_make_view(crops, m, off);
+            T.mk = marks + 2 * off;
+            T.ng = T.mk + m.ch * m.cw;
+            T.o.pts = pts + pt_cap_off[i]; T.o.cap_pts = (int)(pt_cap_off[i + 1] - pt_cap_off[i]);
+            T.o.cstart = cs; T.o.cap_contours = capc; T.o.store = 1;
+            T.o.track = perim0 != nullptr; T.o.diag = s_diag;
+            emia_trace_begin(T);
+            phase = EMIA_TRACE_SCAN;
+        } else if (phase == EMIA_TRACE_SCAN) {
+            phase = emia_trace_scan_step(T);
+        } else {
+            phase = emia_trace_follow_step(T);
+        }
     }
 }
 
@@ -325,10 +356,15 @@ extern "C" int emia_contour_trace_slab(const uint32_t* crops, const emia_inst_me
     if (n == 0) return EMIA_OK;
     if (!crops || !meta || !crop_off || !marks || !pt_cap_off || !pts || !cstart_slab || !n_contours || !scratch_bytes || !overflow)
         return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_trace_slab: %s", "null pointer");
-    const unsigned grid = (unsigned)((n + EMIA_TRACE_THREADS - 1) / EMIA_TRACE_THREADS);
+    // chunk: enough CTAs to fill every SM 8 times over, but at least 2 instances per lane and at most EMIA_TRACE_CHUNK per CTA
+    int64_t chunk = (n + (int64_t)emia_num_sms() * 8 - 1) / ((int64_t)emia_num_sms() * 8);
+    chunk = (chunk + EMIA_TRACE_THREADS - 1) / EMIA_TRACE_THREADS * EMIA_TRACE_THREADS;
+    if (chunk < 2 * EMIA_TRACE_THREADS) chunk = 2 * EMIA_TRACE_THREADS;
+    if (chunk > EMIA_TRACE_CHUNK) chunk = EMIA_TRACE_CHUNK;
+    const unsigned grid = (unsigned)((n + chunk - 1) / chunk);
     emia_launch_clear_marks(marks, crop_off, n, (cudaStream_t)stream);
     k_contour_trace_slab<<<grid, EMIA_TRACE_THREADS, 0, (cudaStream_t)stream>>>(crops, meta, crop_off, n, marks, pt_cap_off, cap_contours, pts,
-                                                                             cstart_slab, n_contours, scratch_bytes, overflow, perim0);
+                                                                             cstart_slab, n_contours, scratch_bytes, overflow, perim0, (int)chunk);
     return emia_check_launch("emia_contour_trace_slab launch: %s");
 }
 

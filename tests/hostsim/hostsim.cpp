@@ -19,6 +19,7 @@ static void pack_bits(const uint8_t* mask, int H, int W, std::vector<uint32_t>& 
             if (mask[(size_t)y * W + x]) bits[(size_t)y * ww + (x >> 5)] |= 1u << (x & 31);
 }
 
+static double g_last_perim = 0.0;
 extern "C" {
 
 // returns number of contours (discovery order) or -1 on overflow
@@ -28,11 +29,15 @@ int sim_find_contours(const uint8_t* mask, int H, int W, uint32_t* pts, int cap_
     pack_bits(mask, H, W, bits, ww);
     std::vector<uint32_t> mk((size_t)H * ww), ng((size_t)H * ww);
     EmiaBitView v{bits.data(), ww, H, ww, 0, 0};
-    EmiaContourOut o{pts, cap_pts, cstart, cap_c, 0, 0, 0, 0, 1};
+    EmiaContourOut o{};
+    o.pts = pts; o.cap_pts = cap_pts; o.cstart = cstart; o.cap_contours = cap_c; o.store = 1; o.track = 1; o.diag = nullptr;
     emia_find_external_contours(v, mk.data(), ng.data(), o);
     *n_pts = o.n_pts;
+    g_last_perim = o.perim_last;
     return o.overflow ? -1 : o.n_contours;
 }
+// running arcLength of the last discovered contour of the previous sim_find_contours call
+double sim_last_perimeter() { return g_last_perim; }
 double sim_contour_area(const uint32_t* pts, int n) { return emia_contour_area(pts, n); }
 double sim_arc_length(const uint32_t* pts, int n) { return emia_arc_length_closed(pts, n); }
 

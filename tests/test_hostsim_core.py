@@ -24,6 +24,7 @@ def L():
     lib = ctypes.CDLL(HS)
     lib.sim_contour_area.restype = ctypes.c_double
     lib.sim_arc_length.restype = ctypes.c_double
+    lib.sim_last_perimeter.restype = ctypes.c_double
     return lib
 
 
@@ -69,6 +70,8 @@ def test_contours_area_perimeter_vs_opencv(L):
         ref = cv2.findContours(np.ascontiguousarray(m), cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)[0]
         got = _contours(L, m)
         assert len(ref) == len(got)
+        if len(ref):     # running arcLength accumulated while following = cv2.arcLength of contours[0] (the last discovered)
+            assert L.sim_last_perimeter() == cv2.arcLength(ref[0], True)
         for r, p in zip(ref, got):
             assert np.array_equal(_pack(r), p)
             assert L.sim_contour_area(_p(p), len(p)) == cv2.contourArea(r)
