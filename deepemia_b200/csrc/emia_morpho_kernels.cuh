@@ -101,6 +101,99 @@ struct EmiaHullSmem {
     int hull[EMIA_PRESORT_MAX];
     int tmp[EMIA_PRESORT_MAX];
 };
+__device__ __forceinline__ uint64_t emia_make_key(uint64_t, int x, int y, int ox, int oy, int t) { (void)ox; (void)oy; return EMIA_KEY(x, y, t); }
+__device__ __forceinline__ uint32_t emia_make_key(uint32_t, int x, int y, int ox, int oy, int t) { return EMIA_KEY32(x - ox, y - oy, t); }
+
+// The warp's work on one contour, templated on the key type (uint32_t: extent < 4096 x 4096, coordinates relative to (ox, oy)).
+template <typename K>
+__device__ __forceinline__ void emia_hull_warp(K* k, EmiaHullSmem& S, const uint32_t* __restrict__ p, int len, int lane, int ox, int oy,
+                                               const long long* qx, const long long* qy, int* g_stack, int* g_hull) {
+    // Akl-Toussaint pre-filter: vertices strictly inside the quadrilateral of the four extreme vertices (left, top, right,
+    // bottom) cannot be hull vertices; dropping them (typically 50-70 % of a blob's contour) shrinks the sort and the chains.
+    // Extremes and all vertices ON the quadrilateral survive, so the sorted order of the survivors, the first min-/max-y
+    // entries and the chains' results are those of the full set; keys keep the ORIGINAL vertex index.
+    int run = 0;
+    for (int t0 = 0; t0 < len; t0 += 32) {
+        const int t = t0 + lane;
+        bool keep = false;
+        K key = (K)~(K)0;
+        if (t < len) {
+            const uint32_t q = p[t];
+            const long long x = EMIA_PT_X(q), y = EMIA_PT_Y(q);
+            int pos = 0, neg = 0, edges = 0;
+            for (int e = 0; e < 4; ++e) {
+                const int f = (e + 1) & 3;
+                const long long ex = qx[f] - qx[e], ey = qy[f] - qy[e];
+                if (ex == 0 && ey == 0) continue;                       // coinciding extremes: the quadrilateral is a triangle
+                const long long cr = ex * (y - qy[e]) - ey * (x - qx[e]);
+                ++edges; pos += cr > 0; neg += cr < 0;
+            }
+            const bool inside = edges >= 3 && (pos == edges || neg == edges);
+            keep = !inside;
+            key = emia_make_key((K)0, (int)x, (int)y, ox, oy, t);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) k[run + __popc(bal & ((1u << lane) - 1u))] = key;
+        run += __popc(bal);
+    }
+    const int m = run;
+    int N = 32;
+    while (N < m) N <<= 1;
+    for (int t = m + lane; t < N; t += 32) k[t] = (K)~(K)0;
+    __syncwarp();
+    for (int size = 2; size <= N; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = lane; t < (N >> 1); t += 32) {
+                const int lo = ((t / stride) * (stride << 1)) + (t % stride);
+                const int hi = lo + stride;
+                const bool up = ((lo & size) == 0);
+                const K a = k[lo], b = k[hi];
+                if ((a > b) == up) { k[lo] = b; k[hi] = a; }
+            }
+            __syncwarp();
+        }
+    }
+    // first index of the minimum / maximum y in sorted order (the serial scan keeps the first occurrence)
+    int mn = 0x7fffffff, mx = 0x7fffffff;
+    for (int t = lane; t < m; t += 32) {
+        const int y = emia_ky(k[t]);
+        mn = min(mn, (y << 9) | t);                   // y < 2^20, t < 2^9
+        mx = min(mx, ((0xFFFFF - y) << 9) | t);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = min(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    const int miny_ind = mn & 511, maxy_ind = mx & 511;
+    int nout = 0;
+    const bool degenerate = (emia_kx(k[0]) == emia_kx(k[m - 1]) && emia_ky(k[0]) == emia_ky(k[m - 1]));
+    if (degenerate) {
+        if (lane == 0) S.hull[0] = 0;
+        nout = 1;
+    } else {
+        int cnt = 0;
+        if (lane < 4) {
+            const int start = (lane & 1) ? m - 1 : 0;
+            const int end = (lane < 2) ? maxy_ind : miny_ind;
+            const int nsign = (lane < 2) ? -1 : 1;
+            const int sign2 = (lane == 0 || lane == 3) ? 1 : -1;
+            cnt = emia_sklansky(k, start, end, S.stacks[lane], nsign, sign2);
+        }
+        __syncwarp();
+        const int tl = __shfl_sync(0xffffffffu, cnt, 0), tr = __shfl_sync(0xffffffffu, cnt, 1);
+        const int bl = __shfl_sync(0xffffffffu, cnt, 2), br = __shfl_sync(0xffffffffu, cnt, 3);
+        if (lane == 0) {
+            const int stop_idx = emia_hull_emit_upper(k, 0, S.stacks[0], tl, S.stacks[1], tr, S.hull, &nout);
+            emia_hull_emit_lower(k, 0, S.stacks[2], bl, S.stacks[3], br, stop_idx, S.hull, &nout);
+            emia_hull_cyclic_shift(S.hull, nout, S.tmp);
+        }
+        nout = __shfl_sync(0xffffffffu, nout, 0);
+    }
+    __syncwarp();
+    for (int t = lane; t < nout; t += 32) g_hull[t] = S.hull[t];
+    if (lane == 0) g_stack[0] = nout;
+}
+
 __global__ void __launch_bounds__(EMIA_PRESORT_WARPS * 32) k_contour_hull(int64_t n, const int32_t* __restrict__ item_inst,
                                                                          const int64_t* __restrict__ rec_off,
                                                                          const int64_t* __restrict__ inst_cont_off,
@@ -123,67 +216,24 @@ __global__ void __launch_bounds__(EMIA_PRESORT_WARPS * 32) k_contour_hull(int64_
     uint8_t* sc = scratch + scratch_off[it];
     int* g_stack = (int*)(sc + (size_t)16 * len);
     int* g_hull = g_stack + (len + 2);
-    int N = 32;
-    while (N < len) N <<= 1;
-    uint64_t* k = S.keys;
     const uint32_t* p = pts + pt_off[i] + cs[0];
-    for (int t = lane; t < N; t += 32) {
-        uint64_t key = ~0ull;
-        if (t < len) { const uint32_t q = p[t]; key = EMIA_KEY(EMIA_PT_X(q), EMIA_PT_Y(q), t); }
-        k[t] = key;
-    }
-    __syncwarp();
-    for (int size = 2; size <= N; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int t = lane; t < (N >> 1); t += 32) {
-                const int lo = ((t / stride) * (stride << 1)) + (t % stride);
-                const int hi = lo + stride;
-                const bool up = ((lo & size) == 0);
-                const uint64_t a = k[lo], b = k[hi];
-                if ((a > b) == up) { k[lo] = b; k[hi] = a; }
-            }
-            __syncwarp();
-        }
-    }
-    // first index of the minimum / maximum y in sorted order (the serial scan keeps the first occurrence)
-    int mn = 0x7fffffff, mx = 0x7fffffff;
+    // the four extreme vertices: (x << 16 | y) for left / right, (y << 16 | x) for top / bottom
+    uint32_t lx = 0xFFFFFFFFu, rx = 0u, ty = 0xFFFFFFFFu, by = 0u;
     for (int t = lane; t < len; t += 32) {
-        const int y = EMIA_KEY_Y(k[t]);
-        mn = min(mn, (y << 9) | t);                   // y < 2^20, t < 2^9
-        mx = min(mx, ((0xFFFFF - y) << 9) | t);
+        const uint32_t q = p[t];
+        const uint32_t xy = ((uint32_t)EMIA_PT_X(q) << 16) | (uint32_t)EMIA_PT_Y(q), yx = ((uint32_t)EMIA_PT_Y(q) << 16) | (uint32_t)EMIA_PT_X(q);
+        lx = min(lx, xy); rx = max(rx, xy); ty = min(ty, yx); by = max(by, yx);
     }
     for (int o = 16; o > 0; o >>= 1) {
-        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        mx = min(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        lx = min(lx, __shfl_xor_sync(0xffffffffu, lx, o)); rx = max(rx, __shfl_xor_sync(0xffffffffu, rx, o));
+        ty = min(ty, __shfl_xor_sync(0xffffffffu, ty, o)); by = max(by, __shfl_xor_sync(0xffffffffu, by, o));
     }
-    const int miny_ind = mn & 511, maxy_ind = mx & 511;
-    int nout = 0;
-    const bool degenerate = (EMIA_KEY_X(k[0]) == EMIA_KEY_X(k[len - 1]) && EMIA_KEY_Y(k[0]) == EMIA_KEY_Y(k[len - 1]));
-    if (degenerate) {
-        if (lane == 0) S.hull[0] = 0;
-        nout = 1;
-    } else {
-        int cnt = 0;
-        if (lane < 4) {
-            const int start = (lane & 1) ? len - 1 : 0;
-            const int end = (lane < 2) ? maxy_ind : miny_ind;
-            const int nsign = (lane < 2) ? -1 : 1;
-            const int sign2 = (lane == 0 || lane == 3) ? 1 : -1;
-            cnt = emia_sklansky(k, start, end, S.stacks[lane], nsign, sign2);
-        }
-        __syncwarp();
-        const int tl = __shfl_sync(0xffffffffu, cnt, 0), tr = __shfl_sync(0xffffffffu, cnt, 1);
-        const int bl = __shfl_sync(0xffffffffu, cnt, 2), br = __shfl_sync(0xffffffffu, cnt, 3);
-        if (lane == 0) {
-            const int stop_idx = emia_hull_emit_upper(k, 0, S.stacks[0], tl, S.stacks[1], tr, S.hull, &nout);
-            emia_hull_emit_lower(k, 0, S.stacks[2], bl, S.stacks[3], br, stop_idx, S.hull, &nout);
-            emia_hull_cyclic_shift(S.hull, nout, S.tmp);
-        }
-        nout = __shfl_sync(0xffffffffu, nout, 0);
-    }
-    __syncwarp();
-    for (int t = lane; t < nout; t += 32) g_hull[t] = S.hull[t];
-    if (lane == 0) g_stack[0] = nout;
+    const long long qx[4] = {(long long)(lx >> 16), (long long)(ty & 0xFFFF), (long long)(rx >> 16), (long long)(by & 0xFFFF)};
+    const long long qy[4] = {(long long)(lx & 0xFFFF), (long long)(ty >> 16), (long long)(rx & 0xFFFF), (long long)(by >> 16)};
+    const int ox = (int)(lx >> 16), oy = (int)(ty >> 16);
+    const bool compact = ((int)(rx >> 16) - ox) < 4096 && ((int)(by >> 16) - oy) < 4096;        // len <= 256 holds here
+    if (compact) emia_hull_warp<uint32_t>((uint32_t*)S.keys, S, p, len, lane, ox, oy, qx, qy, g_stack, g_hull);
+    else emia_hull_warp<uint64_t>(S.keys, S, p, len, lane, ox, oy, qx, qy, g_stack, g_hull);
 }
 
 // ---- morphometry: one THREAD per instance over the stored vertex lists ---------------------------------------------
