@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(EMIA_FUSED_THREADS) k_group_fused(
     for (int size = 2; size <= P; size <<= 1) {
         for (int st = size >> 1; st > 0; st >>= 1) {
             for (int t = tid; t < (P >> 1); t += EMIA_FUSED_THREADS) {
-                const int lo = ((t / st) * (st << 1)) + (t % st);
+                const int lo = ((t & ~(st - 1)) << 1) | (t & (st - 1));      // st is a power of two
                 const int hi = lo + st;
                 const bool up = ((lo & size) == 0);
                 const uint64_t ka = rk[lo], kb = rk[hi];
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(EMIA_FUSED_THREADS) k_containment_fused(
     for (int size = 2; size <= P; size <<= 1) {
         for (int st = size >> 1; st > 0; st >>= 1) {
             for (int t = tid; t < (P >> 1); t += EMIA_FUSED_THREADS) {
-                const int lo = ((t / st) * (st << 1)) + (t % st);
+                const int lo = ((t & ~(st - 1)) << 1) | (t & (st - 1));      // st is a power of two
                 const int hi = lo + st;
                 const bool up = ((lo & size) == 0);
                 const uint32_t xa = S.xs[lo], xb = S.xs[hi];

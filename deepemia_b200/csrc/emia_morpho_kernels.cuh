@@ -144,7 +144,7 @@ __device__ __forceinline__ void emia_hull_warp(K* k, EmiaHullSmem& S, const uint
     for (int size = 2; size <= N; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             for (int t = lane; t < (N >> 1); t += 32) {
-                const int lo = ((t / stride) * (stride << 1)) + (t % stride);
+                const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));      // stride is a power of two
                 const int hi = lo + stride;
                 const bool up = ((lo & size) == 0);
                 const K a = k[lo], b = k[hi];
