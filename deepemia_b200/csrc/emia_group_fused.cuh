@@ -71,9 +71,21 @@ __device__ __forceinline__ int emia_crop_inter_oct(const uint32_t* __restrict__ 
             const int wc = c1 - c0, nw = (r1 - r0) * wc;
             const uint32_t* pa = crops + oa;
             const uint32_t* pb = crops + ob;
-            for (int t = sl; t < nw; t += 8) {
-                const int r = r0 + t / wc, c = c0 + t % wc;
-                cnt += __popc(pa[(r - ga.x) * ga.w + (c - ga.y)] & pb[(r - gb.x) * gb.w + (c - gb.y)]);
+            // four independent word pairs per trip: the loads of a trip are issued back to back (the crops sit in L2 / HBM and
+            // a CTA has few warps, so memory-level parallelism inside the pair is what hides the latency)
+            const int oa = -ga.x * ga.w - ga.y, ob = -gb.x * gb.w - gb.y;
+            for (int t = sl; t < nw; t += 32) {
+                uint32_t wa[4], wb[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int tt = t + 8 * u;
+                    const int r = r0 + tt / wc, c = c0 + tt % wc;
+                    const bool in = tt < nw;
+                    wa[u] = in ? pa[r * ga.w + c + oa] : 0u;
+                    wb[u] = in ? pb[r * gb.w + c + ob] : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) cnt += __popc(wa[u] & wb[u]);
             }
         }
     }

@@ -406,10 +406,10 @@ extern "C" int emia_contour_trace_slab(const uint32_t* crops, const emia_inst_me
     if (n == 0) return EMIA_OK;
     if (!crops || !meta || !crop_off || !marks || !pt_cap_off || !pts || !cstart_slab || !n_contours || !scratch_bytes || !overflow)
         return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_trace_slab: %s", "null pointer");
-    // chunk: enough CTAs to fill every SM 8 times over, but at least 2 instances per lane and at most EMIA_TRACE_CHUNK per CTA
+    // chunk: enough CTAs to fill every SM 8 times over, at least one instance per lane and at most EMIA_TRACE_CHUNK per CTA
     int64_t chunk = (n + (int64_t)emia_num_sms() * 8 - 1) / ((int64_t)emia_num_sms() * 8);
     chunk = (chunk + EMIA_TRACE_THREADS - 1) / EMIA_TRACE_THREADS * EMIA_TRACE_THREADS;
-    if (chunk < 2 * EMIA_TRACE_THREADS) chunk = 2 * EMIA_TRACE_THREADS;
+    if (chunk < EMIA_TRACE_THREADS) chunk = EMIA_TRACE_THREADS;
     if (chunk > EMIA_TRACE_CHUNK) chunk = EMIA_TRACE_CHUNK;
     const unsigned grid = (unsigned)((n + chunk - 1) / chunk);
     emia_launch_clear_marks(marks, crop_off, n, (cudaStream_t)stream);
