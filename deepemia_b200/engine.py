@@ -761,6 +761,19 @@ def gray_hist(iset, image):
     return out[:iset.n]
 
 
+def image_gray_hist(image, device=None):
+    """int64 [256] grey-level histogram of an H x W x 3 (BGR) or H x W uint8 image (host array or device tensor)."""
+    lib = _lib.load()
+    dev = _need_cuda(device)
+    img = torch.as_tensor(np.ascontiguousarray(image) if isinstance(image, np.ndarray) else image, device=dev).contiguous()
+    assert img.dtype == torch.uint8 and img.dim() in (2, 3)
+    ch = 1 if img.dim() == 2 else int(img.shape[2])
+    out = torch.empty(256, dtype=torch.int64, device=dev)
+    _lib.check(lib.emia_image_gray_hist(_ptr(img), int(img.shape[0]), int(img.shape[1]), ch, _ptr(out), _stream()), "emia_image_gray_hist")
+    LAUNCHES["count"] += 1
+    return out
+
+
 def moments01(iset):
     """(m00, m10, m01) int64 [n,3]: cv2.moments of the 0/1 mask (src/functions/inference.py:1101-1104)."""
     lib = _lib.load()

@@ -105,6 +105,40 @@ def generate_tiles_with_overlap(image, tile_size, overlap_ratio):
     return tiles
 
 
+def calculate_image_quality_score(image):
+    """inference.py:256-283: 0.4 * mean(gray) / 255 + 0.6 * std(gray) / 128, clipped to [0, 1].  The grey histogram comes from
+    the GPU; mean and (population) standard deviation follow exactly from its integer counts."""
+    from fractions import Fraction
+    counts = [int(v) for v in engine.image_gray_hist(image).cpu().numpy()]
+    n = sum(counts)
+    s1 = sum(k * c for k, c in enumerate(counts))
+    s2 = sum(k * k * c for k, c in enumerate(counts))
+    brightness = (s1 / n) / 255.0
+    var = Fraction(s2, n) - Fraction(s1, n) ** 2
+    contrast = float(np.sqrt(np.float64(float(var)))) / 128.0
+    return np.clip((0.4 * brightness) + (0.6 * contrast), 0.0, 1.0)
+
+
+def adaptive_confidence_threshold(base_threshold, image, target_class, small_classes, confidence_mode='auto'):
+    """inference.py:286-336 (the reference reads confidence_mode from its config; here it is an argument)."""
+    if confidence_mode == "manual":
+        return base_threshold
+    quality_score = calculate_image_quality_score(image)
+    if quality_score < 0.3:
+        return base_threshold * 0.7
+    if quality_score < 0.5:
+        return base_threshold * 0.85
+    return base_threshold
+
+
+def get_confidence_threshold(image, target_class, small_classes, class_specific_settings=None, confidence_mode='auto'):
+    """inference.py:339-362."""
+    class_config = (class_specific_settings or {}).get(f"class_{target_class}", {})
+    is_small = target_class in small_classes
+    base_threshold = class_config.get("confidence_threshold", 0.3 if is_small else 0.5)
+    return adaptive_confidence_threshold(base_threshold, image, target_class, small_classes, confidence_mode)
+
+
 def process_masks_parallel(masks):
     """inference.py:170-213: fill holes -> erosion(disk 1) -> dilation(disk 1) for every mask (uint8 out)."""
     if len(masks) == 0:
@@ -507,10 +541,12 @@ def infer_image(predictors, image, num_classes, small_classes, class_specific_se
     for target_class in target_classes:
         is_small_class = target_class in small_classes
         class_cfg = class_specific_settings.get(f"class_{target_class}", {})
-        if confidence_mode == 'manual' or confidence_fn is None:
+        if confidence_mode == 'manual':
             confidence_thresh = class_cfg.get("confidence_threshold", 0.3 if is_small_class else 0.5)
-        else:
+        elif confidence_fn is not None:
             confidence_thresh = confidence_fn(image, target_class, small_classes)
+        else:
+            confidence_thresh = get_confidence_threshold(image, target_class, small_classes, class_specific_settings, confidence_mode)
         iou_thresh = class_cfg.get("iou_threshold", 0.5 if is_small_class else 0.7)
         use_ensemble = ensemble_enabled and (not ensemble_small_only or is_small_class)
         active = predictors if (use_ensemble and len(predictors) > 1) else [predictors[0]]

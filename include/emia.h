@@ -265,6 +265,10 @@ int emia_moments01(const uint32_t* crops, const emia_inst_meta* meta, const int6
 int emia_gray_hist(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n,
                    const uint8_t* image, int H, int W, int channels, int32_t* hist, void* stream);
 
+/* 256-bin grey-level histogram of a whole H x W x channels image (same grey conversion as emia_gray_hist): the brightness / contrast
+ * statistics of calculate_image_quality_score (src/functions/inference.py:256-283) follow exactly from the counts. */
+int emia_image_gray_hist(const uint8_t* image, int H, int W, int channels, uint64_t* hist, void* stream);
+
 /* pairwise helpers (drop-in for iou / calculate_iou / calculate_containment on explicit pairs):
  * out[k] = {intersection, area_a, area_b} for pairs (pa[k], pb[k]). */
 int emia_pair_counts(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off,

@@ -105,6 +105,14 @@ def test_calculate_measurements_and_csv(cuda_device, tmp_path):
     ref = omeasure.calculate_measurements(c, um_pix=0.5, gray=gray, mask=binary)
     for k in ("contrast_d10", "contrast_d50", "contrast_d90"):
         np.testing.assert_allclose(got[k], ref[k], rtol=1e-9, err_msg=k)
+    # the masked grey histograms themselves: exact integer counts (cv2's 15-bit fixed-point BGR2GRAY)
+    import torch
+    from deepemia_b200 import engine
+    iset = engine.from_masks(torch.as_tensor(np.stack(ms[:8]).astype(np.uint8), device=cuda_device))
+    hist = engine.gray_hist(iset, image).cpu().numpy()
+    for i in range(8):
+        assert np.array_equal(hist[i], np.bincount(gray[ms[i]], minlength=256)), f"histogram of instance {i}"
+    assert np.array_equal(engine.image_gray_hist(image).cpu().numpy(), np.bincount(gray.reshape(-1), minlength=256))
     # measurement loop rows
     classes = [int(v) for v in rng.integers(0, 2, len(ms))]
     rows = inf.measure_masks(ms, classes, image.shape, 0.5, "imgA.tif", "500", class_names=["pore", "throat"])
@@ -131,3 +139,18 @@ def test_run_inference_writes_reference_csv_schema(cuda_device, tmp_path):
     # every RLE row decodes to a mask whose measurement rows exist
     ids = {r[0].rsplit("_", 1)[0] for r in rows[1:]}
     assert ids <= {"a.png", "b.png"}
+
+
+def test_adaptive_confidence_threshold(cuda_device):
+    """calculate_image_quality_score / adaptive_confidence_threshold / get_confidence_threshold (inference.py:256-362)."""
+    rng = np.random.default_rng(5)
+    for lo, hi in ((0, 40), (60, 200), (0, 256), (200, 256)):
+        img = rng.integers(lo, hi, (301, 417, 3), dtype=np.uint8)
+        gray = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)
+        ref = np.clip(0.4 * (np.mean(gray) / 255.0) + 0.6 * (np.std(gray) / 128.0), 0.0, 1.0)
+        got = inf.calculate_image_quality_score(img)
+        np.testing.assert_allclose(got, ref, rtol=1e-12)
+        assert inf.calculate_image_quality_score(gray) == inf.calculate_image_quality_score(np.ascontiguousarray(gray))
+        want = 0.5 * (0.7 if ref < 0.3 else 0.85 if ref < 0.5 else 1.0)
+        assert inf.get_confidence_threshold(img, 0, {1}) == want
+        assert inf.get_confidence_threshold(img, 1, {1}, {"class_1": {"confidence_threshold": 0.2}}, "manual") == 0.2
