@@ -141,6 +141,8 @@ def paste(probs, boxes, H, W, scores=None, classes=None, scale_x=1.0, scale_y=1.
     n = int(probs.shape[0])
     assert probs.dtype in (torch.float32, torch.float16) and boxes.dtype == torch.float32 and probs.is_contiguous() and boxes.is_contiguous()
     st = _stream()
+    if probs.dtype == torch.float16 and (variant != 2 or ((W + 31) // 32 + 1) * 32 > 2112):
+        probs = probs.to(torch.float32)          # only the variant-2 kernel (frames up to 2048 px wide) reads halves directly
     f16 = (1 << 16) if probs.dtype == torch.float16 else 0      # EMIA_PASTE_PROBS_F16: AMP heads, widened exactly in the kernel
     if plan is None:
         meta, crop_off = paste_plan(boxes, H, W, scale_x, scale_y)

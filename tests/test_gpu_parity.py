@@ -80,6 +80,13 @@ def test_paste_fp16_heads_equal_fp32(cuda_device):
     b = engine.paste(tp.to(torch.float16).contiguous(), tb, H, W, frames=True)
     assert torch.equal(a.crops[:a.total_crop_words], b.crops[:b.total_crop_words]) and torch.equal(a.frames, b.frames)
     assert torch.equal(a.area, b.area) and torch.equal(a.bbox, b.bbox)
+    # frames wider than the variant-2 kernel handles: the halves are widened on the way in
+    Hw, Ww = 40, 2500
+    pw, bw, _, _ = _heads(78, 12, Hw, Ww, rmin=4, rmax=12, margin=14)
+    tpw, tbw = _dev(cuda_device, pw, bw)
+    c = engine.paste(tpw, tbw, Hw, Ww)
+    d = engine.paste(tpw.to(torch.float16).contiguous(), tbw, Hw, Ww)
+    assert torch.equal(c.crops[:c.total_crop_words], d.crops[:d.total_crop_words]) and torch.equal(c.area, d.area)
 
 
 def test_exclusive_scan(cuda_device):
