@@ -515,8 +515,8 @@ __global__ void __launch_bounds__(EMIA_PASTE_THREADS, EMIA_P2_MIN_CTAS) k_paste_
     const void* __restrict__ probs_raw, const float4* __restrict__ boxes, const emia_inst_meta* __restrict__ meta,
     const int64_t* __restrict__ crop_off, int64_t n, float sx, float sy, int H, int W, uint32_t* __restrict__ frames,
     int64_t frame_slots, int pitch_words, uint32_t* __restrict__ crops, int32_t* __restrict__ bbox, int32_t* __restrict__ area) {
-    __shared__ __align__(16) float s_pp[EMIA_P2_PAD_ROWS * EMIA_P2_PAD_STRIDE];   // padded probabilities
-    __shared__ __align__(16) __half s_half[kHalf ? EMIA_MASK_SIDE * EMIA_MASK_SIDE : 8];   // fp16 head outputs: staged, then widened
+    __shared__ __align__(16) float s_pp2[2][EMIA_P2_PAD_ROWS * EMIA_P2_PAD_STRIDE];   // padded probabilities, double-buffered
+    __shared__ __align__(16) __half s_half2[2][kHalf ? EMIA_MASK_SIDE * EMIA_MASK_SIDE : 8];   // fp16 head outputs: staged, then widened
     const float* probs = (const float*)probs_raw;
     const __half* probs_h = (const __half*)probs_raw;
     __shared__ __align__(32) uint32_t s_tile[EMIA_PASTE_TILE_WORDS];              // one band of frame rows (chunk span)
@@ -529,26 +529,41 @@ __global__ void __launch_bounds__(EMIA_PASTE_THREADS, EMIA_P2_MIN_CTAS) k_paste_
     const int warp = tid >> 5;
     const int nwarps = EMIA_PASTE_THREADS / 32;
     const int cpr = pitch_words >> 3;               // 32-byte chunks per frame row
-    for (int k = tid; k < EMIA_P2_PAD_ROWS * EMIA_P2_PAD_STRIDE; k += EMIA_PASTE_THREADS) s_pp[k] = 0.f;
+    for (int k = tid; k < 2 * EMIA_P2_PAD_ROWS * EMIA_P2_PAD_STRIDE; k += EMIA_PASTE_THREADS) (&s_pp2[0][0])[k] = 0.f;
     __syncthreads();
+    // copy of the probabilities of instance `q` into buffer b (28 rows x 7 chunks of 16 bytes -> padded tile rows 2..29, columns
+    // 4..31; fp16: 98 chunks staged and widened after the wait).  Always commits a group, so the group count is uniform.
+    auto issue = [&](int64_t q, bool q_live, int b) {
+        if (q_live) {
+            if (kHalf) {
+                if (tid < (EMIA_MASK_SIDE * EMIA_MASK_SIDE) / 8)
+                    emia_cp_async16(&s_half2[b][tid * 8], probs_h + q * (EMIA_MASK_SIDE * EMIA_MASK_SIDE) + tid * 8);
+            } else if (tid < EMIA_MASK_SIDE * 7) {
+                const int r = tid / 7, c7 = tid - r * 7;
+                emia_cp_async16(&s_pp2[b][(r + 2) * EMIA_P2_PAD_STRIDE + 4 + c7 * 4],
+                                probs + q * (EMIA_MASK_SIDE * EMIA_MASK_SIDE) + r * EMIA_MASK_SIDE + c7 * 4);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // software pipeline over the CTA's instances: the meta / box / probabilities of instance k + 1 are fetched while instance k
+    // is processed (ncu: 16 % of the stall samples sat on these dependent DRAM reads at the top of every instance)
+    emia_inst_meta m_next;
+    float4 bx_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    m_next.valid = 0; m_next.ch = m_next.cw = 0;
+    if ((int64_t)blockIdx.x < n) { m_next = meta[blockIdx.x]; bx_next = boxes[blockIdx.x]; }
+    issue(blockIdx.x, (int64_t)blockIdx.x < n && m_next.valid && m_next.ch > 0 && m_next.cw > 0, 0);
+    int buf = 0;
 
     for (int64_t inst = blockIdx.x; inst < n; inst += gridDim.x) {
-        const emia_inst_meta m = meta[inst];
-        const float4 bx = boxes[inst];
+        const emia_inst_meta m = m_next;
+        const float4 bx = bx_next;
+        float* s_pp = s_pp2[buf];
+        const __half* s_half = s_half2[buf];
         const EmiaPasteBox pb = emia_paste_prepare(bx.x, bx.y, bx.z, bx.w, sx, sy, W, H);
         const bool live = m.valid && m.ch > 0 && m.cw > 0;
         if (tid < 5) s_red[tid] = (tid == 0) ? 0 : ((tid == 1 || tid == 2) ? 0x7fffffff : -1);
-        // ---- 1. start the copy of the probabilities (28 rows x 7 chunks of 16 bytes -> padded tile rows 2..29, columns 4..31)
-        if (kHalf) {
-            // 784 halves = 98 chunks of 16 bytes; exact widening to float happens after the wait (AMP heads emit fp16)
-            if (live && tid < (EMIA_MASK_SIDE * EMIA_MASK_SIDE) / 8)
-                emia_cp_async16(&s_half[tid * 8], probs_h + inst * (EMIA_MASK_SIDE * EMIA_MASK_SIDE) + tid * 8);
-        } else if (live && tid < EMIA_MASK_SIDE * 7) {
-            const int r = tid / 7, q = tid - r * 7;
-            emia_cp_async16(&s_pp[(r + 2) * EMIA_P2_PAD_STRIDE + 4 + q * 4], probs + inst * (EMIA_MASK_SIDE * EMIA_MASK_SIDE) + r * EMIA_MASK_SIDE + q * 4);
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        // ---- 2. zero-fill the frame outside the crop's rows / chunk span while the copy is in flight
+        // ---- 1. zero-fill the frame outside the crop's rows / chunk span
         const int cc0 = live ? (m.wc0 >> 3) : 0;
         const int cc1 = live ? ((m.wc0 + m.cw - 1) >> 3) : -1;   // inclusive
         unsigned char* frame = nullptr;
@@ -567,6 +582,13 @@ __global__ void __launch_bounds__(EMIA_PASTE_THREADS, EMIA_P2_MIN_CTAS) k_paste_
                 }
             }
         }
+        // ---- 2. fetch the next instance (its copy lands while this one is sampled)
+        {
+            const int64_t nx = inst + gridDim.x;
+            bool nlive = false;
+            if (nx < n) { m_next = meta[nx]; bx_next = boxes[nx]; nlive = m_next.valid && m_next.ch > 0 && m_next.cw > 0; }
+            issue(nx, nlive, buf ^ 1);
+        }
         if (live) {
             // ---- 3. column taps (independent of the probabilities)
             const int ncols = m.cw * 32;
@@ -578,7 +600,7 @@ __global__ void __launch_bounds__(EMIA_PASTE_THREADS, EMIA_P2_MIN_CTAS) k_paste_
                 s_ctap[k] = make_int2(i0 + 4, __float_as_int(a.w1));
             }
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");       // everything but the prefetch just issued has landed
         __syncthreads();
         if (kHalf) {
             if (live)
@@ -674,7 +696,9 @@ __global__ void __launch_bounds__(EMIA_PASTE_THREADS, EMIA_P2_MIN_CTAS) k_paste_
             ((int4*)bbox)[inst] = a > 0 ? make_int4(s_red[1], s_red[2], s_red[3], s_red[4]) : make_int4(-1, -1, -1, -1);
         }
         __syncthreads();
+        buf ^= 1;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 extern "C" int emia_paste_threshold_bitpack(const float* probs, const float* boxes, const emia_inst_meta* meta,
