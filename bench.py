@@ -249,6 +249,9 @@ def main():
     per_step_ms = [step_ev[i].elapsed_time(step_ev[i + 1]) for i in range(args.steps)]
     launches = engine.LAUNCHES["count"] - l0
     ms_total = ev[0].elapsed_time(ev[1])
+    assert not pipe.aborted(), "a capacity guard tripped in the timed region: the results of the last step are invalid"
+    for r in res:
+        r["meas"].finalize()
     if args.device_pass_only:
         if sampler is not None:
             sampler.terminate()
@@ -309,15 +312,19 @@ def main():
     ev[1].record()
     barrier()
     ms_e2e16 = ev[0].elapsed_time(ev[1])
+    assert not pipe_e2e.aborted()
     same16 = all(torch.equal(a["host"]["records"], b["host"]["records"]) and torch.equal(a["host"]["kept_idx"], b["host"]["kept_idx"])
                  for a, b in zip(res_h, res_h16))
     if sampler is not None:
         sampler.terminate()
     t = torch.tensor([ms_total, ms_e2e, float(np.mean(k1_ms)), ms_e2e16], dtype=torch.float64, device=dev)
     cnt = torch.tensor([float(n_local)], dtype=torch.float64, device=dev)
+    per_rank = [t.clone() for _ in range(world)]
     if world > 1:
+        dist.all_gather(per_rank, t)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    per_rank_ms = [round(float(x[0].item()) / args.steps, 3) for x in per_rank]
     ms_total, ms_e2e, k1, ms_e2e16 = t.tolist()
     n_global = cnt.item()
     if rank == 0:
@@ -349,8 +356,9 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"config5: {args.tiles} tiles x ~Poisson(500) instances, 1024x1024, tile t -> rank t mod G",
                        "instances": int(n_global), "paste_variant": args.variant, "frame_arena_gb": round(slots * frame_bytes / 2**30, 1),
-                       "tile_batches": args.batches, "e2e_tile_batches": args.e2e_batches, "paste_ctas_per_sm": args.paste_ctas,
-                       "per_step_ms": [round(v, 2) for v in per_step_ms],
+                       "tile_batches": args.batches, "e2e_tile_batches": args.e2e_batches,
+                       "host_syncs_per_step": 0 if pipe.sync_free else 2, "paste_ctas_per_sm": args.paste_ctas,
+                       "per_step_ms": [round(v, 2) for v in per_step_ms], "per_rank_ms_per_step": per_rank_ms,
                        "l2": "per step each rank writes >= 16 GB of frames and re-reads GBs of inputs: far larger than the 126 MB L2",
                        "um_pix": UM_PIX, "dedup_iou": DEDUP_IOU, "rules": "polyhipes_tommy"},
             "mask_mpix_per_sec": value * H * W / 1e6,

@@ -21,7 +21,7 @@ _SIGNATURES = {
     "emia_exclusive_scan_i64": (c_int, [c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
     "emia_paste_plan": (c_int, [c_void_p, c_int64, c_float, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "emia_paste_threshold_bitpack": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_int, c_int,
-                                             c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+                                             c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "emia_mask_bbox": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "emia_mask_pack": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "emia_mask_unpack": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
@@ -32,11 +32,11 @@ _SIGNATURES = {
                                    c_void_p]),
     "emia_contour_trace_plan": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "emia_contour_trace_slab": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
-                                        c_void_p, c_void_p, c_void_p, c_void_p]),
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "emia_list_measure_plan": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_void_p]),
     "emia_contour_measure_list": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_double,
-                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "emia_contour_measure_stored": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_double, c_double,
                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "emia_group_workspace_bytes": (c_size_t, [c_void_p, c_int]),

@@ -208,7 +208,8 @@ __global__ void __launch_bounds__(EMIA_PASTE_THREADS) k_paste(
     const float* __restrict__ probs, const float4* __restrict__ boxes, const emia_inst_meta* __restrict__ meta,
     const int64_t* __restrict__ crop_off, int64_t n, float sx, float sy, int H, int W, uint32_t* __restrict__ frames,
     int64_t frame_slots, int pitch_words, uint32_t* __restrict__ crops, int32_t* __restrict__ bbox,
-    int32_t* __restrict__ area, int max_cols) {
+    int32_t* __restrict__ area, int max_cols, const int32_t* __restrict__ abort_flag) {
+    if (abort_flag && *abort_flag) return;      // a caller-side capacity guard tripped: write nothing
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* s_prob = (float*)smem_raw;                                  // 784
     uint32_t* s_tile = (uint32_t*)(s_prob + EMIA_MASK_SIDE * EMIA_MASK_SIDE);   // EMIA_PASTE_TILE_WORDS
@@ -361,7 +362,8 @@ __global__ void __launch_bounds__(EMIA_PASTE_THREADS) k_paste_bulk(
     const float* __restrict__ probs, const float4* __restrict__ boxes, const emia_inst_meta* __restrict__ meta,
     const int64_t* __restrict__ crop_off, int64_t n, float sx, float sy, int H, int W, uint32_t* __restrict__ frames,
     int64_t frame_slots, int pitch_words, uint32_t* __restrict__ crops, int32_t* __restrict__ bbox,
-    int32_t* __restrict__ area, int max_cols) {
+    int32_t* __restrict__ area, int max_cols, const int32_t* __restrict__ abort_flag) {
+    if (abort_flag && *abort_flag) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t* s_zero = (uint32_t*)smem_raw;                              // EMIA_BULK_BYTES
     uint32_t* s_band = s_zero + EMIA_BULK_BYTES / 4;                     // EMIA_BULK_BYTES
@@ -514,7 +516,9 @@ template <bool kHalf>
 __global__ void __launch_bounds__(EMIA_PASTE_THREADS, EMIA_P2_MIN_CTAS) k_paste_v2(
     const void* __restrict__ probs_raw, const float4* __restrict__ boxes, const emia_inst_meta* __restrict__ meta,
     const int64_t* __restrict__ crop_off, int64_t n, float sx, float sy, int H, int W, uint32_t* __restrict__ frames,
-    int64_t frame_slots, int pitch_words, uint32_t* __restrict__ crops, int32_t* __restrict__ bbox, int32_t* __restrict__ area) {
+    int64_t frame_slots, int pitch_words, uint32_t* __restrict__ crops, int32_t* __restrict__ bbox, int32_t* __restrict__ area,
+    const int32_t* __restrict__ abort_flag) {
+    if (abort_flag && *abort_flag) return;      // a caller-side capacity guard tripped: write nothing
     __shared__ __align__(16) float s_pp2[2][EMIA_P2_PAD_ROWS * EMIA_P2_PAD_STRIDE];   // padded probabilities, double-buffered
     __shared__ __align__(16) __half s_half2[2][kHalf ? EMIA_MASK_SIDE * EMIA_MASK_SIDE : 8];   // fp16 head outputs: staged, then widened
     const float* probs = (const float*)probs_raw;
@@ -704,7 +708,8 @@ __global__ void __launch_bounds__(EMIA_PASTE_THREADS, EMIA_P2_MIN_CTAS) k_paste_
 extern "C" int emia_paste_threshold_bitpack(const float* probs, const float* boxes, const emia_inst_meta* meta,
                                             const int64_t* crop_off, int64_t n, float scale_x, float scale_y, int H,
                                             int W, uint32_t* frames, int64_t frame_slots, int pitch_words,
-                                            uint32_t* crops, int32_t* bbox, int32_t* area, int variant_and_grid, void* stream) {
+                                            uint32_t* crops, int32_t* bbox, int32_t* area, int variant_and_grid,
+                                            const int32_t* abort_flag, void* stream) {
     // bits 0-7: variant; bits 8-15: resident CTAs per SM (0 = default) — a smaller grid leaves SM room for other streams
     const int variant = variant_and_grid & 0xff;
     const int ctas_req = (variant_and_grid >> 8) & 0xff;
@@ -727,10 +732,10 @@ extern "C" int emia_paste_threshold_bitpack(const float* probs, const float* box
         const unsigned grid = (unsigned)(n < (int64_t)sms * per_sm ? n : (int64_t)sms * per_sm);
         if (probs_f16)
             k_paste_v2<true><<<grid, EMIA_PASTE_THREADS, 0, st>>>(probs, (const float4*)boxes, meta, crop_off, n, scale_x, scale_y, H, W, frames,
-                                                                  frames ? frame_slots : 1, pitch_words, crops, bbox, area);
+                                                                  frames ? frame_slots : 1, pitch_words, crops, bbox, area, abort_flag);
         else
             k_paste_v2<false><<<grid, EMIA_PASTE_THREADS, 0, st>>>(probs, (const float4*)boxes, meta, crop_off, n, scale_x, scale_y, H, W, frames,
-                                                                   frames ? frame_slots : 1, pitch_words, crops, bbox, area);
+                                                                   frames ? frame_slots : 1, pitch_words, crops, bbox, area, abort_flag);
         return emia_check_launch("emia_paste_threshold_bitpack (v2) launch: %s");
     }
     if (probs_f16) return emia_fail(EMIA_ERR_UNSUPPORTED, "emia_paste_threshold_bitpack: %s", "fp16 probabilities need variant 2 (W <= 2048, 32-byte frame rows)");
@@ -741,7 +746,7 @@ extern "C" int emia_paste_threshold_bitpack(const float* probs, const float* box
         const int64_t per_sm = ctas_req ? ctas_req : 4;
         const unsigned grid = (unsigned)(n < (int64_t)sms * per_sm ? n : (int64_t)sms * per_sm);
         k_paste_bulk<<<grid, EMIA_PASTE_THREADS, smem, st>>>(probs, (const float4*)boxes, meta, crop_off, n, scale_x, scale_y, H, W,
-                                                             frames, frame_slots, pitch_words, crops, bbox, area, max_cols);
+                                                             frames, frame_slots, pitch_words, crops, bbox, area, max_cols, abort_flag);
         return emia_check_launch("emia_paste_threshold_bitpack (bulk) launch: %s");
     }
     const size_t smem = EMIA_MASK_SIDE * EMIA_MASK_SIDE * 4 + EMIA_PASTE_TILE_WORDS * 4 + (size_t)max_cols * 12;
@@ -750,11 +755,11 @@ extern "C" int emia_paste_threshold_bitpack(const float* probs, const float* box
     if (frames) {
         cudaFuncSetAttribute(k_paste<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_paste<true><<<grid, EMIA_PASTE_THREADS, smem, st>>>(probs, (const float4*)boxes, meta, crop_off, n, scale_x, scale_y, H, W,
-                                                              frames, frame_slots, pitch_words, crops, bbox, area, max_cols);
+                                                              frames, frame_slots, pitch_words, crops, bbox, area, max_cols, abort_flag);
     } else {
         cudaFuncSetAttribute(k_paste<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_paste<false><<<grid, EMIA_PASTE_THREADS, smem, st>>>(probs, (const float4*)boxes, meta, crop_off, n, scale_x, scale_y, H, W,
-                                                               nullptr, 1, pitch_words, crops, bbox, area, max_cols);
+                                                               nullptr, 1, pitch_words, crops, bbox, area, max_cols, abort_flag);
     }
     return emia_check_launch("emia_paste_threshold_bitpack launch: %s");
 }

@@ -200,7 +200,9 @@ __global__ void __launch_bounds__(EMIA_PRESORT_WARPS * 32) k_contour_hull(int64_
                                                                          const int64_t* __restrict__ pt_off,
                                                                          const int32_t* __restrict__ cstart, int cstart_stride,
                                                                          const int64_t* __restrict__ scratch_off,
-                                                                         const uint32_t* __restrict__ pts, uint8_t* __restrict__ scratch) {
+                                                                         const uint32_t* __restrict__ pts, uint8_t* __restrict__ scratch,
+                                                                         const int32_t* __restrict__ abort_flag) {
+    if (abort_flag && *abort_flag) return;
     __shared__ EmiaHullSmem s_all[EMIA_PRESORT_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t it = (int64_t)blockIdx.x * EMIA_PRESORT_WARPS + warp;
@@ -244,7 +246,8 @@ __global__ void __launch_bounds__(128, 4) k_contour_measure(int64_t n, const int
                                                          const uint32_t* __restrict__ pts, const int32_t* __restrict__ cstart,
                                                          int cstart_stride, int presort_max, double* __restrict__ records,
                                                          int32_t* __restrict__ rec_inst, double* __restrict__ perim0,
-                                                         uint8_t* __restrict__ scratch) {
+                                                         uint8_t* __restrict__ scratch, const int32_t* __restrict__ abort_flag) {
+    if (abort_flag && *abort_flag) return;
     const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (it >= n) return;
     const int64_t i = item_inst ? (int64_t)item_inst[it] : it;
@@ -297,9 +300,9 @@ extern "C" int emia_contour_measure(const uint32_t* crops, const emia_inst_meta*
                                                                                   cont_off, pt_off, pts, cstart, nullptr);
     const unsigned grid = (unsigned)((n + 127) / 128);
     k_contour_hull<<<(unsigned)((n + EMIA_PRESORT_WARPS - 1) / EMIA_PRESORT_WARPS), EMIA_PRESORT_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        n, nullptr, cont_off, cont_off, pt_off, cstart, 0, scratch_off, pts, scratch);
+        n, nullptr, cont_off, cont_off, pt_off, cstart, 0, scratch_off, pts, scratch, nullptr);
     k_contour_measure<<<grid, 128, 0, (cudaStream_t)stream>>>(n, nullptr, cont_off, cont_off, pt_off, scratch_off, um_pix, min_area, pts, cstart, 0,
-                                                              EMIA_PRESORT_MAX, records, rec_inst, perim0, scratch);
+                                                              EMIA_PRESORT_MAX, records, rec_inst, perim0, scratch, nullptr);
     return emia_check_launch("emia_contour_measure launch: %s");
 }
 
@@ -337,7 +340,8 @@ __global__ void __launch_bounds__(EMIA_TRACE_THREADS) k_contour_trace_slab(
     const uint32_t* __restrict__ crops, const emia_inst_meta* __restrict__ meta, const int64_t* __restrict__ crop_off, int64_t n,
     uint32_t* __restrict__ marks, const int64_t* __restrict__ pt_cap_off, int capc, uint32_t* __restrict__ pts,
     int32_t* __restrict__ cstart_slab, int64_t* __restrict__ n_contours, int64_t* __restrict__ scratch_bytes,
-    int32_t* __restrict__ overflow, double* __restrict__ perim0, int chunk) {
+    int32_t* __restrict__ overflow, double* __restrict__ perim0, int chunk, const int32_t* __restrict__ abort_flag) {
+    if (abort_flag && *abort_flag) return;      // a caller-side capacity guard tripped: write nothing
     __shared__ float s_diag[EMIA_DIAG_TABLE];
     __shared__ int s_next;
     emia_fill_diag_table(s_diag);
@@ -401,7 +405,7 @@ extern "C" int emia_contour_trace_plan(const emia_inst_meta* meta, int64_t n, in
 extern "C" int emia_contour_trace_slab(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n,
                                        uint32_t* marks, const int64_t* pt_cap_off, int32_t cap_contours, uint32_t* pts,
                                        int32_t* cstart_slab, int64_t* n_contours, int64_t* scratch_bytes, int32_t* overflow,
-                                       double* perim0, void* stream) {
+                                       double* perim0, const int32_t* abort_flag, void* stream) {
     if (n < 0 || cap_contours < 1) return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_trace_slab: %s", "bad argument");
     if (n == 0) return EMIA_OK;
     if (!crops || !meta || !crop_off || !marks || !pt_cap_off || !pts || !cstart_slab || !n_contours || !scratch_bytes || !overflow)
@@ -414,7 +418,7 @@ extern "C" int emia_contour_trace_slab(const uint32_t* crops, const emia_inst_me
     const unsigned grid = (unsigned)((n + chunk - 1) / chunk);
     emia_launch_clear_marks(marks, crop_off, n, (cudaStream_t)stream);
     k_contour_trace_slab<<<grid, EMIA_TRACE_THREADS, 0, (cudaStream_t)stream>>>(crops, meta, crop_off, n, marks, pt_cap_off, cap_contours, pts,
-                                                                             cstart_slab, n_contours, scratch_bytes, overflow, perim0, (int)chunk);
+                                                                             cstart_slab, n_contours, scratch_bytes, overflow, perim0, (int)chunk, abort_flag);
     return emia_check_launch("emia_contour_trace_slab launch: %s");
 }
 
@@ -427,9 +431,9 @@ extern "C" int emia_contour_measure_stored(const emia_inst_meta* meta, int64_t n
     if (!meta || !cont_off || !pt_off || !cstart || !scratch_off || !pts || !records || !rec_inst || !perim0 || !scratch)
         return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_measure_stored: %s", "null pointer");
     k_contour_hull<<<(unsigned)((n + EMIA_PRESORT_WARPS - 1) / EMIA_PRESORT_WARPS), EMIA_PRESORT_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        n, nullptr, cont_off, cont_off, pt_off, cstart, cstart_stride, scratch_off, pts, (uint8_t*)scratch);
+        n, nullptr, cont_off, cont_off, pt_off, cstart, cstart_stride, scratch_off, pts, (uint8_t*)scratch, nullptr);
     k_contour_measure<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(n, nullptr, cont_off, cont_off, pt_off, scratch_off, um_pix, min_area, pts,
-                                                                                  cstart, cstart_stride, EMIA_PRESORT_MAX, records, rec_inst, perim0, scratch);
+                                                                                  cstart, cstart_stride, EMIA_PRESORT_MAX, records, rec_inst, perim0, scratch, nullptr);
     return emia_check_launch("emia_contour_measure_stored launch: %s");
 }
 
@@ -468,16 +472,16 @@ extern "C" int emia_list_measure_plan(const int32_t* cap_off, int32_t G, int32_t
 extern "C" int emia_contour_measure_list(int64_t n_items, const int32_t* item_inst, const int64_t* rec_off, const int64_t* scr_off,
                                          const int64_t* inst_cont_off, const int64_t* pt_off, const int32_t* cstart,
                                          int32_t cstart_stride, double um_pix, double min_area, const uint32_t* pts, double* records,
-                                         int32_t* rec_inst, uint8_t* scratch, void* stream) {
+                                         int32_t* rec_inst, uint8_t* scratch, const int32_t* abort_flag, void* stream) {
     if (n_items < 0 || cstart_stride < 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_measure_list: %s", "bad argument");
     if (n_items == 0) return EMIA_OK;
     if (!item_inst || !rec_off || !scr_off || !pt_off || !cstart || !pts || !records || !rec_inst || !scratch ||
         (cstart_stride == 0 && !inst_cont_off))
         return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_measure_list: %s", "null pointer");
     k_contour_hull<<<(unsigned)((n_items + EMIA_PRESORT_WARPS - 1) / EMIA_PRESORT_WARPS), EMIA_PRESORT_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        n_items, item_inst, rec_off, inst_cont_off, pt_off, cstart, cstart_stride, scr_off, pts, scratch);
+        n_items, item_inst, rec_off, inst_cont_off, pt_off, cstart, cstart_stride, scr_off, pts, scratch, abort_flag);
     k_contour_measure<<<(unsigned)((n_items + 127) / 128), 128, 0, (cudaStream_t)stream>>>(n_items, item_inst, rec_off, inst_cont_off, pt_off, scr_off,
                                                                                         um_pix, min_area, pts, cstart, cstart_stride,
-                                                                                        EMIA_PRESORT_MAX, records, rec_inst, nullptr, scratch);
+                                                                                        EMIA_PRESORT_MAX, records, rec_inst, nullptr, scratch, abort_flag);
     return emia_check_launch("emia_contour_measure_list launch: %s");
 }

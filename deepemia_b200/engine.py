@@ -129,7 +129,7 @@ def paste_plan(boxes, H, W, scale_x=1.0, scale_y=1.0):
 
 
 def paste(probs, boxes, H, W, scores=None, classes=None, scale_x=1.0, scale_y=1.0, frames=None, frame_slots=0,
-          variant=2, crops_out=None, plan=None, ctas_per_sm=0):
+          variant=2, crops_out=None, plan=None, ctas_per_sm=0, abort=None):
     """K1.  probs [n,28,28] f32 (or f16, as an AMP mask head emits them), boxes [n,4] f32 xyxy (device tensors) -> InstanceSet.
     frames: None (crops only), True (allocate n full frames) or a preallocated int32 [slots, H, pitch_words] ring.
     plan: (meta, crop_off, total_crop_words) from paste_plan() — possibly a slice of a larger plan whose crop offsets index
@@ -167,7 +167,7 @@ def paste(probs, boxes, H, W, scores=None, classes=None, scale_x=1.0, scale_y=1.
     with _stage("k1_paste"):
         _lib.check(lib.emia_paste_threshold_bitpack(_ptr(probs), _ptr(boxes), _ptr(meta), _ptr(crop_off), n, scale_x, scale_y, H, W,
                                                     _ptr(frames), slots, pw, _ptr(crops), _ptr(bbox), _ptr(area),
-                                                    int(variant) | (int(ctas_per_sm) << 8) | f16, st),
+                                                    int(variant) | (int(ctas_per_sm) << 8) | f16, _ptr(abort), st),
                    "emia_paste_threshold_bitpack")
     LAUNCHES["count"] += 1
     return InstanceSet(n=n, H=H, W=W, meta=meta, crop_off=crop_off, crops=crops, bbox=bbox, area=area, scores=scores,
@@ -347,7 +347,7 @@ def default_min_area(H, W):
     return max(5, H * W * 0.000005 * 0.05)
 
 
-def trace(iset, single_pass=True, marks=None):
+def trace(iset, single_pass=True, marks=None, abort=None):
     """K5a: external contours of every instance.  Leaves on the device: vertex lists (pts, cstart), the number of contours and
     the hull scratch size per instance, and perim0 = arcLength(contours[0]) (the compactness pre-filter of
     deduplicate_masks_smart needs it).  single_pass follows every border once into bounded per-instance slabs and does NOT
@@ -374,7 +374,7 @@ def trace(iset, single_pass=True, marks=None):
         with _stage("k5_trace"):
             _lib.check(lib.emia_contour_trace_slab(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), n, _ptr(marks), _ptr(sizes[1]),
                                                    CAP_CONTOURS, _ptr(pts), _ptr(cstart), _ptr(sizes[0]), _ptr(sizes[2]), _ptr(flag),
-                                                   _ptr(perim0), st), "emia_contour_trace_slab")
+                                                   _ptr(perim0), _ptr(abort), st), "emia_contour_trace_slab")
         LAUNCHES["count"] += 2
         iset.cstart_stride = CAP_CONTOURS + 1
         iset.extra["overflow"] = flag
@@ -410,8 +410,18 @@ class Measurements:
     records: torch.Tensor     # float64 [R, 16]
     rec_inst: torch.Tensor    # int32 [R]
     rec_off: torch.Tensor     # int64 [L + 1]
-    n_records: int
+    n_records: Optional[int]  # None: sized by capacity, call finalize()
     groups: "Groups"
+    totals: object = None     # (records, scratch bytes): host ints, or a device tensor until finalize()
+
+    def finalize(self):
+        """Read the totals back (one host synchronisation) and trim the capacity-sized buffers."""
+        if self.n_records is None:
+            n_rec, n_scr = (int(v) for v in self.totals.tolist())
+            self.totals = (n_rec, n_scr)
+            self.n_records = n_rec
+            self.records, self.rec_inst = self.records[:n_rec], self.rec_inst[:n_rec]
+        return self
 
     def rows_to_host(self):
         """Per group: list of (instance id, float64 [k,16] rows) in list order (host copies)."""
@@ -422,9 +432,12 @@ class Measurements:
                 for g in range(self.groups.G)]
 
 
-def measure_list(iset, groups, um_pix=1.0, min_area=None):
+def measure_list(iset, groups, um_pix=1.0, min_area=None, capacity=None, abort=None):
     """K5b: morphometry of the members of `groups` only (what the reference's measurement loop sees).  Needs trace().
-    Returns None when the single-pass trace overflowed (the caller re-traces with single_pass=False)."""
+    Returns None when the single-pass trace overflowed (the caller re-traces with single_pass=False).
+    capacity = (records, scratch bytes) + abort (device int32 flag): no host synchronisation — the buffers take the given
+    capacities, the flag is raised on the device when the actual totals (or a slab) overflow, and nothing is written then;
+    the returned Measurements has n_records = None until finalize()."""
     lib = _lib.load()
     dev = iset.device
     assert iset.pts is not None, "run trace() first"
@@ -442,10 +455,17 @@ def measure_list(iset, groups, um_pix=1.0, min_area=None):
         exclusive_scan_(offs[1])
     LAUNCHES["count"] += 1
     flag = iset.extra.get("overflow")
-    tot = torch.stack([offs[0, L], offs[1, L], flag[0].to(torch.int64) if flag is not None else offs[0, 0]]).tolist()
-    n_rec, n_scr, overflow = int(tot[0]), int(tot[1]), int(tot[2])
-    if overflow:
-        return None
+    if capacity is not None:
+        n_rec, n_scr = int(capacity[0]), int(capacity[1])
+        over = (offs[0, L] > n_rec) | (offs[1, L] > n_scr)
+        if flag is not None:
+            over = over | (flag[0] != 0)
+        abort.logical_or_(over)          # int32 flag, stays 0 / 1; stream-ordered before the kernels that honour it
+    else:
+        tot = torch.stack([offs[0, L], offs[1, L], flag[0].to(torch.int64) if flag is not None else offs[0, 0]]).tolist()
+        n_rec, n_scr, overflow = int(tot[0]), int(tot[1]), int(tot[2])
+        if overflow:
+            return None
     records = torch.empty((max(n_rec, 1), REC_FIELDS), dtype=torch.float64, device=dev)
     rec_inst = torch.empty(max(n_rec, 1), dtype=torch.int32, device=dev)
     scratch = torch.empty(max(n_scr, 16), dtype=torch.uint8, device=dev)
@@ -453,10 +473,15 @@ def measure_list(iset, groups, um_pix=1.0, min_area=None):
         with _stage("k5_measure"):
             _lib.check(lib.emia_contour_measure_list(L, _ptr(item_inst), _ptr(offs[0]), _ptr(offs[1]), _ptr(iset.cont_off),
                                                      _ptr(iset.pt_off), _ptr(iset.cstart), iset.cstart_stride, float(um_pix),
-                                                     float(min_area), _ptr(iset.pts), _ptr(records), _ptr(rec_inst), _ptr(scratch), st),
+                                                     float(min_area), _ptr(iset.pts), _ptr(records), _ptr(rec_inst), _ptr(scratch),
+                                                     _ptr(abort) if capacity is not None else 0, st),
                        "emia_contour_measure_list")
         LAUNCHES["count"] += 2
-    return Measurements(records=records[:n_rec], rec_inst=rec_inst[:n_rec], rec_off=offs[0], n_records=n_rec, groups=groups)
+    if capacity is not None:
+        return Measurements(records=records, rec_inst=rec_inst, rec_off=offs[0], n_records=None, groups=groups,
+                            totals=torch.stack([offs[0, L], offs[1, L]]))
+    return Measurements(records=records[:n_rec], rec_inst=rec_inst[:n_rec], rec_off=offs[0], n_records=n_rec, groups=groups,
+                        totals=(n_rec, n_scr))
 
 
 def measure(iset, um_pix=1.0, min_area=None, single_pass=True):
@@ -893,7 +918,7 @@ class TilePipeline:
     Batches see slices of shard-wide arrays; list indices stay shard-global."""
 
     def __init__(self, H, W, um_pix=1.0, rules=None, dedup_iou=0.7, frames=None, variant=2, batches=8, paste_ctas_per_sm=0,
-                 device=None):
+                 device=None, sync_free=True, hint_margin=1.05):
         self.H, self.W, self.um_pix, self.rules, self.dedup_iou = H, W, um_pix, rules, dedup_iou
         self.frames, self.variant, self.batches, self.paste_ctas = frames, variant, batches, paste_ctas_per_sm
         self.dev = _need_cuda(device)
@@ -904,6 +929,9 @@ class TilePipeline:
         self._groups_cache = {}
         self._pinned = {}
         self.k1_events = []
+        # sizes of the previous run per shard shape: the next run of that shape is enqueued without reading anything back
+        self.sync_free, self.hint_margin = sync_free, hint_margin
+        self._hints, self._ib_cache, self._abort, self._last_hkey = {}, {}, None, None
 
     def _groups(self, offs):
         key = offs.tobytes()
@@ -949,9 +977,26 @@ class TilePipeline:
         _lib.check(lib.emia_contour_trace_plan(_ptr(meta), n, _ptr(cap_off), _stream()), "emia_contour_trace_plan")
         exclusive_scan_(cap_off)
         LAUNCHES["count"] += 1
-        ib_t = torch.as_tensor(ib, device=dev)
-        bounds = torch.stack([crop_off[ib_t], cap_off[ib_t]]).cpu().numpy()
-        total_words = int(bounds[0, -1])
+        # Sizes: read back once (first run of this shard shape), afterwards taken from the previous run ("hints") and only
+        # CHECKED on the device: the whole step is then enqueued without a single host synchronisation, the abort flag is
+        # looked at when the results are consumed (aborted()).  A tripped guard makes the paste / trace / measure kernels
+        # write nothing; the caller re-runs, which takes the exact-size path again.
+        hkey = (n, offs.tobytes(), B)
+        hints = self._hints.get(hkey) if self.sync_free else None
+        ib_t = self._ib_cache.get(hkey)
+        if ib_t is None:
+            ib_t = torch.as_tensor(ib, device=dev)
+            self._ib_cache[hkey] = ib_t
+        abort = torch.zeros(1, dtype=torch.int32, device=dev)
+        if hints is None:
+            bounds = torch.stack([crop_off[ib_t], cap_off[ib_t]]).cpu().numpy()
+            total_words = int(bounds[0, -1])
+            pt_caps = [int(bounds[1, b + 1] - bounds[1, b]) for b in range(B)]
+            meas_caps = [None] * B
+        else:
+            total_words, pt_caps, meas_caps, caps_t = hints["total_words"], hints["pt_caps"], hints["meas_caps"], hints["pt_caps_t"]
+            over = (crop_off[n] > total_words) | ((cap_off[ib_t[1:]] - cap_off[ib_t[:-1]]) > caps_t).any()
+            abort.logical_or_(over)
         crops = torch.empty(max(total_words, 1), dtype=torch.int32, device=dev)
         marks = torch.empty(max(2 * total_words, 1), dtype=torch.int32, device=dev)
         self.s_paste.wait_stream(main); self.s_post.wait_stream(main)
@@ -966,10 +1011,11 @@ class TilePipeline:
                     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e0.record(self.s_paste)
                 it = paste(d_probs[i0:i1], d_boxes[i0:i1], self.H, self.W, scores=d_scores[i0:i1], classes=d_classes[i0:i1],
                            frames=self.frames, variant=self.variant, crops_out=crops,
-                           plan=(meta[i0:i1], crop_off[i0:i1 + 1], total_words), ctas_per_sm=self.paste_ctas)
+                           plan=(meta[i0:i1], crop_off[i0:i1 + 1], total_words), ctas_per_sm=self.paste_ctas,
+                           abort=abort if hints is not None else None)
                 if time_k1:
                     e1.record(self.s_paste); self.k1_events.append((e0, e1))
-                it.extra["pt_cap_total"] = int(bounds[1, b + 1] - bounds[1, b])
+                it.extra["pt_cap_total"] = pt_caps[b]
                 e = torch.cuda.Event(); e.record(self.s_paste); ev_paste.append(e)
                 isets.append(it)
         out = []
@@ -978,15 +1024,23 @@ class TilePipeline:
                 it = isets[b]
                 self.s_post.wait_event(ev_paste[b])
                 groups = self._groups(offs[tb[b]:tb[b + 1] + 1] - ib[b])
-                single_pass = True
-                while True:
-                    trace(it, single_pass=single_pass, marks=marks)
+                if hints is not None:
+                    trace(it, single_pass=True, marks=marks, abort=abort)
                     kept = dedup_smart(it, groups, iou_threshold=self.dedup_iou)
                     kept = apply_spatial_constraints(it, kept, self.rules)
-                    meas = measure_list(it, kept, um_pix=self.um_pix)
-                    if meas is not None:
-                        break
-                    single_pass = False
+                    meas = measure_list(it, kept, um_pix=self.um_pix, capacity=meas_caps[b], abort=abort)
+                else:
+                    single_pass = True
+                    while True:
+                        trace(it, single_pass=single_pass, marks=marks)
+                        kept = dedup_smart(it, groups, iou_threshold=self.dedup_iou)
+                        kept = apply_spatial_constraints(it, kept, self.rules)
+                        meas = measure_list(it, kept, um_pix=self.um_pix)
+                        if meas is not None:
+                            break
+                        single_pass = False
+                    meas_caps[b] = (max(int(meas.totals[0] * self.hint_margin) + 16, 16), max(int(meas.totals[1] * self.hint_margin) + 64, 64)) \
+                        if single_pass else None
                 res = {"tiles": (int(tb[b]), int(tb[b + 1])), "inst0": int(ib[b]), "iset": it, "kept": kept, "meas": meas}
                 if to_host:
                     res["host"] = {k: self._pinned_like(b, k, v).copy_(v, non_blocking=True)
@@ -997,7 +1051,24 @@ class TilePipeline:
         if host_in:
             main.wait_stream(self.s_copy)
         self._keep = (crops, marks, meta, crop_off, cap_off, d_probs)
+        self._abort = abort
+        if hints is None and self.sync_free and all(c is not None for c in meas_caps):
+            m = self.hint_margin
+            caps = [int(c * m) + 64 for c in pt_caps]
+            if len(self._hints) > 64:
+                self._hints.clear()
+            self._hints[hkey] = {"total_words": int(total_words * m) + 64, "pt_caps": caps, "meas_caps": meas_caps,
+                                 "pt_caps_t": torch.as_tensor(np.asarray(caps, np.int64), device=dev)}
+        self._last_hkey = hkey
         return out
+
+    def aborted(self):
+        """True when a capacity guard (or a contour slab) tripped in the last sync-free run(): its results are invalid, the hints
+        of that shard shape are dropped and the caller runs again (exact-size path).  One host synchronisation."""
+        if self._abort is None or not bool(self._abort.item()):
+            return False
+        self._hints.pop(self._last_hkey, None)
+        return True
 
     def _pinned_like(self, b, name, t):
         """Persistent pinned result buffers (one per batch and result array, grown on demand): page-locking memory inside

@@ -66,6 +66,11 @@ const char* emia_last_error(void);
 size_t emia_scan_workspace_bytes(int64_t n);
 int emia_exclusive_scan_i64(int64_t* data, int64_t n, void* workspace, size_t workspace_bytes, void* stream);
 
+/* abort_flag (optional device int32, may be NULL) on the three entry points that WRITE variable-size outputs — paste, contour
+ * tracing, list measurement: when *abort_flag != 0 at kernel start the call writes nothing.  It lets a host enqueue a whole step
+ * without reading sizes back: buffers are sized from the previous step, a device-side comparison of the new totals with those
+ * capacities raises the flag, and the host looks at it once, when it consumes the results (engine.TilePipeline). */
+
 /* ---- K1: paste + threshold + bit-pack ----------------------------------------------------------------------
  * Replaces Detectron2 0.6 detector_postprocess + paste_masks_in_image(threshold 0.5) reached through
  * `predictor(image)` at src/functions/inference.py:1395,1398,1507,1669,2107, the D2H of pred_masks at :1401,
@@ -85,7 +90,7 @@ int emia_paste_plan(const float* boxes, int64_t n, float scale_x, float scale_y,
 int emia_paste_threshold_bitpack(const float* probs, const float* boxes, const emia_inst_meta* meta,
                                  const int64_t* crop_off, int64_t n, float scale_x, float scale_y, int H, int W,
                                  uint32_t* frames, int64_t frame_slots, int pitch_words, uint32_t* crops,
-                                 int32_t* bbox, int32_t* area, int variant, void* stream);
+                                 int32_t* bbox, int32_t* area, int variant, const int32_t* abort_flag, void* stream);
 
 /* ---- mask import: byte masks -> crops (for callers that already hold H x W masks) ---------------------------
  * Replaces the reference's list-of-H x W-numpy-arrays representation (src/functions/inference.py:1401-1403,
@@ -133,7 +138,8 @@ int emia_contour_trace_plan(const emia_inst_meta* meta, int64_t n, int64_t* pt_c
 int emia_contour_trace_slab(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n,
                             uint32_t* marks, const int64_t* pt_cap_off, int32_t cap_contours, uint32_t* pts,
                             int32_t* cstart_slab, int64_t* n_contours, int64_t* scratch_bytes, int32_t* overflow,
-                            double* perim0 /* optional: arcLength(contours[0]) per instance */, void* stream);
+                            double* perim0 /* optional: arcLength(contours[0]) per instance */, const int32_t* abort_flag,
+                            void* stream);
 int emia_contour_measure_stored(const emia_inst_meta* meta, int64_t n, const int64_t* cont_off, const int64_t* pt_off,
                                 const int32_t* cstart, int32_t cstart_stride, const int64_t* scratch_off, double um_pix,
                                 double min_area, const uint32_t* pts, double* records, int32_t* rec_inst, double* perim0,
@@ -151,7 +157,7 @@ int emia_list_measure_plan(const int32_t* cap_off, int32_t G, int32_t total_cap,
 int emia_contour_measure_list(int64_t n_items, const int32_t* item_inst, const int64_t* rec_off, const int64_t* scr_off,
                               const int64_t* inst_cont_off, const int64_t* pt_off, const int32_t* cstart,
                               int32_t cstart_stride, double um_pix, double min_area, const uint32_t* pts, double* records,
-                              int32_t* rec_inst, uint8_t* scratch, void* stream);
+                              int32_t* rec_inst, uint8_t* scratch, const int32_t* abort_flag, void* stream);
 
 /* ---- K4: mask-IoU de-duplication and spatial constraints ----------------------------------------------------
  * All operate on G groups at once; see "Instance layout".  total_cap = cap_off[G] (the host knows it).

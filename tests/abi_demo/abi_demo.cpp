@@ -48,7 +48,7 @@ int main(int argc, char** argv) {
     const int64_t total_words = fetch(crop_off + n);
     uint32_t* crops = dalloc<uint32_t>(total_words);
     int32_t *bbox = dalloc<int32_t>((size_t)n * 4), *area = dalloc<int32_t>(n);
-    EK(emia_paste_threshold_bitpack(d_probs, d_boxes, meta, crop_off, n, 1.f, 1.f, H, W, nullptr, 1, 8 * ((W + 255) / 256), crops, bbox, area, 2, st));
+    EK(emia_paste_threshold_bitpack(d_probs, d_boxes, meta, crop_off, n, 1.f, 1.f, H, W, nullptr, 1, 8 * ((W + 255) / 256), crops, bbox, area, 2, nullptr, st));
 
     // ---- K5a: contours into per-instance slabs
     const int capc = 8;
@@ -61,7 +61,7 @@ int main(int argc, char** argv) {
     int32_t *cstart = dalloc<int32_t>((size_t)n * (capc + 1) + 1), *overflow = dalloc<int32_t>(1);
     double* perim0 = dalloc<double>(n);
     CK(cudaMemsetAsync(overflow, 0, 4, st));
-    EK(emia_contour_trace_slab(crops, meta, crop_off, n, marks, pt_cap, capc, pts, cstart, ncont, scr_bytes, overflow, perim0, st));
+    EK(emia_contour_trace_slab(crops, meta, crop_off, n, marks, pt_cap, capc, pts, cstart, ncont, scr_bytes, overflow, perim0, nullptr, st));
 
     // ---- K4: de-dup 0.7, overlap rules (0: 0.30, 1: 0.50), containment 1 -> 0 at 0.95 (polyhipes_tommy)
     int max_cap = 0;
@@ -101,7 +101,7 @@ int main(int argc, char** argv) {
     int32_t* rec_inst = dalloc<int32_t>(n_rec);
     uint8_t* scratch = dalloc<uint8_t>(n_scr + 16);
     const double min_area = 5.0 > H * W * 0.000005 * 0.05 ? 5.0 : H * W * 0.000005 * 0.05;
-    EK(emia_contour_measure_list(n, item_inst, rec_off, scr_off, nullptr, pt_cap, cstart, capc + 1, 0.5, min_area, pts, records, rec_inst, scratch, st));
+    EK(emia_contour_measure_list(n, item_inst, rec_off, scr_off, nullptr, pt_cap, cstart, capc + 1, 0.5, min_area, pts, records, rec_inst, scratch, nullptr, st));
     CK(cudaStreamSynchronize(st));
 
     std::vector<int32_t> klen(T), kidx(n), rinst(n_rec);

@@ -33,7 +33,7 @@ def test_bad_arguments_return_error_codes():
     lib = _lib.load()
     assert lib.emia_paste_plan(None, 4, 1.0, 1.0, 16, 16, None, None, None) == -1
     assert b"emia_paste_plan" in lib.emia_last_error()
-    assert lib.emia_paste_threshold_bitpack(None, None, None, None, -1, 1.0, 1.0, 8, 8, None, 1, 4, None, None, None, 0, None) == -1
+    assert lib.emia_paste_threshold_bitpack(None, None, None, None, -1, 1.0, 1.0, 8, 8, None, 1, 4, None, None, None, 0, None, None) == -1
     assert lib.emia_dedup_smart(*([None] * 10), -1, 0, 0, None, None, 0.5, 0.0, None, None, None, 0, None) == -1
     assert lib.emia_exclusive_scan_i64(None, 0, None, 0, None) == -1
 

@@ -355,3 +355,33 @@ def test_tile_pipeline_matches_single_batch_path(cuda_device, host_inputs):
     p, b, s, c = tiles[4]
     final, rows, _ = pipeline.run_tile(p, b, s, c, H, W, um_pix=0.5, rules=syn.POLYHIPES_RULES, dedup_iou=0.7)
     assert [k - offs[4] for k in ref_kept[4]] == final
+
+
+def test_tile_pipeline_sync_free_guards(cuda_device):
+    """Runs after the first of a shard shape are enqueued without reading sizes back; when the new inputs need more room than the
+    previous run left, the device-side guard trips, nothing is written, aborted() reports it and the re-run is exact again."""
+    H, W = 256, 256
+    def shard(seed, rmax):
+        tiles = [_heads(seed + t, 40, H, W, duplicate_frac=0.3, rmin=5, rmax=rmax, margin=30) for t in range(4)]
+        cat = [np.concatenate([t[k] for t in tiles]) for k in range(4)]
+        offs = np.concatenate([[0], np.cumsum([len(t[0]) for t in tiles])])
+        return _dev(cuda_device, *cat), offs
+    pipe = engine.TilePipeline(H, W, um_pix=0.5, rules=syn.POLYHIPES_RULES, dedup_iou=0.7, batches=2, device=cuda_device)
+    small, offs = shard(100, 9)
+    big, offs_b = shard(200, 28)
+    assert np.array_equal(offs, offs_b)                      # same shard shape, much larger particles
+    def result(res):
+        out = []
+        for r in res:
+            r["meas"].finalize()
+            out.append((r["kept"].to_lists(), r["meas"].records.cpu().numpy().copy()))
+        return out
+    ref_small = result(pipe.run(*small, offs)); assert not pipe.aborted()          # exact-size path, records the hints
+    again = result(pipe.run(*small, offs)); assert not pipe.aborted()               # sync-free path
+    assert all(a[0] == b[0] and np.array_equal(a[1], b[1]) for a, b in zip(ref_small, again))
+    pipe.run(*big, offs)                                                            # does not fit the hints
+    assert pipe.aborted()
+    got_big = result(pipe.run(*big, offs)); assert not pipe.aborted()               # exact-size path again
+    fresh = engine.TilePipeline(H, W, um_pix=0.5, rules=syn.POLYHIPES_RULES, dedup_iou=0.7, batches=2, device=cuda_device, sync_free=False)
+    ref_big = result(fresh.run(*big, offs))
+    assert all(a[0] == b[0] and np.array_equal(a[1], b[1]) for a, b in zip(ref_big, got_big))
