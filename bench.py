@@ -286,12 +286,15 @@ def main():
         r = step(h_probs, h_boxes, h_scores, h_classes, to_host=True)
         torch.cuda.current_stream().synchronize()      # the pinned result buffers are complete
         return r
-    for _ in range(2):
+    for _ in range(max(2, args.warmup)):
         res_h = e2e_step()
     barrier()
+    e2e_wall = []
     ev[0].record()
     for _ in range(args.steps):
+        t0 = time.perf_counter()
         res_h = e2e_step()
+        e2e_wall.append(round((time.perf_counter() - t0) * 1e3, 2))
     ev[1].record()
     barrier()
     ms_e2e = ev[0].elapsed_time(ev[1])
@@ -303,7 +306,7 @@ def main():
         r = pipe_e2e.run(h_probs16, h_boxes, h_scores, h_classes, offs, to_host=True)
         torch.cuda.current_stream().synchronize()
         return r
-    for _ in range(2):
+    for _ in range(max(2, args.warmup)):
         res_h16 = e2e16_step()
     barrier()
     ev[0].record()
@@ -364,7 +367,7 @@ def main():
             "mask_mpix_per_sec": value * H * W / 1e6,
             "clocks": _clock_summary(clk_path, local),
             "e2e": {"value": e2e_val, "unit": "instances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps, "rank0_wall_ms_per_step": e2e_wall},
             "e2e_fp16_heads": {"value": n_global / (ms_e2e16 / args.steps * 1e-3), "unit": "instances/s",
                                "h2d_bytes_per_step": int(h_probs16.numel() * 2 + h_boxes.numel() * 4 + h_scores.numel() * 4 + h_classes.numel() * 4),
                                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e16 / args.steps, "identical_results_to_f32": bool(same16),
