@@ -154,7 +154,6 @@ def paste(probs, boxes, H, W, scores=None, classes=None, scale_x=1.0, scale_y=1.
         assert crops_out.numel() >= max(total, 1)
         crops = crops_out
     else:
-        assert plan is None or n == 0 or True
         crops = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
     bbox = torch.empty((n, 4), dtype=torch.int32, device=dev)
     area = torch.empty(n, dtype=torch.int32, device=dev)

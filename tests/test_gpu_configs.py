@@ -64,10 +64,12 @@ def test_config3_8192_micrograph_tiles(cuda_device):
     finally:
         engine.FUSED_K4 = old
     assert len(dup.scores) == 2 * len(d) and len(staged) >= len(d)
-    # every survivor of the doubled list is one of the two copies of a distinct instance unless Q1 (lower-left half) keeps both
+    # an exact duplicate is only kept next to its original where the Q1 bbox test (lower-left half of the image: x_min < y_min)
+    # or the Q2 slice start lets it through; outside that half at least one copy of every pair must be gone
     bb = iset.bbox.cpu().numpy()
-    both = [i for i in range(len(d)) if i in staged and i + len(d) in staged]
-    assert all(bb[i][1] < bb[i][0] or True for i in both)
+    st = set(staged)
+    both = [i for i in range(len(d)) if i in st and i + len(d) in st]
+    assert len(both) < len(d)
     # (3) bit-packed storage: the whole micrograph's instances take megabytes, not 64 MiB each
     assert iset.total_crop_words * 4 < 64 * 2**20
     # (4) scores are sorted (keep order of deduplicate_masks_smart)
