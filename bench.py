@@ -385,7 +385,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            ntl = max(1, min(cores, args.ref_tiles))
+            ntl = max(1, min(len(tiles), args.ref_tiles))          # default 8 tiles (~6 s on 8 cores); more for a wider parity sample
             sample = tiles[:ntl]
             dt, cres = cpu_reference_run(sample, protos, min(cores, ntl))
             inst = sum(r[1] for r in cres)
@@ -405,7 +405,7 @@ def main():
                 if len(gv) != len(vals) or not all(np.allclose(a, np.array(b), rtol=1e-5, atol=0) for a, b in zip(gv, vals)):
                     ok = False
             line["cpu_baseline"] = {"value": inst / dt, "unit": "instances/s", "cores": min(cores, ntl), "kind": "port",
-                                    "sample": f"{ntl} of {args.tiles} tiles ({inst} instances), one process per core, {dt:.1f} s, "
+                                    "sample": f"{ntl} of {args.tiles} tiles ({inst} instances), one process per core ({min(cores, ntl)}), {dt:.1f} s, "
                                               "compute only (no per-instance JPEG dump / gc.collect)",
                                     "parity_vs_gpu_on_sample": bool(ok)}
         print(json.dumps(line))
