@@ -12,7 +12,7 @@
 #pragma once
 
 #define EMIA_FUSED_MAX_CAP 1024
-#define EMIA_FUSED_THREADS 256
+#define EMIA_FUSED_THREADS 512
 #define EMIA_FUSED_QUEUE 4096
 
 struct EmiaFusedSmem {
