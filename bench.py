@@ -252,14 +252,6 @@ def main():
     assert not pipe.aborted(), "a capacity guard tripped in the timed region: the results of the last step are invalid"
     for r in res:
         r["meas"].finalize()
-    if args.device_pass_only:
-        if sampler is not None:
-            sampler.terminate()
-        if rank == 0:
-            print(json.dumps({"device_pass_only": True, "ms_per_step": ms_total / args.steps, "instances": n_local}))
-        if world > 1:
-            dist.destroy_process_group()
-        return
     if args.breakdown and rank == 0:
         # un-overlapped pass (one batch, one stream) with per-stage CUDA events
         engine.STAGE_TIMING["enabled"] = True
@@ -271,6 +263,14 @@ def main():
         engine.STAGE_TIMING["enabled"] = False
         summ = engine.stage_summary()
         print(json.dumps({"stage_ms": summ, "sum_ms": sum(summ.values()), "wall_ms": wall}), file=sys.stderr)
+    if args.device_pass_only:
+        if sampler is not None:
+            sampler.terminate()
+        if rank == 0:
+            print(json.dumps({"device_pass_only": True, "ms_per_step": ms_total / args.steps, "instances": n_local}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     # K1 alone (nothing else on the GPU), for comparison with its in-pipeline duration
     k1_alone = []
     for _ in range(3):

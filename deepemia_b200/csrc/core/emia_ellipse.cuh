@@ -292,11 +292,40 @@ EMIA_HD void emia_solve_sym2_minnorm(double a, double b, double c, double r0, do
     *x0 = sx; *x1 = sy;
 }
 
+// Axes / angle of the re-fitted conic A' x^2 + B' y^2 + C' xy = 1 about the centre rp[0..1] (scaled coordinates), rounded to
+// float32 as OpenCV does.  rp[2..4] are work space.  Shared by the serial fit and the cooperative kernel.
+EMIA_HD EmiaEllipse emia_ellipse_from_conic(const double* gfp, double* rp, double scale, float cxf, float cyf) {
+    EmiaEllipse box;
+    const double min_eps = 1e-8;
+    double t;
+    rp[4] = -0.5 * atan2(gfp[2], gfp[1] - gfp[0]);
+    if (fabs(gfp[2]) > min_eps) t = gfp[2] / sin(-2.0 * rp[4]);
+    else t = gfp[1] - gfp[0];
+    rp[2] = fabs(gfp[0] + gfp[1] - t);
+    if (rp[2] > min_eps) rp[2] = sqrt(2.0 / rp[2]);
+    rp[3] = fabs(gfp[0] + gfp[1] + t);
+    if (rp[3] > min_eps) rp[3] = sqrt(2.0 / rp[3]);
+
+    box.cx = (float)(rp[0] / scale) + cxf;
+    box.cy = (float)(rp[1] / scale) + cyf;
+    box.w = (float)(rp[2] * 2 / scale);
+    box.h = (float)(rp[3] * 2 / scale);
+    if (box.w > box.h) {
+        const float tmp = box.w; box.w = box.h; box.h = tmp;
+        box.angle = (float)(90 + rp[4] * 180 / M_PI);
+    } else {
+        box.angle = (float)(rp[4] * 180 / M_PI);   // only the axes are consumed by the reference
+    }
+    if (box.angle < -180) box.angle += 360;
+    if (box.angle > 360) box.angle -= 360;
+    box.ok = 1;
+    return box;
+}
+
 // General (non-"direct") fit; n >= 5 packed integer points.
 EMIA_HD_NOINLINE EmiaEllipse emia_fit_ellipse_general(const uint32_t* pts, int n) {
     EmiaEllipse box; box.cx = box.cy = box.w = box.h = box.angle = 0.f; box.ok = 0;
     if (n < 5) return box;
-    const double min_eps = 1e-8;
     float cxf = 0.f, cyf = 0.f;
     for (int i = 0; i < n; ++i) { cxf += (float)EMIA_PT_X(pts[i]); cyf += (float)EMIA_PT_Y(pts[i]); }
     cxf /= (float)n; cyf /= (float)n;
@@ -351,29 +380,7 @@ EMIA_HD_NOINLINE EmiaEllipse emia_fit_ellipse_general(const uint32_t* pts, int n
         double smax, smin;
         emia_svd_solve<3>(R, qtb, gfp, &smax, &smin);
     }
-    double t;
-    rp[4] = -0.5 * atan2(gfp[2], gfp[1] - gfp[0]);
-    if (fabs(gfp[2]) > min_eps) t = gfp[2] / sin(-2.0 * rp[4]);
-    else t = gfp[1] - gfp[0];
-    rp[2] = fabs(gfp[0] + gfp[1] - t);
-    if (rp[2] > min_eps) rp[2] = sqrt(2.0 / rp[2]);
-    rp[3] = fabs(gfp[0] + gfp[1] + t);
-    if (rp[3] > min_eps) rp[3] = sqrt(2.0 / rp[3]);
-
-    box.cx = (float)(rp[0] / scale) + cxf;
-    box.cy = (float)(rp[1] / scale) + cyf;
-    box.w = (float)(rp[2] * 2 / scale);
-    box.h = (float)(rp[3] * 2 / scale);
-    if (box.w > box.h) {
-        const float tmp = box.w; box.w = box.h; box.h = tmp;
-        box.angle = (float)(90 + rp[4] * 180 / M_PI);
-    } else {
-        box.angle = (float)(rp[4] * 180 / M_PI);   // only the axes are consumed by the reference
-    }
-    if (box.angle < -180) box.angle += 360;
-    if (box.angle > 360) box.angle -= 360;
-    box.ok = 1;
-    return box;
+    return emia_ellipse_from_conic(gfp, rp, scale, cxf, cyf);
 }
 
 // ---- n == 5: OpenCV's fitEllipse routes the exactly-determined case to fitEllipseDirect (Halir & Flusser, "Numerically stable

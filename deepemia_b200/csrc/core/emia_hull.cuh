@@ -105,22 +105,22 @@ EMIA_HD int emia_sklansky(const K* arr, int start, int end, S* stack, int nsign,
 // The hull is assembled from four monotone chains (tl: leftmost -> topmost, tr: rightmost -> topmost, bl / br likewise for
 // the bottom).  The three helpers below are OpenCV's assembly steps; they are shared by the serial emia_convex_hull and
 // the warp-cooperative hull kernel (which runs the four chains on four lanes, keys and stacks in shared memory).
-template <typename S, typename K>
+template <typename S, typename K, typename H>
 EMIA_HD int emia_hull_emit_upper(const K* keys, int clockwise, S* tl_stack, int tl_count, S* tr_stack, int tr_count,
-                                 int* hull, int* nout_io) {
+                                 H* hull, int* nout_io) {
     int nout = *nout_io;
     if (!clockwise) {
         S* ts = tl_stack; tl_stack = tr_stack; tr_stack = ts;
         int tc = tl_count; tl_count = tr_count; tr_count = tc;
     }
-    for (int i = 0; i < tl_count - 1; ++i) hull[nout++] = emia_ki(keys[tl_stack[i]]);
-    for (int i = tr_count - 1; i > 0; --i) hull[nout++] = emia_ki(keys[tr_stack[i]]);
+    for (int i = 0; i < tl_count - 1; ++i) hull[nout++] = (H)emia_ki(keys[tl_stack[i]]);
+    for (int i = tr_count - 1; i > 0; --i) hull[nout++] = (H)emia_ki(keys[tr_stack[i]]);
     *nout_io = nout;
     return tr_count > 2 ? (int)tr_stack[1] : tl_count > 2 ? (int)tl_stack[tl_count - 2] : -1;   // stop_idx
 }
-template <typename S, typename K>
+template <typename S, typename K, typename H>
 EMIA_HD void emia_hull_emit_lower(const K* keys, int clockwise, S* bl_stack, int bl_count, S* br_stack, int br_count,
-                                  int stop_idx, int* hull, int* nout_io) {
+                                  int stop_idx, H* hull, int* nout_io) {
     int nout = *nout_io;
     if (clockwise) {
         S* ts = bl_stack; bl_stack = br_stack; br_stack = ts;
@@ -135,17 +135,18 @@ EMIA_HD void emia_hull_emit_lower(const K* keys, int clockwise, S* bl_stack, int
             br_count = emia_min(br_count, 2);
         }
     }
-    for (int i = 0; i < bl_count - 1; ++i) hull[nout++] = emia_ki(keys[bl_stack[i]]);
-    for (int i = br_count - 1; i > 0; --i) hull[nout++] = emia_ki(keys[br_stack[i]]);
+    for (int i = 0; i < bl_count - 1; ++i) hull[nout++] = (H)emia_ki(keys[bl_stack[i]]);
+    for (int i = br_count - 1; i > 0; --i) hull[nout++] = (H)emia_ki(keys[br_stack[i]]);
     *nout_io = nout;
 }
-// cyclic shift so that indices ascend/descend when possible
-EMIA_HD void emia_hull_cyclic_shift(int* hull, int nout, int* tmp) {
+// cyclic shift so that indices ascend/descend when possible (H: int, or uint8_t for the packed hull kernel)
+template <typename H>
+EMIA_HD void emia_hull_cyclic_shift(H* hull, int nout, H* tmp) {
     if (nout < 3) return;
     int min_idx = 0, max_idx = 0, lt = 0;
     for (int i = 1; i < nout; ++i) {
         const int idx = hull[i];
-        lt += hull[i - 1] < idx;
+        lt += (int)hull[i - 1] < idx;
         if (lt > 1 && lt <= i - 2) break;
         if (idx < hull[min_idx]) min_idx = i;
         if (idx > hull[max_idx]) max_idx = i;
@@ -206,40 +207,45 @@ EMIA_HD_NOINLINE int emia_convex_hull(const uint32_t* pts, int n, int clockwise,
     return nout;
 }
 
-// ---- rotating calipers, min-area rectangle.  hp = hull points as float2 (x,y interleaved), n >= 3.
-// vect / inv_len: scratch (2n floats, n floats).  out[6] = corner (x,y), vec1 (x,y), vec2 (x,y).
-EMIA_HD_NOINLINE void emia_rotating_calipers(const float* hp, int n, float* vect, float* inv_len, float* out) {
+// ---- rotating calipers, min-area rectangle.  hq = hull points packed (x | y << 16) in hull order, n >= 3.
+// out[6] = corner (x,y), vec1 (x,y), vec2 (x,y).  OpenCV keeps the edge vectors and their inverse lengths in two arrays; here
+// they are recomputed where they are used (the same float32 / float64 operations on the same integer-valued inputs, so the
+// results are bit-identical), which leaves the packed hull points as the only memory the loop touches — they fit in shared
+// memory in the hull kernel and in a 4n-byte scratch region in the serial path.
+struct EmiaHullEdge { float x, y; };
+EMIA_HD EmiaHullEdge emia_hull_edge(const uint32_t* hq, int n, int i) {
+    const int nx = (i + 1 < n) ? i + 1 : 0;
+    EmiaHullEdge e;
+    e.x = (float)(EMIA_PT_X(hq[nx]) - EMIA_PT_X(hq[i]));          // exact: |difference| < 2^16
+    e.y = (float)(EMIA_PT_Y(hq[nx]) - EMIA_PT_Y(hq[i]));
+    return e;
+}
+EMIA_HD_NOINLINE void emia_rotating_calipers(const uint32_t* hq, int n, float* out) {
     float minarea = FLT_MAX;
     int left = 0, bottom = 0, right = 0, top = 0;
     int seq[4] = {-1, -1, -1, -1};
     float orientation = 0.f;
     float base_a, base_b = 0.f;
     float left_x, right_x, top_y, bottom_y;
-    float p0x = hp[0], p0y = hp[1];
-    left_x = right_x = p0x;
-    top_y = bottom_y = p0y;
+    left_x = right_x = (float)EMIA_PT_X(hq[0]);
+    top_y = bottom_y = (float)EMIA_PT_Y(hq[0]);
     // saved best
     int best_left = 0, best_bottom = 0;
     float best_a = 0.f, best_w = 0.f, best_b = 0.f, best_h = 0.f;
 
     for (int i = 0; i < n; ++i) {
+        const float p0x = (float)EMIA_PT_X(hq[i]), p0y = (float)EMIA_PT_Y(hq[i]);
         if (p0x < left_x) { left_x = p0x; left = i; }
         if (p0x > right_x) { right_x = p0x; right = i; }
         if (p0y > top_y) { top_y = p0y; top = i; }
         if (p0y < bottom_y) { bottom_y = p0y; bottom = i; }
-        const int nx = (i + 1 < n) ? i + 1 : 0;
-        const float ptx = hp[2 * nx], pty = hp[2 * nx + 1];
-        const double dx = (double)(ptx - p0x);
-        const double dy = (double)(pty - p0y);
-        vect[2 * i] = (float)dx;
-        vect[2 * i + 1] = (float)dy;
-        inv_len[i] = (float)(1. / sqrt(dx * dx + dy * dy));
-        p0x = ptx; p0y = pty;
     }
     {
-        double ax = vect[2 * (n - 1)], ay = vect[2 * (n - 1) + 1];
+        const EmiaHullEdge last = emia_hull_edge(hq, n, n - 1);
+        double ax = last.x, ay = last.y;
         for (int i = 0; i < n; ++i) {
-            const double bx = vect[2 * i], by = vect[2 * i + 1];
+            const EmiaHullEdge e = emia_hull_edge(hq, n, i);
+            const double bx = e.x, by = e.y;
             const double convexity = ax * by - ay * bx;
             if (convexity != 0) { orientation = (convexity > 0) ? 1.f : -1.f; break; }
             ax = bx; ay = by;
@@ -252,20 +258,25 @@ EMIA_HD_NOINLINE void emia_rotating_calipers(const float* hp, int n, float* vect
         // Choose the calipers side that makes the smallest angle with its polygon edge: rotate the four edge
         // vectors into a common frame and compare them pairwise by the sign of a cross product (exact for
         // integer-valued hull points; no cosine/inverse-length rounding involved).
+        const EmiaHullEdge e0 = emia_hull_edge(hq, n, seq[0]), e1 = emia_hull_edge(hq, n, seq[1]);
+        const EmiaHullEdge e2 = emia_hull_edge(hq, n, seq[2]), e3 = emia_hull_edge(hq, n, seq[3]);
         float rvx[4], rvy[4];
-        rvx[0] = vect[2 * seq[0]];      rvy[0] = vect[2 * seq[0] + 1];
-        rvx[1] = vect[2 * seq[1] + 1];  rvy[1] = -vect[2 * seq[1]];       // rotated 90 deg clockwise
-        rvx[2] = -vect[2 * seq[2]];     rvy[2] = -vect[2 * seq[2] + 1];   // rotated 180 deg
-        rvx[3] = -vect[2 * seq[3] + 1]; rvy[3] = vect[2 * seq[3]];        // rotated 90 deg counter-clockwise
+        rvx[0] = e0.x;   rvy[0] = e0.y;
+        rvx[1] = e1.y;   rvy[1] = -e1.x;      // rotated 90 deg clockwise
+        rvx[2] = -e2.x;  rvy[2] = -e2.y;      // rotated 180 deg
+        rvx[3] = -e3.y;  rvy[3] = e3.x;       // rotated 90 deg counter-clockwise
         int main_element = 0;
+        float mx = rvx[0], my = rvy[0];
         for (int i = 1; i < 4; ++i) {
             const float tx = rvy[i], ty = -rvx[i];
-            if (tx * rvx[main_element] + ty * rvy[main_element] < 0) main_element = i;
+            if (tx * mx + ty * my < 0) { main_element = i; mx = rvx[i]; my = rvy[i]; }
         }
         {
-            const int pindex = seq[main_element];
-            const float lead_x = vect[2 * pindex] * inv_len[pindex];
-            const float lead_y = vect[2 * pindex + 1] * inv_len[pindex];
+            const EmiaHullEdge lead = main_element == 0 ? e0 : main_element == 1 ? e1 : main_element == 2 ? e2 : e3;
+            const double dx = (double)lead.x, dy = (double)lead.y;
+            const float inv_len = (float)(1. / sqrt(dx * dx + dy * dy));
+            const float lead_x = lead.x * inv_len;
+            const float lead_y = lead.y * inv_len;
             switch (main_element) {
                 case 0: base_a = lead_x; base_b = lead_y; break;
                 case 1: base_a = lead_y; base_b = -lead_x; break;
@@ -276,11 +287,11 @@ EMIA_HD_NOINLINE void emia_rotating_calipers(const float* hp, int n, float* vect
         seq[main_element] += 1;
         seq[main_element] = (seq[main_element] == n) ? 0 : seq[main_element];
         {
-            float dx = hp[2 * seq[1]] - hp[2 * seq[3]];
-            float dy = hp[2 * seq[1] + 1] - hp[2 * seq[3] + 1];
+            float dx = (float)EMIA_PT_X(hq[seq[1]]) - (float)EMIA_PT_X(hq[seq[3]]);
+            float dy = (float)EMIA_PT_Y(hq[seq[1]]) - (float)EMIA_PT_Y(hq[seq[3]]);
             const float width = dx * base_a + dy * base_b;
-            dx = hp[2 * seq[2]] - hp[2 * seq[0]];
-            dy = hp[2 * seq[2] + 1] - hp[2 * seq[0] + 1];
+            dx = (float)EMIA_PT_X(hq[seq[2]]) - (float)EMIA_PT_X(hq[seq[0]]);
+            dy = (float)EMIA_PT_Y(hq[seq[2]]) - (float)EMIA_PT_Y(hq[seq[0]]);
             const float height = -dx * base_b + dy * base_a;
             const float area = width * height;
             if (area <= minarea) {
@@ -294,8 +305,8 @@ EMIA_HD_NOINLINE void emia_rotating_calipers(const float* hp, int n, float* vect
     {
         const float A1 = best_a, B1 = best_b;
         const float A2 = -best_b, B2 = best_a;
-        const float C1 = A1 * hp[2 * best_left] + hp[2 * best_left + 1] * B1;
-        const float C2 = A2 * hp[2 * best_bottom] + hp[2 * best_bottom + 1] * B2;
+        const float C1 = A1 * (float)EMIA_PT_X(hq[best_left]) + (float)EMIA_PT_Y(hq[best_left]) * B1;
+        const float C2 = A2 * (float)EMIA_PT_X(hq[best_bottom]) + (float)EMIA_PT_Y(hq[best_bottom]) * B2;
         const float idet = 1.f / (A1 * B2 - A2 * B1);
         const float px = (C1 * B2 - C2 * B1) * idet;
         const float py = (A1 * C2 - A2 * C1) * idet;
@@ -307,36 +318,42 @@ EMIA_HD_NOINLINE void emia_rotating_calipers(const float* hp, int n, float* vect
 
 struct EmiaRotRect { float cx, cy, w, h, angle; };
 
-// cv2.minAreaRect (OpenCV 4.13) on the counter-clockwise hull points (float), n = hull size.
+// cv2.minAreaRect (OpenCV 4.13) from the calipers result out[6] (n > 2) or the first two hull points hq01 (n <= 2).
 // The angle is evaluated in double from the first side vector and normalised into [-90, 0) by quarter turns
 // (each turn swaps width and height) before the single rounding to float32.
-EMIA_HD EmiaRotRect emia_min_area_rect_from_hull(const float* hp, int n, float* vect, float* inv_len) {
+EMIA_HD EmiaRotRect emia_min_area_rect_finish(int n, const float* out, const uint32_t* hq01) {
     EmiaRotRect box; box.cx = box.cy = box.w = box.h = box.angle = 0.f;
     double ang = 0.0;
     if (n > 2) {
-        float out[6];
-        emia_rotating_calipers(hp, n, vect, inv_len, out);
         box.cx = out[0] + (out[2] + out[4]) * 0.5f;
         box.cy = out[1] + (out[3] + out[5]) * 0.5f;
         box.w = (float)sqrt((double)out[2] * out[2] + (double)out[3] * out[3]);
         box.h = (float)sqrt((double)out[4] * out[4] + (double)out[5] * out[5]);
         ang = atan2((double)out[3], (double)out[2]);
     } else if (n == 2) {
-        box.cx = (hp[0] + hp[2]) * 0.5f;
-        box.cy = (hp[1] + hp[3]) * 0.5f;
-        const double dx = hp[2] - hp[0];
-        const double dy = hp[3] - hp[1];
+        const float x0 = (float)EMIA_PT_X(hq01[0]), y0 = (float)EMIA_PT_Y(hq01[0]);
+        const float x1 = (float)EMIA_PT_X(hq01[1]), y1 = (float)EMIA_PT_Y(hq01[1]);
+        box.cx = (x0 + x1) * 0.5f;
+        box.cy = (y0 + y1) * 0.5f;
+        const double dx = x1 - x0;
+        const double dy = y1 - y0;
         box.w = (float)sqrt(dx * dx + dy * dy);
         box.h = 0;
         ang = atan2(dy, dx);
     } else if (n == 1) {
-        box.cx = hp[0]; box.cy = hp[1];
+        box.cx = (float)EMIA_PT_X(hq01[0]); box.cy = (float)EMIA_PT_Y(hq01[0]);
     }
     ang = ang * 180 / M_PI;
     while (ang >= 0.0) { ang -= 90.0; const float t = box.w; box.w = box.h; box.h = t; }
     while (ang < -90.0) { ang += 90.0; const float t = box.w; box.w = box.h; box.h = t; }
     box.angle = (float)ang;
     return box;
+}
+// ... on the counter-clockwise hull points hq (packed), n = hull size.
+EMIA_HD EmiaRotRect emia_min_area_rect_from_hull(const uint32_t* hq, int n) {
+    float out[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (n > 2) emia_rotating_calipers(hq, n, out);
+    return emia_min_area_rect_finish(n, out, hq);
 }
 
 // cv2.boxPoints: 4 corners as float32 (x,y interleaved)

@@ -39,6 +39,11 @@ enum EmiaRecField {
 
 // bytes of scratch needed for a contour of n vertices
 EMIA_HD size_t emia_measure_scratch_bytes(int n) { return (size_t)28 * (size_t)n + 64; }
+// An instance's scratch block holds one 16-byte aligned sub-block per contour, in discovery order (so that the hulls of all
+// its contours can be prepared before the morphometry runs): stride of a contour of n vertices, and an upper bound of the
+// block for nc contours with n_pts vertices in total.
+EMIA_HD size_t emia_measure_sub_bytes(int n) { return (emia_measure_scratch_bytes(n) + 15) & ~(size_t)15; }
+EMIA_HD size_t emia_measure_item_scratch_bytes(int n_pts, int nc) { return nc ? (((size_t)28 * (size_t)n_pts + (size_t)80 * (size_t)nc + 15) & ~(size_t)15) : 0; }
 
 EMIA_HD float emia_dist2f(float ax, float ay, float bx, float by) {
     const float dx = ax - bx, dy = ay - by;
@@ -75,27 +80,50 @@ EMIA_HD void emia_order_points(const float* p /*8*/, float* o /*8: tl,tr,br,bl*/
     o[6] = p[2 * bl]; o[7] = p[2 * bl + 1];
 }
 
+// The three ellipse columns of a record from the fitted (width <= height) axes; zeros for contours of fewer than 5 vertices
+// (src/utils/measurements.py:176-193, Q3).
+EMIA_HD void emia_ellipse_columns(const EmiaEllipse& e, int n, double um_pix, double* rec) {
+    double major_len = 0.0, minor_len = 0.0, ecc = 0.0;
+    if (n >= 5) {
+        const double major_axis = (double)e.w, minor_axis = (double)e.h;
+        double a, b;
+        if (major_axis > minor_axis) { a = major_axis / 2.0; b = minor_axis / 2.0; }
+        else { a = minor_axis / 2.0; b = major_axis / 2.0; }
+        ecc = (a != 0.0) ? sqrt(1 - ((b * b) / (a * a))) : 0.0;
+        major_len = major_axis * um_pix;
+        minor_len = minor_axis * um_pix;
+    }
+    rec[EMIA_F_MAJOR_AXIS] = major_len;
+    rec[EMIA_F_MINOR_AXIS] = minor_len;
+    rec[EMIA_F_ECCENTRICITY] = ecc;
+}
+
+// Where the hull kernel leaves its result inside a contour's scratch sub-block (behind the carve-up below, in the 56 spare
+// bytes): int nh, then either the calipers result out[6] (nh > 2) or the first two hull points (packed, nh <= 2).
+EMIA_HD size_t emia_measure_rect_off(int n) { return (size_t)28 * (size_t)n + 8; }
+
 // Fill rec[16] for one contour.  scratch: emia_measure_scratch_bytes(n), 8-byte aligned.
-// prepared: 0 = nothing, 1 = scratch starts with the n sorted hull keys, 2 = the hull is ready (indices in the `hull`
-// region of the scratch, its size in stack[0]) — both written by the warp-cooperative hull kernel beforehand.
+// prepared: 0 = nothing, 1 = scratch starts with the n sorted hull keys, 3 = hull and rotating calipers are done (result at
+// emia_measure_rect_off, written by the warp-cooperative hull kernel beforehand).
 EMIA_HD_NOINLINE void emia_measure_contour(const uint32_t* pts, int n, double um_pix, void* scratch, double* rec, int prepared = 0) {
     const double area = emia_contour_area(pts, n);
     const double perimeter = emia_arc_length_closed(pts, n);
 
-    // ---- scratch carve-up (regions are reused once dead)
-    uint64_t* keys = (uint64_t*)scratch;               // 8n   (later: vect, 2n floats)
-    float* hp = (float*)(keys + n);                    // 8n   hull points
-    int* stack = (int*)(hp + 2 * n);                   // 4(n+2) (later: inv_len)
-    int* hull = stack + (n + 2);                       // 4n
-    int* tmp = hull + n;                               // 4n
-    const int nh = (prepared == 2) ? stack[0] : emia_convex_hull(pts, n, /*clockwise=*/0, keys, stack, hull, tmp, prepared);
-    for (int i = 0; i < nh; ++i) {
-        hp[2 * i] = (float)EMIA_PT_X(pts[hull[i]]);
-        hp[2 * i + 1] = (float)EMIA_PT_Y(pts[hull[i]]);
+    EmiaRotRect rr;
+    if (prepared == 3) {
+        const int* r = (const int*)((const uint8_t*)scratch + emia_measure_rect_off(n));
+        rr = emia_min_area_rect_finish(r[0], (const float*)(r + 1), (const uint32_t*)(r + 1));
+    } else {
+        // ---- scratch carve-up (regions are reused once dead)
+        uint64_t* keys = (uint64_t*)scratch;               // 8n   (later: hull points, packed)
+        int* stack = (int*)(keys + 2 * n);                 // 4(n+2), behind 8n unused bytes (layout shared with the hull kernel)
+        int* hull = stack + (n + 2);                       // 4n
+        int* tmp = hull + n;                               // 4n
+        const int nh = emia_convex_hull(pts, n, /*clockwise=*/0, keys, stack, hull, tmp, prepared);
+        uint32_t* hq = (uint32_t*)keys;
+        for (int i = 0; i < nh; ++i) hq[i] = pts[hull[i]];
+        rr = emia_min_area_rect_from_hull(hq, nh);
     }
-    float* vect = (float*)keys;
-    float* inv_len = (float*)stack;
-    const EmiaRotRect rr = emia_min_area_rect_from_hull(hp, nh, vect, inv_len);
     float bp[8];
     emia_box_points(rr, bp);
     for (int i = 0; i < 8; ++i) bp[i] = (float)(long long)bp[i];   // np.array(box, dtype="int"): truncation
@@ -124,20 +152,9 @@ EMIA_HD_NOINLINE void emia_measure_contour(const uint32_t* pts, int n, double um
     rec[EMIA_F_SPHERICITY] = (perimeter != 0.0) ? (2 * sqrt(M_PI * area)) / perimeter * um_pix : 0.0;
     rec[EMIA_F_CIRCULARITY] = (perimeter != 0.0) ? (4 * M_PI) * (area / (perimeter * perimeter)) * um_pix : 0.0;
 
-    double major_len = 0.0, minor_len = 0.0, ecc = 0.0;
-    if (n >= 5) {
-        const EmiaEllipse e = emia_fit_ellipse(pts, n);
-        const double major_axis = (double)e.w, minor_axis = (double)e.h;
-        double a, b;
-        if (major_axis > minor_axis) { a = major_axis / 2.0; b = minor_axis / 2.0; }
-        else { a = minor_axis / 2.0; b = major_axis / 2.0; }
-        ecc = (a != 0.0) ? sqrt(1 - ((b * b) / (a * a))) : 0.0;
-        major_len = major_axis * um_pix;
-        minor_len = minor_axis * um_pix;
-    }
-    rec[EMIA_F_MAJOR_AXIS] = major_len;
-    rec[EMIA_F_MINOR_AXIS] = minor_len;
-    rec[EMIA_F_ECCENTRICITY] = ecc;
+    EmiaEllipse e; e.w = e.h = 0.f;
+    if (n >= 5) e = emia_fit_ellipse(pts, n);
+    emia_ellipse_columns(e, n, um_pix, rec);
     rec[EMIA_F_AREA] = area;
     rec[EMIA_F_PERIMETER] = perimeter;
     rec[EMIA_F_NVERT] = (double)n;

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(EMIA_TRACE_THREADS) k_contour_trace(
     if (!kStore) {
         n_contours[i] = o.n_contours;
         n_points[i] = o.n_pts;
-        scratch_bytes[i] = o.n_contours ? (int64_t)((emia_measure_scratch_bytes(o.max_len) + 15) & ~(size_t)15) : 0;
+        scratch_bytes[i] = (int64_t)emia_measure_item_scratch_bytes(o.n_pts, o.n_contours);
     } else if (perim0) {
         // arcLength of contours[0] in OpenCV order = the LAST discovered contour (deduplicate_masks_smart's compactness, Q10)
         const int nc = o.n_contours;
@@ -88,30 +88,84 @@ __global__ void __launch_bounds__(EMIA_TRACE_THREADS) k_contour_trace(
 // The hull (Sklansky on the vertices sorted by (x, y, index)) was 75 % of the per-thread morphometry kernel: a chain of
 // dependent, uncoalesced global loads (ncu source view, profiles/).  For the common case (one contour, <= EMIA_PRESORT_MAX
 // vertices) a warp now sorts the keys with a bitonic network in shared memory, runs the four monotone chains on four
-// lanes (keys and stacks in shared memory), lane 0 assembles the hull exactly as the serial code does, and the hull
-// indices + size are written where emia_measure_contour(prepared = 2) expects them in the item's scratch block.
+// lanes (keys and stacks in shared memory), one lane assembles the hull exactly as the serial code does, gathers the hull
+// points into shared memory and runs the rotating calipers there; the calipers result (6 floats) is written where
+// emia_measure_contour(prepared = 3) expects it in the item's scratch block.
 // Work items: item `it` measures instance item_inst[it] (identity when item_inst == nullptr; < 0 = nothing to do); its records
 // start at rec_off[it] (rec_off[it+1] - rec_off[it] = number of contours) and its scratch at scratch_off[it].
 // inst_cont_off (per INSTANCE) locates the packed cstart layout and is only read when cstart_stride == 0.
 #define EMIA_PRESORT_MAX 256
 #define EMIA_PRESORT_WARPS 4
+// Packed path: the serial phases (four Sklansky chains, hull assembly) used 4 and 1 lanes of the warp and were 60 % of the
+// kernel's issue slots.  A warp therefore takes EMIA_HULL_PACK work items: it pre-filters and sorts them one after the other
+// (all lanes), parks each sorted key list (<= EMIA_HULL_FAST_MAX survivors, 32-bit compact keys) in a small shared-memory slot,
+// and then runs the chains of ALL its items at once (lane = item * 4 + chain) and the assembly on one lane per item.
+// Items with more survivors or a larger extent take the one-item-per-warp path afterwards (its buffers alias the slots).
+#define EMIA_HULL_PACK 8
+#define EMIA_HULL_FAST_MAX 64
 struct EmiaHullSmem {
     uint64_t keys[EMIA_PRESORT_MAX];
     uint16_t stacks[4][EMIA_PRESORT_MAX + 4];
     int hull[EMIA_PRESORT_MAX];
     int tmp[EMIA_PRESORT_MAX];
 };
+struct EmiaHullSlot {
+    uint32_t keys[EMIA_HULL_FAST_MAX];
+    uint8_t stacks[4][EMIA_HULL_FAST_MAX + 4];
+    uint8_t hull[EMIA_HULL_FAST_MAX + 8];
+    uint8_t tmp[EMIA_HULL_FAST_MAX + 8];
+    int cnt[4];
+    int m, miny, maxy, len;
+    long long scratch_off;
+    const uint32_t* p;                                        // the contour's vertices
+};
+union EmiaHullWarpSmem {
+    EmiaHullSmem one;                                         // one-item path
+    struct {
+        uint64_t staging[EMIA_PRESORT_MAX];                   // same bytes as one.keys: pre-filter / sort area of the current item
+        EmiaHullSlot slot[EMIA_HULL_PACK];
+    } packed;
+};
 __device__ __forceinline__ uint64_t emia_make_key(uint64_t, int x, int y, int ox, int oy, int t) { (void)ox; (void)oy; return EMIA_KEY(x, y, t); }
 __device__ __forceinline__ uint32_t emia_make_key(uint32_t, int x, int y, int ox, int oy, int t) { return EMIA_KEY32(x - ox, y - oy, t); }
 
-// The warp's work on one contour, templated on the key type (uint32_t: extent < 4096 x 4096, coordinates relative to (ox, oy)).
-template <typename K>
-__device__ __forceinline__ void emia_hull_warp(K* k, EmiaHullSmem& S, const uint32_t* __restrict__ p, int len, int lane, int ox, int oy,
-                                               const long long* qx, const long long* qy, int* g_stack, int* g_hull) {
-    // Akl-Toussaint pre-filter: vertices strictly inside the quadrilateral of the four extreme vertices (left, top, right,
-    // bottom) cannot be hull vertices; dropping them (typically 50-70 % of a blob's contour) shrinks the sort and the chains.
-    // Extremes and all vertices ON the quadrilateral survive, so the sorted order of the survivors, the first min-/max-y
-    // entries and the chains' results are those of the full set; keys keep the ORIGINAL vertex index.
+// The four extreme vertices of a contour (left, top, right, bottom; first in (x, y) resp. (y, x) order), warp-cooperative.
+struct EmiaHullQuad { int qx[4], qy[4]; int ox, oy; bool compact; };
+__device__ __forceinline__ EmiaHullQuad emia_hull_extremes(const uint32_t* __restrict__ p, int len, int lane) {
+    // (x << 16 | y) for left / right, (y << 16 | x) for top / bottom
+    uint32_t lx = 0xFFFFFFFFu, rx = 0u, ty = 0xFFFFFFFFu, by = 0u;
+    for (int t = lane; t < len; t += 32) {
+        const uint32_t q = p[t];
+        const uint32_t xy = ((uint32_t)EMIA_PT_X(q) << 16) | (uint32_t)EMIA_PT_Y(q), yx = ((uint32_t)EMIA_PT_Y(q) << 16) | (uint32_t)EMIA_PT_X(q);
+        lx = min(lx, xy); rx = max(rx, xy); ty = min(ty, yx); by = max(by, yx);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lx = min(lx, __shfl_xor_sync(0xffffffffu, lx, o)); rx = max(rx, __shfl_xor_sync(0xffffffffu, rx, o));
+        ty = min(ty, __shfl_xor_sync(0xffffffffu, ty, o)); by = max(by, __shfl_xor_sync(0xffffffffu, by, o));
+    }
+    EmiaHullQuad Q;
+    Q.qx[0] = (int)(lx >> 16); Q.qx[1] = (int)(ty & 0xFFFF); Q.qx[2] = (int)(rx >> 16); Q.qx[3] = (int)(by & 0xFFFF);
+    Q.qy[0] = (int)(lx & 0xFFFF); Q.qy[1] = (int)(ty >> 16); Q.qy[2] = (int)(rx & 0xFFFF); Q.qy[3] = (int)(by >> 16);
+    Q.ox = (int)(lx >> 16); Q.oy = (int)(ty >> 16);
+    Q.compact = ((int)(rx >> 16) - Q.ox) < 4096 && ((int)(by >> 16) - Q.oy) < 4096;             // len <= 256 holds for the callers
+    return Q;
+}
+
+// Akl-Toussaint pre-filter: vertices strictly inside the quadrilateral of the four extreme vertices (left, top, right,
+// bottom) cannot be hull vertices; dropping them (typically 50-70 % of a blob's contour) shrinks the sort and the chains.
+// Extremes and all vertices ON the quadrilateral survive, so the sorted order of the survivors, the first min-/max-y
+// entries and the chains' results are those of the full set; keys keep the ORIGINAL vertex index.  Returns the survivor count.
+// I: arithmetic type of the cross products (int when the extent is below 4096 x 4096: |products| < 2^24; else long long).
+template <typename K, typename I>
+__device__ __forceinline__ int emia_hull_prefilter(K* k, const uint32_t* __restrict__ p, int len, int lane, const EmiaHullQuad& Q) {
+    I ex[4], ey[4];
+    int edges = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int f = (e + 1) & 3;
+        ex[e] = (I)(Q.qx[f] - Q.qx[e]); ey[e] = (I)(Q.qy[f] - Q.qy[e]);
+        edges += (ex[e] != 0 || ey[e] != 0);                            // coinciding extremes: the quadrilateral is a triangle
+    }
     int run = 0;
     for (int t0 = 0; t0 < len; t0 += 32) {
         const int t = t0 + lane;
@@ -119,24 +173,54 @@ __device__ __forceinline__ void emia_hull_warp(K* k, EmiaHullSmem& S, const uint
         K key = (K)~(K)0;
         if (t < len) {
             const uint32_t q = p[t];
-            const long long x = EMIA_PT_X(q), y = EMIA_PT_Y(q);
-            int pos = 0, neg = 0, edges = 0;
+            const int x = EMIA_PT_X(q), y = EMIA_PT_Y(q);
+            int pos = 0, neg = 0;
+#pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int f = (e + 1) & 3;
-                const long long ex = qx[f] - qx[e], ey = qy[f] - qy[e];
-                if (ex == 0 && ey == 0) continue;                       // coinciding extremes: the quadrilateral is a triangle
-                const long long cr = ex * (y - qy[e]) - ey * (x - qx[e]);
-                ++edges; pos += cr > 0; neg += cr < 0;
+                const I cr = ex[e] * (I)(y - Q.qy[e]) - ey[e] * (I)(x - Q.qx[e]);       // 0 for a degenerate edge
+                pos += cr > 0; neg += cr < 0;
             }
             const bool inside = edges >= 3 && (pos == edges || neg == edges);
             keep = !inside;
-            key = emia_make_key((K)0, (int)x, (int)y, ox, oy, t);
+            key = emia_make_key((K)0, x, y, Q.ox, Q.oy, t);
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         if (keep) k[run + __popc(bal & ((1u << lane) - 1u))] = key;
         run += __popc(bal);
     }
-    const int m = run;
+    return run;
+}
+
+// Bitonic sort of up to 64 keys held two per lane (k0: element `lane`, k1: element `lane + 32`; unused elements all-ones) with
+// shuffles — no shared memory, no barriers.  two = false: only k0 is sorted (<= 32 keys).
+__device__ __forceinline__ void emia_hull_sort_regs(uint32_t& k0, uint32_t& k1, int lane, bool two) {
+#pragma unroll
+    for (int size = 2; size <= 64; size <<= 1) {
+        if (size == 64 && !two) break;
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride == 32) {                     // partner in the same lane; size == 64: ascending everywhere
+                const uint32_t lo = min(k0, k1), hi = max(k0, k1);
+                k0 = lo; k1 = hi;
+            } else {
+                const bool lower = (lane & stride) == 0;
+                const bool up0 = size == 64 ? true : (lane & size) == 0;                 // element lane
+                const bool up1 = size == 64 ? true : size == 32 ? false : (lane & size) == 0;     // element lane + 32
+                const uint32_t o0 = __shfl_xor_sync(0xffffffffu, k0, stride);
+                k0 = (lower == up0) ? min(k0, o0) : max(k0, o0);
+                if (two) {
+                    const uint32_t o1 = __shfl_xor_sync(0xffffffffu, k1, stride);
+                    k1 = (lower == up1) ? min(k1, o1) : max(k1, o1);
+                }
+            }
+        }
+    }
+}
+
+// Bitonic sort of k[0..m) (padded with all-ones keys to a power of two >= 32) by one warp, then the first index of the
+// minimum / maximum y in sorted order (the serial scan keeps the first occurrence).
+template <typename K>
+__device__ __forceinline__ void emia_hull_sort(K* k, int m, int lane, int* miny_ind, int* maxy_ind) {
     int N = 32;
     while (N < m) N <<= 1;
     for (int t = m + lane; t < N; t += 32) k[t] = (K)~(K)0;
@@ -153,7 +237,6 @@ __device__ __forceinline__ void emia_hull_warp(K* k, EmiaHullSmem& S, const uint
             __syncwarp();
         }
     }
-    // first index of the minimum / maximum y in sorted order (the serial scan keeps the first occurrence)
     int mn = 0x7fffffff, mx = 0x7fffffff;
     for (int t = lane; t < m; t += 32) {
         const int y = emia_ky(k[t]);
@@ -164,7 +247,17 @@ __device__ __forceinline__ void emia_hull_warp(K* k, EmiaHullSmem& S, const uint
         mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
         mx = min(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
-    const int miny_ind = mn & 511, maxy_ind = mx & 511;
+    *miny_ind = mn & 511; *maxy_ind = mx & 511;
+}
+
+// One item per warp (any extent, up to EMIA_PRESORT_MAX vertices), templated on the key type (uint32_t: extent < 4096 x 4096,
+// coordinates relative to (ox, oy)): chains on four lanes, assembly on lane 0.
+template <typename K>
+__device__ __forceinline__ void emia_hull_warp(K* k, EmiaHullSmem& S, const uint32_t* __restrict__ p, int len, int lane,
+                                               const EmiaHullQuad& Q, int* r) {
+    const int m = Q.compact ? emia_hull_prefilter<K, int>(k, p, len, lane, Q) : emia_hull_prefilter<K, long long>(k, p, len, lane, Q);
+    int miny_ind, maxy_ind;
+    emia_hull_sort<K>(k, m, lane, &miny_ind, &maxy_ind);
     int nout = 0;
     const bool degenerate = (emia_kx(k[0]) == emia_kx(k[m - 1]) && emia_ky(k[0]) == emia_ky(k[m - 1]));
     if (degenerate) {
@@ -190,8 +283,39 @@ __device__ __forceinline__ void emia_hull_warp(K* k, EmiaHullSmem& S, const uint
         nout = __shfl_sync(0xffffffffu, nout, 0);
     }
     __syncwarp();
-    for (int t = lane; t < nout; t += 32) g_hull[t] = S.hull[t];
-    if (lane == 0) g_stack[0] = nout;
+    // hull points (packed) over the shift buffer, which is dead; calipers on lane 0; result where
+    // emia_measure_contour(prepared = 3) expects it
+    uint32_t* hq = (uint32_t*)S.tmp;
+    for (int t = lane; t < nout; t += 32) hq[t] = p[S.hull[t]];
+    __syncwarp();
+    if (lane == 0) {
+        r[0] = nout;
+        if (nout > 2) {
+            float out[6];
+            emia_rotating_calipers(hq, nout, out);
+#pragma unroll
+            for (int t = 0; t < 6; ++t) ((float*)(r + 1))[t] = out[t];
+        } else {
+            r[1] = (int)hq[0];
+            if (nout > 1) r[2] = (int)hq[1];
+        }
+    }
+    __syncwarp();
+}
+
+// Locates work item `it`: number of contours (0 = nothing to do), the instance's cstart entries and vertex list.
+__device__ __forceinline__ int emia_hull_item(int64_t it, int64_t n, const int32_t* __restrict__ item_inst, const int64_t* __restrict__ rec_off,
+                                              const int64_t* __restrict__ inst_cont_off, const int64_t* __restrict__ pt_off,
+                                              const int32_t* __restrict__ cstart, int cstart_stride, const uint32_t* __restrict__ pts,
+                                              const int32_t** cs_out, const uint32_t** p) {
+    if (it >= n) return 0;
+    const int nc = (int)(rec_off[it + 1] - rec_off[it]);
+    if (nc < 1) return 0;
+    const int64_t i = item_inst ? (int64_t)item_inst[it] : it;
+    if (i < 0) return 0;
+    *cs_out = cstart_stride > 0 ? cstart + (size_t)i * cstart_stride : cstart + inst_cont_off[i] + i;
+    *p = pts + pt_off[i];
+    return nc;
 }
 
 __global__ void __launch_bounds__(EMIA_PRESORT_WARPS * 32) k_contour_hull(int64_t n, const int32_t* __restrict__ item_inst,
@@ -203,43 +327,127 @@ __global__ void __launch_bounds__(EMIA_PRESORT_WARPS * 32) k_contour_hull(int64_
                                                                          const uint32_t* __restrict__ pts, uint8_t* __restrict__ scratch,
                                                                          const int32_t* __restrict__ abort_flag) {
     if (abort_flag && *abort_flag) return;
-    __shared__ EmiaHullSmem s_all[EMIA_PRESORT_WARPS];
+    __shared__ EmiaHullWarpSmem s_all[EMIA_PRESORT_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t it = (int64_t)blockIdx.x * EMIA_PRESORT_WARPS + warp;
-    if (it >= n) return;
-    if (rec_off[it + 1] - rec_off[it] != 1) return;
-    const int64_t i = item_inst ? (int64_t)item_inst[it] : it;
-    if (i < 0) return;
-    const int32_t* cs = cstart_stride > 0 ? cstart + (size_t)i * cstart_stride : cstart + inst_cont_off[i] + i;
-    const int len = cs[1] - cs[0];
-    if (len > EMIA_PRESORT_MAX || len < 1) return;
-    EmiaHullSmem& S = s_all[warp];
-    // scratch carve-up of emia_measure_contour: keys 8n | hp 8n | stack 4(n+2) | hull 4n | tmp 4n
-    uint8_t* sc = scratch + scratch_off[it];
-    int* g_stack = (int*)(sc + (size_t)16 * len);
-    int* g_hull = g_stack + (len + 2);
-    const uint32_t* p = pts + pt_off[i] + cs[0];
-    // the four extreme vertices: (x << 16 | y) for left / right, (y << 16 | x) for top / bottom
-    uint32_t lx = 0xFFFFFFFFu, rx = 0u, ty = 0xFFFFFFFFu, by = 0u;
-    for (int t = lane; t < len; t += 32) {
-        const uint32_t q = p[t];
-        const uint32_t xy = ((uint32_t)EMIA_PT_X(q) << 16) | (uint32_t)EMIA_PT_Y(q), yx = ((uint32_t)EMIA_PT_Y(q) << 16) | (uint32_t)EMIA_PT_X(q);
-        lx = min(lx, xy); rx = max(rx, xy); ty = min(ty, yx); by = max(by, yx);
+    const int64_t it0 = ((int64_t)blockIdx.x * EMIA_PRESORT_WARPS + warp) * EMIA_HULL_PACK;
+    if (it0 >= n) return;
+    EmiaHullWarpSmem& W = s_all[warp];
+    uint32_t* stage = (uint32_t*)W.packed.staging;
+    unsigned fast = 0u, slow = 0u;                    // warp-uniform item masks
+    // phase 1: pre-filter + sort, one item after the other, all lanes
+    for (int j = 0; j < EMIA_HULL_PACK; ++j) {
+        const uint32_t* p; const int32_t* cs;
+        const int nc = emia_hull_item(it0 + j, n, item_inst, rec_off, inst_cont_off, pt_off, cstart, cstart_stride, pts, &cs, &p);
+        if (nc == 0) continue;
+        const int len = cs[1] - cs[0];
+        if (nc > 1) { slow |= 1u << j; continue; }                 // several contours: one after the other in phase 5
+        if (len > EMIA_PRESORT_MAX || len < 1) continue;           // k_contour_measure runs the serial hull itself
+        p += cs[0];
+        const EmiaHullQuad Q = emia_hull_extremes(p, len, lane);
+        if (!Q.compact) { slow |= 1u << j; continue; }
+        const int m = emia_hull_prefilter<uint32_t, int>(stage, p, len, lane, Q);
+        __syncwarp();
+        if (m > EMIA_HULL_FAST_MAX) { slow |= 1u << j; continue; }
+        // sort in registers, then the first index of the minimum / maximum y in sorted order
+        uint32_t k0 = lane < m ? stage[lane] : 0xFFFFFFFFu, k1 = lane + 32 < m ? stage[lane + 32] : 0xFFFFFFFFu;
+        __syncwarp();                                  // the next item's pre-filter overwrites the staging area
+        emia_hull_sort_regs(k0, k1, lane, m > 32);
+        int mn = 0x7fffffff, mx = 0x7fffffff;
+        if (lane < m) { const int y = emia_ky(k0); mn = (y << 9) | lane; mx = ((0xFFFFF - y) << 9) | lane; }
+        if (lane + 32 < m) { const int y = emia_ky(k1); mn = min(mn, (y << 9) | (lane + 32)); mx = min(mx, ((0xFFFFF - y) << 9) | (lane + 32)); }
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = min(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        EmiaHullSlot& S = W.packed.slot[j];
+        S.keys[lane] = k0;
+        if (m > 32) S.keys[lane + 32] = k1;
+        if (lane == 0) { S.m = m; S.miny = mn & 511; S.maxy = mx & 511; S.len = len; S.scratch_off = (long long)scratch_off[it0 + j]; S.p = p; }
+        fast |= 1u << j;
+        __syncwarp();
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        lx = min(lx, __shfl_xor_sync(0xffffffffu, lx, o)); rx = max(rx, __shfl_xor_sync(0xffffffffu, rx, o));
-        ty = min(ty, __shfl_xor_sync(0xffffffffu, ty, o)); by = max(by, __shfl_xor_sync(0xffffffffu, by, o));
+    // phase 2: the four chains of every parked item at once (lane = item * 4 + chain)
+    {
+        const int j = lane >> 2, c = lane & 3;
+        EmiaHullSlot& S = W.packed.slot[j];
+        const bool mine = (fast >> j) & 1u;
+        bool degenerate = false;
+        if (mine) {
+            const int m = S.m;
+            degenerate = (emia_kx(S.keys[0]) == emia_kx(S.keys[m - 1]) && emia_ky(S.keys[0]) == emia_ky(S.keys[m - 1]));
+            if (!degenerate) {
+                const int start = (c & 1) ? m - 1 : 0;
+                const int end = (c < 2) ? S.maxy : S.miny;
+                const int nsign = (c < 2) ? -1 : 1;
+                const int sign2 = (c == 0 || c == 3) ? 1 : -1;
+                S.cnt[c] = emia_sklansky(S.keys, start, end, S.stacks[c], nsign, sign2);
+            }
+        }
+        __syncwarp();
+        // phase 3: assembly, one lane per item
+        int nout = 0;
+        if (mine && c == 0) {
+            if (degenerate) { S.hull[0] = 0; nout = 1; }
+            else {
+                const int stop_idx = emia_hull_emit_upper(S.keys, 0, S.stacks[0], S.cnt[0], S.stacks[1], S.cnt[1], S.hull, &nout);
+                emia_hull_emit_lower(S.keys, 0, S.stacks[2], S.cnt[2], S.stacks[3], S.cnt[3], stop_idx, S.hull, &nout);
+                emia_hull_cyclic_shift(S.hull, nout, S.tmp);
+            }
+        }
+        nout = __shfl_sync(0xffffffffu, nout, lane & ~3);
+        __syncwarp();
+        // phase 4: the hull points (original vertices, packed) into shared memory — over the chain stacks, which are dead — and
+        // the rotating calipers on them, one lane per item; the result goes to the item's scratch block where
+        // emia_measure_contour(prepared = 3) expects it (emia_measure_rect_off)
+        uint32_t* hq = (uint32_t*)&S.stacks[0][0];
+        if (mine) for (int t = c; t < nout; t += 4) hq[t] = S.p[S.hull[t]];
+        __syncwarp();
+        if (mine && c == 0) {
+            int* r = (int*)(scratch + S.scratch_off + emia_measure_rect_off(S.len));
+            r[0] = nout;
+            if (nout > 2) {
+                float out[6];
+                emia_rotating_calipers(hq, nout, out);
+#pragma unroll
+                for (int t = 0; t < 6; ++t) ((float*)(r + 1))[t] = out[t];
+            } else {
+                r[1] = (int)hq[0];
+                if (nout > 1) r[2] = (int)hq[1];
+            }
+        }
+        __syncwarp();
     }
-    const long long qx[4] = {(long long)(lx >> 16), (long long)(ty & 0xFFFF), (long long)(rx >> 16), (long long)(by & 0xFFFF)};
-    const long long qy[4] = {(long long)(lx & 0xFFFF), (long long)(ty >> 16), (long long)(rx & 0xFFFF), (long long)(by >> 16)};
-    const int ox = (int)(lx >> 16), oy = (int)(ty >> 16);
-    const bool compact = ((int)(rx >> 16) - ox) < 4096 && ((int)(by >> 16) - oy) < 4096;        // len <= 256 holds here
-    if (compact) emia_hull_warp<uint32_t>((uint32_t*)S.keys, S, p, len, lane, ox, oy, qx, qy, g_stack, g_hull);
-    else emia_hull_warp<uint64_t>(S.keys, S, p, len, lane, ox, oy, qx, qy, g_stack, g_hull);
+    // phase 5: the rare large or multi-contour items, one contour at a time (the buffers alias the slots, which are dead now);
+    // contour k of an item owns the k-th sub-block of the item's scratch (emia_measure_sub_bytes)
+    for (int j = 0; j < EMIA_HULL_PACK; ++j) {
+        if (!((slow >> j) & 1u)) continue;
+        const uint32_t* p0; const int32_t* cs;
+        const int nc = emia_hull_item(it0 + j, n, item_inst, rec_off, inst_cont_off, pt_off, cstart, cstart_stride, pts, &cs, &p0);
+        uint8_t* sc = scratch + scratch_off[it0 + j];
+        for (int k = 0; k < nc; ++k) {
+            const int len = cs[k + 1] - cs[k];
+            if (len >= 1 && len <= EMIA_PRESORT_MAX) {
+                const uint32_t* p = p0 + cs[k];
+                const EmiaHullQuad Q = emia_hull_extremes(p, len, lane);
+                int* r = (int*)(sc + emia_measure_rect_off(len));
+                if (Q.compact) emia_hull_warp<uint32_t>((uint32_t*)W.one.keys, W.one, p, len, lane, Q, r);
+                else emia_hull_warp<uint64_t>(W.one.keys, W.one, p, len, lane, Q, r);
+            }
+            sc += emia_measure_sub_bytes(len);
+        }
+    }
 }
+#define EMIA_HULL_GRID(n) ((unsigned)(((n) + EMIA_PRESORT_WARPS * EMIA_HULL_PACK - 1) / (EMIA_PRESORT_WARPS * EMIA_HULL_PACK)))
 
 // ---- morphometry: one THREAD per instance over the stored vertex lists ---------------------------------------------
-__global__ void __launch_bounds__(128, 4) k_contour_measure(int64_t n, const int32_t* __restrict__ item_inst,
+#ifndef EMIA_MEASURE_THREADS
+#define EMIA_MEASURE_THREADS 128
+#endif
+#ifndef EMIA_MEASURE_MIN_CTAS
+#define EMIA_MEASURE_MIN_CTAS 4
+#endif
+#define EMIA_MEASURE_GRID(n) ((unsigned)(((n) + EMIA_MEASURE_THREADS - 1) / EMIA_MEASURE_THREADS))
+__global__ void __launch_bounds__(EMIA_MEASURE_THREADS, EMIA_MEASURE_MIN_CTAS) k_contour_measure(int64_t n, const int32_t* __restrict__ item_inst,
                                                          const int64_t* __restrict__ rec_off, const int64_t* __restrict__ inst_cont_off,
                                                          const int64_t* __restrict__ pt_off,
                                                          const int64_t* __restrict__ scratch_off, double um_pix, double min_area,
@@ -257,14 +465,27 @@ __global__ void __launch_bounds__(128, 4) k_contour_measure(int64_t n, const int
     if (nc == 0) { if (perim0) perim0[i] = 0.0; return; }
     const int32_t* cs = cstart_stride > 0 ? cstart + (size_t)i * cstart_stride : cstart + inst_cont_off[i] + i;
     const uint32_t* p = pts + pt_off[i];
-    void* sc = scratch + scratch_off[it];
+    uint8_t* sc0 = scratch + scratch_off[it];
+    size_t sub_end = 0;                                // sub-blocks are laid out in discovery order, measured in reverse
+    for (int k = 0; k < nc; ++k) sub_end += emia_measure_sub_bytes(cs[k + 1] - cs[k]);
     for (int j = 0; j < nc; ++j) {
         const int k = nc - 1 - j;                     // OpenCV returns contours in reverse discovery order
         const uint32_t* cp = p + cs[k];
         const int len = cs[k + 1] - cs[k];
+        sub_end -= emia_measure_sub_bytes(len);
         double* rec = records + (size_t)(c0 + j) * EMIA_REC_FIELDS;
-        emia_measure_contour(cp, len, um_pix, sc, rec, (nc == 1 && len <= presort_max) ? 2 : 0);
-        rec[EMIA_REC_MEASURED] = (rec[EMIA_REC_AREA] >= min_area) ? 1.0 : 0.0;
+        // the reference skips a contour below the area gate BEFORE measuring it (src/functions/inference.py:1176-1190): such a
+        // record carries area, perimeter and vertex count only (specks are also where fitEllipse is ill-conditioned and slow)
+        const double area = emia_contour_area(cp, len);
+        if (area < min_area) {
+            for (int f = 0; f < EMIA_REC_FIELDS; ++f) rec[f] = 0.0;
+            rec[EMIA_REC_AREA] = area;
+            rec[EMIA_REC_PERIMETER] = emia_arc_length_closed(cp, len);
+            rec[EMIA_F_NVERT] = (double)len;
+        } else {
+            emia_measure_contour(cp, len, um_pix, sc0 + sub_end, rec, (len >= 1 && len <= presort_max) ? 3 : 0);
+            rec[EMIA_REC_MEASURED] = 1.0;
+        }
         rec_inst[c0 + j] = (int32_t)i;
         if (j == 0 && perim0) perim0[i] = rec[EMIA_REC_PERIMETER];
     }
@@ -298,10 +519,10 @@ extern "C" int emia_contour_measure(const uint32_t* crops, const emia_inst_meta*
     emia_launch_clear_marks(marks, crop_off, n, (cudaStream_t)stream);
     k_contour_trace<true><<<gridt, EMIA_TRACE_THREADS, EMIA_TRACE_SMEM_BYTES, (cudaStream_t)stream>>>(crops, meta, crop_off, n, marks, nullptr, nullptr, nullptr,
                                                                                   cont_off, pt_off, pts, cstart, nullptr);
-    const unsigned grid = (unsigned)((n + 127) / 128);
-    k_contour_hull<<<(unsigned)((n + EMIA_PRESORT_WARPS - 1) / EMIA_PRESORT_WARPS), EMIA_PRESORT_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    const unsigned grid = EMIA_MEASURE_GRID(n);
+    k_contour_hull<<<EMIA_HULL_GRID(n), EMIA_PRESORT_WARPS * 32, 0, (cudaStream_t)stream>>>(
         n, nullptr, cont_off, cont_off, pt_off, cstart, 0, scratch_off, pts, scratch, nullptr);
-    k_contour_measure<<<grid, 128, 0, (cudaStream_t)stream>>>(n, nullptr, cont_off, cont_off, pt_off, scratch_off, um_pix, min_area, pts, cstart, 0,
+    k_contour_measure<<<grid, EMIA_MEASURE_THREADS, 0, (cudaStream_t)stream>>>(n, nullptr, cont_off, cont_off, pt_off, scratch_off, um_pix, min_area, pts, cstart, 0,
                                                               EMIA_PRESORT_MAX, records, rec_inst, perim0, scratch, nullptr);
     return emia_check_launch("emia_contour_measure launch: %s");
 }
@@ -362,7 +583,7 @@ __global__ void __launch_bounds__(EMIA_TRACE_THREADS) k_contour_trace_slab(
                 else {
                     const int nc = T.o.n_contours;
                     n_contours[i] = nc;
-                    scratch_bytes[i] = nc ? (int64_t)((emia_measure_scratch_bytes(T.o.max_len) + 15) & ~(size_t)15) : 0;
+                    scratch_bytes[i] = (int64_t)emia_measure_item_scratch_bytes(T.o.n_pts, nc);
                     // arcLength of contours[0] in OpenCV order = the LAST discovered contour (deduplicate_masks_smart, Q10),
                     // accumulated while the border was followed
                     if (perim0 && nc) perim0[i] = T.o.perim_last;
@@ -430,9 +651,9 @@ extern "C" int emia_contour_measure_stored(const emia_inst_meta* meta, int64_t n
     if (n == 0) return EMIA_OK;
     if (!meta || !cont_off || !pt_off || !cstart || !scratch_off || !pts || !records || !rec_inst || !perim0 || !scratch)
         return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_measure_stored: %s", "null pointer");
-    k_contour_hull<<<(unsigned)((n + EMIA_PRESORT_WARPS - 1) / EMIA_PRESORT_WARPS), EMIA_PRESORT_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    k_contour_hull<<<EMIA_HULL_GRID(n), EMIA_PRESORT_WARPS * 32, 0, (cudaStream_t)stream>>>(
         n, nullptr, cont_off, cont_off, pt_off, cstart, cstart_stride, scratch_off, pts, (uint8_t*)scratch, nullptr);
-    k_contour_measure<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(n, nullptr, cont_off, cont_off, pt_off, scratch_off, um_pix, min_area, pts,
+    k_contour_measure<<<EMIA_MEASURE_GRID(n), EMIA_MEASURE_THREADS, 0, (cudaStream_t)stream>>>(n, nullptr, cont_off, cont_off, pt_off, scratch_off, um_pix, min_area, pts,
                                                                                   cstart, cstart_stride, EMIA_PRESORT_MAX, records, rec_inst, perim0, scratch, nullptr);
     return emia_check_launch("emia_contour_measure_stored launch: %s");
 }
@@ -478,9 +699,9 @@ extern "C" int emia_contour_measure_list(int64_t n_items, const int32_t* item_in
     if (!item_inst || !rec_off || !scr_off || !pt_off || !cstart || !pts || !records || !rec_inst || !scratch ||
         (cstart_stride == 0 && !inst_cont_off))
         return emia_fail(EMIA_ERR_BAD_ARG, "emia_contour_measure_list: %s", "null pointer");
-    k_contour_hull<<<(unsigned)((n_items + EMIA_PRESORT_WARPS - 1) / EMIA_PRESORT_WARPS), EMIA_PRESORT_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    k_contour_hull<<<EMIA_HULL_GRID(n_items), EMIA_PRESORT_WARPS * 32, 0, (cudaStream_t)stream>>>(
         n_items, item_inst, rec_off, inst_cont_off, pt_off, cstart, cstart_stride, scr_off, pts, scratch, abort_flag);
-    k_contour_measure<<<(unsigned)((n_items + 127) / 128), 128, 0, (cudaStream_t)stream>>>(n_items, item_inst, rec_off, inst_cont_off, pt_off, scr_off,
+    k_contour_measure<<<EMIA_MEASURE_GRID(n_items), EMIA_MEASURE_THREADS, 0, (cudaStream_t)stream>>>(n_items, item_inst, rec_off, inst_cont_off, pt_off, scr_off,
                                                                                         um_pix, min_area, pts, cstart, cstart_stride,
                                                                                         EMIA_PRESORT_MAX, records, rec_inst, nullptr, scratch, abort_flag);
     return emia_check_launch("emia_contour_measure_list launch: %s");

@@ -114,7 +114,9 @@ int emia_mask_unpack(const uint32_t* crops, const emia_inst_meta* meta, const in
  * Pass 2 (emia_contour_measure): pts (packed x | y<<16, frame coordinates), cstart (per instance n_contours+1
  *   entries at cont_off[i] + i, relative to pt_off[i], DISCOVERY order), records in OpenCV order (reverse
  *   discovery) at cont_off[i] + j, rec_inst (instance id per record), perim0[i] = arcLength of the first
- *   returned contour (0 if none).  records[..][EMIA_REC_MEASURED] = 1 when contourArea >= min_area. */
+ *   returned contour (0 if none).  records[..][EMIA_REC_MEASURED] = 1 when contourArea >= min_area; like the reference,
+ *   which skips such a contour before calculate_measurements, a record below the gate carries only EMIA_REC_AREA,
+ *   EMIA_REC_PERIMETER and EMIA_REC_NVERT (everything else 0).  Pass min_area = 0 to measure every contour. */
 int emia_contour_count(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n,
                        uint32_t* marks, int64_t* n_contours, int64_t* n_points, int64_t* scratch_bytes,
                        void* stream);

@@ -50,10 +50,10 @@ int sim_convex_hull(const uint32_t* pts, int n, int clockwise, int* hull) {
 int sim_min_area_rect(const uint32_t* pts, int n, int clockwise, float* rect, float* box) {
     std::vector<uint64_t> keys(n + 1); std::vector<int> stack(n + 3), tmp(n + 1), hull(n + 1);
     int nh = emia_convex_hull(pts, n, clockwise, keys.data(), stack.data(), hull.data(), tmp.data());
-    std::vector<float> hp(2 * nh + 2), vect(2 * nh + 2), inv(nh + 1);
-    for (int i = 0; i < nh; ++i) { hp[2*i] = (float)EMIA_PT_X(pts[hull[i]]); hp[2*i+1] = (float)EMIA_PT_Y(pts[hull[i]]); }
-    EmiaRotRect r = emia_min_area_rect_from_hull(hp.data(), nh, vect.data(), inv.data());
-    if (nh > 2) emia_rotating_calipers(hp.data(), nh, vect.data(), inv.data(), rect + 5);
+    std::vector<uint32_t> hq(nh + 2);
+    for (int i = 0; i < nh; ++i) hq[i] = pts[hull[i]];
+    EmiaRotRect r = emia_min_area_rect_from_hull(hq.data(), nh);
+    if (nh > 2) emia_rotating_calipers(hq.data(), nh, rect + 5);
     rect[0] = r.cx; rect[1] = r.cy; rect[2] = r.w; rect[3] = r.h; rect[4] = r.angle;
     emia_box_points(r, box);
     return nh;
