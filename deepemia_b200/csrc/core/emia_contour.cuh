@@ -94,27 +94,6 @@ EMIA_HD void emia_mark(const EmiaMarks& m, int lx, int ly, int negative) {
 #define EMIA_DX(s) ((int)((0x21000122u >> (4 * (s))) & 0xFu) - 1)
 #define EMIA_DY(s) ((int)((0x22210001u >> (4 * (s))) & 0xFu) - 1)
 
-// bits of row ly at columns lx-1, lx, lx+1 (bit 0, 1, 2); anything outside the crop reads as 0
-EMIA_HD uint32_t emia_row3(const EmiaBitView& v, int lx, int ly) {
-    if ((unsigned)ly >= (unsigned)v.h) return 0u;
-    const uint32_t* row = v.bits + (size_t)ly * v.pitch_words;
-    if (lx == 0) return (row[0] << 1) & 7u;
-    const int c = (lx - 1) >> 5, sh = (lx - 1) & 31;
-    const uint32_t w0 = row[c];
-    const uint32_t w1 = (c + 1 < v.wwords) ? row[c + 1] : 0u;
-#if defined(__CUDA_ARCH__)
-    return __funnelshift_r(w0, w1, sh) & 7u;
-#else
-    return (uint32_t)(((((uint64_t)w1) << 32) | w0) >> sh) & 7u;
-#endif
-}
-// 8-bit neighbour mask of local pixel (lx, ly): bit s set <=> the neighbour in direction s is foreground
-EMIA_HD uint32_t emia_nbr8(const EmiaBitView& v, int lx, int ly) {
-    const uint32_t up = emia_row3(v, lx, ly - 1), mid = emia_row3(v, lx, ly), dn = emia_row3(v, lx, ly + 1);
-    return ((mid >> 2) & 1u) | (((up >> 2) & 1u) << 1) | (((up >> 1) & 1u) << 2) | ((up & 1u) << 3) | ((mid & 1u) << 4) |
-           ((dn & 1u) << 5) | (((dn >> 1) & 1u) << 6) | (((dn >> 2) & 1u) << 7);
-}
-
 // All external contours of the crop, in discovery (raster) order.  OpenCV returns them in REVERSE discovery order;
 // consumers iterate k = n_contours-1 .. 0.  mk/ng must hold h*wwords words each.
 //
@@ -130,6 +109,11 @@ struct EmiaTraceState {
     int y, c;                 // scan position (row, word)
     uint32_t done_mask;       // bits of the current word already examined
     int x0, y0, x1, y1, x3, y3, s, prev_s, before;
+    // 3 x 64-pixel window of the crop around the border pixel being followed: rows wy-1, wy, wy+1, word columns wc, wc+1
+    // (wc = (x - 1) >> 5, i.e. -1 when x == 0; words outside the crop read as 0).  A border step moves by one pixel, so the next
+    // step reuses two of the three rows (or all of them) instead of re-loading six words.
+    uint32_t wu0, wu1, wm0, wm1, wd0, wd1;
+    int wc, wy;
 };
 #define EMIA_TRACE_SCAN 0
 #define EMIA_TRACE_FOLLOW 1
@@ -141,6 +125,63 @@ EMIA_HD void emia_trace_begin(EmiaTraceState& T) {
     if (T.o.store) T.o.cstart[0] = 0;
     T.y = 0; T.c = 0; T.done_mask = 0u;
     T.x0 = T.y0 = T.x1 = T.y1 = T.x3 = T.y3 = T.s = T.prev_s = T.before = 0;
+    T.wu0 = T.wu1 = T.wm0 = T.wm1 = T.wd0 = T.wd1 = 0u;
+    T.wc = -2; T.wy = -4;                       // no window yet
+}
+
+EMIA_HD void emia_win_load_row(const EmiaBitView& v, int ly, int c, uint32_t* w0, uint32_t* w1) {
+    if ((unsigned)ly >= (unsigned)v.h) { *w0 = 0u; *w1 = 0u; return; }
+    const uint32_t* row = v.bits + (size_t)ly * v.pitch_words;
+    *w0 = (c >= 0) ? row[c] : 0u;
+    *w1 = (c + 1 < v.wwords) ? row[c + 1] : 0u;
+}
+// Centre the window on local pixel (x, y); called as soon as the next pixel is known, so that the loads are in flight while the
+// other lanes of the warp take their turn.
+EMIA_HD void emia_win_move(EmiaTraceState& T, int x, int y) {
+    const int c = (x - 1) >> 5;
+    if (c == T.wc) {
+        if (y == T.wy) return;
+        if (y == T.wy + 1) {
+            T.wu0 = T.wm0; T.wu1 = T.wm1; T.wm0 = T.wd0; T.wm1 = T.wd1;
+            emia_win_load_row(T.v, y + 1, c, &T.wd0, &T.wd1);
+            T.wy = y;
+            return;
+        }
+        if (y == T.wy - 1) {
+            T.wd0 = T.wm0; T.wd1 = T.wm1; T.wm0 = T.wu0; T.wm1 = T.wu1;
+            emia_win_load_row(T.v, y - 1, c, &T.wu0, &T.wu1);
+            T.wy = y;
+            return;
+        }
+    }
+    emia_win_load_row(T.v, y - 1, c, &T.wu0, &T.wu1);
+    emia_win_load_row(T.v, y, c, &T.wm0, &T.wm1);
+    emia_win_load_row(T.v, y + 1, c, &T.wd0, &T.wd1);
+    T.wc = c; T.wy = y;
+}
+EMIA_HD uint32_t emia_win_row3(uint32_t w0, uint32_t w1, int sh) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(w0, w1, sh) & 7u;
+#else
+    return (uint32_t)(((((uint64_t)w1) << 32) | w0) >> sh) & 7u;
+#endif
+}
+// 8-bit neighbour mask of the pixel the window is centred on: bit s set <=> the neighbour in direction s is foreground
+EMIA_HD uint32_t emia_win_nbr8(const EmiaTraceState& T, int x) {
+    const int sh = (x - 1) & 31;
+    const uint32_t up = emia_win_row3(T.wu0, T.wu1, sh), mid = emia_win_row3(T.wm0, T.wm1, sh), dn = emia_win_row3(T.wd0, T.wd1, sh);
+    return ((mid >> 2) & 1u) | (((up >> 2) & 1u) << 1) | (((up >> 1) & 1u) << 2) | ((up & 1u) << 3) | ((mid & 1u) << 4) |
+           ((dn & 1u) << 5) | (((dn >> 1) & 1u) << 6) | (((dn >> 2) & 1u) << 7);
+}
+// Mark-plane update of a followed border pixel.  On the device it is a fire-and-forget reduction (RED.OR): the old value is
+// not needed, so the step does not wait for a load; the thread's own later reads of the word (scan phase) are ordered behind
+// it by same-address program order.
+EMIA_HD void emia_mark_or(uint32_t* word, uint32_t bit) {
+#if defined(__CUDA_ARCH__) && !defined(EMIA_MARK_PLAIN)
+    atomicOr(word, bit);
+#else
+    *word |= bit;
+#endif
 }
 
 // One scan step: walks the rest of the current row for a start candidate.  Returns the next phase.
@@ -175,14 +216,15 @@ EMIA_HD int emia_trace_scan_step(EmiaTraceState& T) {
     EmiaContourOut& o = T.o;
     if (o.store && o.n_contours >= o.cap_contours) { o.overflow = 1; return EMIA_TRACE_DONE; }
     T.before = o.n_pts;
-    const uint32_t N8 = emia_nbr8(v, x, y);
+    emia_win_move(T, x, y);
+    const uint32_t N8 = emia_win_nbr8(T, x);
     // first neighbour clockwise from W: directions 3,2,1,0,7,6,5 -> bit k of M
     const uint32_t M = ((N8 >> 3) & 1u) | (((N8 >> 2) & 1u) << 1) | (((N8 >> 1) & 1u) << 2) | ((N8 & 1u) << 3) |
                        (((N8 >> 7) & 1u) << 4) | (((N8 >> 6) & 1u) << 5) | (((N8 >> 5) & 1u) << 6);
     const int wi = y * ww + (x >> 5);
     const uint32_t bit = 1u << (x & 31);
     if (M == 0u) {   // isolated pixel
-        T.mk[wi] |= bit; T.ng[wi] |= bit;
+        emia_mark_or(&T.mk[wi], bit); emia_mark_or(&T.ng[wi], bit);
         emia_contour_emit(o, v.x_origin + x, v.y_origin + y);
         emia_contour_close(o);
         o.n_contours++;
@@ -202,15 +244,15 @@ EMIA_HD int emia_trace_follow_step(EmiaTraceState& T) {
     const EmiaBitView& v = T.v;
     const int ww = v.wwords;
     EmiaContourOut& o = T.o;
-    const uint32_t N8 = emia_nbr8(v, T.x3, T.y3);
+    const uint32_t N8 = emia_win_nbr8(T, T.x3);                    // the window was centred on (x3, y3) by the previous step
     const int s_end = T.s;
     const int r = (s_end + 1) & 7;
     const uint32_t rot = ((N8 >> r) | (N8 << (8 - r))) & 0xFFu;
     const int s = (s_end + 1 + emia_ctz(rot)) & 7;                 // next foreground neighbour counter-clockwise
     const int wi = T.y3 * ww + (T.x3 >> 5);
     const uint32_t bit = 1u << (T.x3 & 31);
-    T.mk[wi] |= bit;                                                // label +2 ...
-    if ((unsigned)(s - 1) < (unsigned)s_end) T.ng[wi] |= bit;       // ... or -126 when the east neighbour was examined empty
+    emia_mark_or(&T.mk[wi], bit);                                   // label +2 ...
+    if ((unsigned)(s - 1) < (unsigned)s_end) emia_mark_or(&T.ng[wi], bit);   // ... or -126 when the east neighbour was examined empty
     if (s != T.prev_s) {
         emia_contour_emit(o, v.x_origin + T.x3, v.y_origin + T.y3);
         T.prev_s = s;
@@ -226,6 +268,7 @@ EMIA_HD int emia_trace_follow_step(EmiaTraceState& T) {
     }
     T.x3 = x4; T.y3 = y4;
     T.s = (s + 4) & 7;
+    emia_win_move(T, x4, y4);
     return EMIA_TRACE_FOLLOW;
 }
 

@@ -557,7 +557,10 @@ __global__ void k_trace_caps(const emia_inst_meta* __restrict__ meta, int64_t n,
 // shared-memory counter INSIDE the same flat loop (phase "next"), so the warp keeps executing one instruction stream with
 // most lanes busy — border lengths differ 4x between instances and one-instance-per-thread left 8 of 32 lanes active (ncu).
 #define EMIA_TRACE_CHUNK 1024          // instances per CTA (upper bound; smaller inputs use smaller chunks to fill the GPU)
-__global__ void __launch_bounds__(EMIA_TRACE_THREADS) k_contour_trace_slab(
+#ifndef EMIA_TRACE_MIN_CTAS
+#define EMIA_TRACE_MIN_CTAS 8
+#endif
+__global__ void __launch_bounds__(EMIA_TRACE_THREADS, EMIA_TRACE_MIN_CTAS) k_contour_trace_slab(
     const uint32_t* __restrict__ crops, const emia_inst_meta* __restrict__ meta, const int64_t* __restrict__ crop_off, int64_t n,
     uint32_t* __restrict__ marks, const int64_t* __restrict__ pt_cap_off, int capc, uint32_t* __restrict__ pts,
     int32_t* __restrict__ cstart_slab, int64_t* __restrict__ n_contours, int64_t* __restrict__ scratch_bytes,
