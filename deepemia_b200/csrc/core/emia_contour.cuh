@@ -139,17 +139,19 @@ EMIA_HD void emia_win_load_row(const EmiaBitView& v, int ly, int c, uint32_t* w0
 // other lanes of the warp take their turn.
 EMIA_HD void emia_win_move(EmiaTraceState& T, int x, int y) {
     const int c = (x - 1) >> 5;
+    const int dy = y - T.wy;
     if (c == T.wc) {
-        if (y == T.wy) return;
-        if (y == T.wy + 1) {
-            T.wu0 = T.wm0; T.wu1 = T.wm1; T.wm0 = T.wd0; T.wm1 = T.wd1;
-            emia_win_load_row(T.v, y + 1, c, &T.wd0, &T.wd1);
-            T.wy = y;
-            return;
-        }
-        if (y == T.wy - 1) {
-            T.wd0 = T.wm0; T.wd1 = T.wm1; T.wm0 = T.wu0; T.wm1 = T.wu1;
-            emia_win_load_row(T.v, y - 1, c, &T.wu0, &T.wu1);
+        if (dy == 0) return;
+        if (dy == 1 || dy == -1) {
+            // one row enters the window: a single load site for both directions (SIMT: the lanes that moved up and the lanes
+            // that moved down execute it together), the register rotation is a handful of selects
+            uint32_t n0, n1;
+            emia_win_load_row(T.v, y + dy, c, &n0, &n1);
+            const bool down = dy > 0;
+            const uint32_t m0 = T.wm0, m1 = T.wm1;
+            T.wm0 = down ? T.wd0 : T.wu0; T.wm1 = down ? T.wd1 : T.wu1;
+            T.wu0 = down ? m0 : n0;       T.wu1 = down ? m1 : n1;
+            T.wd0 = down ? n0 : m0;       T.wd1 = down ? n1 : m1;
             T.wy = y;
             return;
         }
@@ -192,11 +194,30 @@ EMIA_HD int emia_trace_scan_step(EmiaTraceState& T) {
     const uint32_t* row = v.bits + (size_t)T.y * v.pitch_words;
     const uint32_t* mrow = T.mk + T.y * ww;
     uint32_t cand = 0u;
-    for (; T.c < ww; ++T.c, T.done_mask = 0u) {
-        const uint32_t F = row[T.c];
-        const uint32_t left = (F << 1) | (T.c > 0 ? (row[T.c - 1] >> 31) : 0u);
-        cand = F & ~left & ~mrow[T.c] & ~T.done_mask;
-        if (cand) break;
+    if (ww <= 4) {
+        // narrow crops (the common case): all words of the row and of its mark row are loaded at once (independent loads, one
+        // exposed latency per row instead of one per word), the candidates are then found in registers
+        uint32_t F[4], Mk[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { F[c] = (c < ww) ? row[c] : 0u; Mk[c] = (c < ww) ? mrow[c] : 0u; }
+        int first_c = ww;
+#pragma unroll
+        for (int c = 3; c >= 0; --c) {
+            const uint32_t left = (F[c] << 1) | (c > 0 ? (F[c > 0 ? c - 1 : 0] >> 31) : 0u);
+            uint32_t cd = F[c] & ~left & ~Mk[c];
+            if (c < T.c) cd = 0u;
+            if (c == T.c) cd &= ~T.done_mask;
+            if (cd) { cand = cd; first_c = c; }
+        }
+        if (cand && first_c != T.c) T.done_mask = 0u;
+        T.c = first_c;
+    } else {
+        for (; T.c < ww; ++T.c, T.done_mask = 0u) {
+            const uint32_t F = row[T.c];
+            const uint32_t left = (F << 1) | (T.c > 0 ? (row[T.c - 1] >> 31) : 0u);
+            cand = F & ~left & ~mrow[T.c] & ~T.done_mask;
+            if (cand) break;
+        }
     }
     if (!cand) { T.c = 0; ++T.y; T.done_mask = 0u; return EMIA_TRACE_SCAN; }
     const int c = T.c, y = T.y;
