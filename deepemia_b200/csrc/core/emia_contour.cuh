@@ -310,6 +310,7 @@ EMIA_HD double emia_contour_area(const uint32_t* pts, int n) {
     if (n == 0) return 0.0;
     long long a = 0;
     int px = EMIA_PT_X(pts[n - 1]), py = EMIA_PT_Y(pts[n - 1]);
+#pragma unroll 4
     for (int i = 0; i < n; ++i) {
         const int x = EMIA_PT_X(pts[i]), y = EMIA_PT_Y(pts[i]);
         a += (long long)px * y - (long long)py * x;
@@ -329,6 +330,7 @@ EMIA_HD double emia_arc_length_closed(const uint32_t* pts, int n, const float* d
     if (n <= 1) return 0.0;
     double per = 0.0;
     int px = EMIA_PT_X(pts[n - 1]), py = EMIA_PT_Y(pts[n - 1]);
+#pragma unroll 4
     for (int i = 0; i < n; ++i) {
         const int x = EMIA_PT_X(pts[i]), y = EMIA_PT_Y(pts[i]);
         per += (double)emia_seg_len(x - px, y - py, diag);

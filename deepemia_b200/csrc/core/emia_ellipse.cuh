@@ -200,8 +200,10 @@ EMIA_HD void emia_chol_resolve(const double* L, const double* g, double* x) {
 struct EmiaEllipsePts {
     const uint32_t* pts; int n; float cxf, cyf; double scale; int perturbed; float eps;
 };
-EMIA_HD void emia_ellipse_pt(const EmiaEllipsePts& P, int i, double* px, double* py) {
-    float fx = (float)EMIA_PT_X(P.pts[i]), fy = (float)EMIA_PT_Y(P.pts[i]);
+// q = P.pts[i], loaded by the caller one iteration ahead (the loops below are software-pipelined by hand: the load of vertex
+// i + 1 is in flight while the ~20 dependent fp64 operations of vertex i execute)
+EMIA_HD void emia_ellipse_pt(const EmiaEllipsePts& P, int i, uint32_t q, double* px, double* py) {
+    float fx = (float)EMIA_PT_X(q), fy = (float)EMIA_PT_Y(q);
     if (P.perturbed) { float ox, oy; emia_ellipse_ofs(i, P.eps, &ox, &oy); fx = fx + ox; fy = fy + oy; }
     const float dx = fx - P.cxf, dy = fy - P.cyf;
     *px = dx * P.scale; *py = dy * P.scale;
@@ -215,8 +217,11 @@ EMIA_HD int emia_ellipse_stage1_fast(const EmiaEllipsePts& P, double* gfp) {
     double G[25], g[5], L[25];
     for (int i = 0; i < 25; ++i) { G[i] = 0.0; L[i] = 0.0; }
     for (int i = 0; i < 5; ++i) g[i] = 0.0;
+    uint32_t qn = P.pts[0];
     for (int i = 0; i < P.n; ++i) {
-        double px, py; emia_ellipse_pt(P, i, &px, &py);
+        const uint32_t q = qn;
+        if (i + 1 < P.n) qn = P.pts[i + 1];
+        double px, py; emia_ellipse_pt(P, i, q, &px, &py);
         const double row[5] = {-px * px, -py * py, -px * py, px, py};
         for (int a = 0; a < 5; ++a) {
             for (int b = a; b < 5; ++b) G[a * 5 + b] += row[a] * row[b];
@@ -229,8 +234,11 @@ EMIA_HD int emia_ellipse_stage1_fast(const EmiaEllipsePts& P, double* gfp) {
     // two steps of iterative refinement with residuals taken against the rows themselves
     for (int it = 0; it < 2; ++it) {
         double r5[5] = {0, 0, 0, 0, 0};
+        uint32_t qn = P.pts[0];
         for (int i = 0; i < P.n; ++i) {
-            double px, py; emia_ellipse_pt(P, i, &px, &py);
+            const uint32_t q = qn;
+            if (i + 1 < P.n) qn = P.pts[i + 1];
+            double px, py; emia_ellipse_pt(P, i, q, &px, &py);
             const double row[5] = {-px * px, -py * py, -px * py, px, py};
             double res = 10000.0;
             for (int a = 0; a < 5; ++a) res -= row[a] * gfp[a];
@@ -246,8 +254,11 @@ EMIA_HD int emia_ellipse_stage2_fast(const EmiaEllipsePts& P, const double* rp, 
     double G[9], g[3], L[9];
     for (int i = 0; i < 9; ++i) { G[i] = 0.0; L[i] = 0.0; }
     for (int i = 0; i < 3; ++i) g[i] = 0.0;
+    uint32_t qn = P.pts[0];
     for (int i = 0; i < P.n; ++i) {
-        double px, py; emia_ellipse_pt(P, i, &px, &py);
+        const uint32_t q = qn;
+        if (i + 1 < P.n) qn = P.pts[i + 1];
+        double px, py; emia_ellipse_pt(P, i, q, &px, &py);
         const double row[3] = {(px - rp[0]) * (px - rp[0]), (py - rp[1]) * (py - rp[1]), (px - rp[0]) * (py - rp[1])};
         for (int a = 0; a < 3; ++a) {
             for (int b = a; b < 3; ++b) G[a * 3 + b] += row[a] * row[b];
@@ -259,8 +270,11 @@ EMIA_HD int emia_ellipse_stage2_fast(const EmiaEllipsePts& P, const double* rp, 
     if (!(ratio > EMIA_ELLIPSE_FAST_MIN_RATIO)) return 0;
     for (int it = 0; it < 2; ++it) {
         double r3[3] = {0, 0, 0};
+        uint32_t qn = P.pts[0];
         for (int i = 0; i < P.n; ++i) {
-            double px, py; emia_ellipse_pt(P, i, &px, &py);
+            const uint32_t q = qn;
+            if (i + 1 < P.n) qn = P.pts[i + 1];
+            double px, py; emia_ellipse_pt(P, i, q, &px, &py);
             const double row[3] = {(px - rp[0]) * (px - rp[0]), (py - rp[1]) * (py - rp[1]), (px - rp[0]) * (py - rp[1])};
             double res = 1.0;
             for (int a = 0; a < 3; ++a) res -= row[a] * gfp[a];
@@ -327,9 +341,11 @@ EMIA_HD_NOINLINE EmiaEllipse emia_fit_ellipse_general(const uint32_t* pts, int n
     EmiaEllipse box; box.cx = box.cy = box.w = box.h = box.angle = 0.f; box.ok = 0;
     if (n < 5) return box;
     float cxf = 0.f, cyf = 0.f;
+#pragma unroll 4
     for (int i = 0; i < n; ++i) { cxf += (float)EMIA_PT_X(pts[i]); cyf += (float)EMIA_PT_Y(pts[i]); }
     cxf /= (float)n; cyf /= (float)n;
     double s = 0;
+#pragma unroll 4
     for (int i = 0; i < n; ++i) {
         const float dx = (float)EMIA_PT_X(pts[i]) - cxf, dy = (float)EMIA_PT_Y(pts[i]) - cyf;
         s += fabsf(dx) + fabsf(dy);
@@ -347,7 +363,7 @@ EMIA_HD_NOINLINE EmiaEllipse emia_fit_ellipse_general(const uint32_t* pts, int n
             for (int i = 0; i < 25; ++i) R[i] = 0.0;
             for (int i = 0; i < 5; ++i) qtb[i] = 0.0;
             for (int i = 0; i < n; ++i) {
-                double px, py; emia_ellipse_pt(P, i, &px, &py);
+                double px, py; emia_ellipse_pt(P, i, P.pts[i], &px, &py);
                 double row[5] = {-px * px, -py * py, -px * py, px, py};
                 emia_givens_add_row<5>(R, qtb, row, 10000.0);
             }
@@ -373,7 +389,7 @@ EMIA_HD_NOINLINE EmiaEllipse emia_fit_ellipse_general(const uint32_t* pts, int n
         for (int i = 0; i < 9; ++i) R[i] = 0.0;
         for (int i = 0; i < 3; ++i) qtb[i] = 0.0;
         for (int i = 0; i < n; ++i) {
-            double px, py; emia_ellipse_pt(P, i, &px, &py);
+            double px, py; emia_ellipse_pt(P, i, P.pts[i], &px, &py);
             double row[3] = {(px - rp[0]) * (px - rp[0]), (py - rp[1]) * (py - rp[1]), (px - rp[0]) * (py - rp[1])};
             emia_givens_add_row<3>(R, qtb, row, 1.0);
         }

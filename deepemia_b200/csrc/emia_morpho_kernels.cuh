@@ -101,7 +101,9 @@ __global__ void __launch_bounds__(EMIA_TRACE_THREADS) k_contour_trace(
 // (all lanes), parks each sorted key list (<= EMIA_HULL_FAST_MAX survivors, 32-bit compact keys) in a small shared-memory slot,
 // and then runs the chains of ALL its items at once (lane = item * 4 + chain) and the assembly on one lane per item.
 // Items with more survivors or a larger extent take the one-item-per-warp path afterwards (its buffers alias the slots).
+#ifndef EMIA_HULL_PACK
 #define EMIA_HULL_PACK 8
+#endif
 #define EMIA_HULL_FAST_MAX 64
 struct EmiaHullSmem {
     uint64_t keys[EMIA_PRESORT_MAX];
