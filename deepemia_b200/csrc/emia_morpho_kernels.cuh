@@ -95,7 +95,9 @@ __global__ void __launch_bounds__(EMIA_TRACE_THREADS) k_contour_trace(
 // start at rec_off[it] (rec_off[it+1] - rec_off[it] = number of contours) and its scratch at scratch_off[it].
 // inst_cont_off (per INSTANCE) locates the packed cstart layout and is only read when cstart_stride == 0.
 #define EMIA_PRESORT_MAX 256
+#ifndef EMIA_PRESORT_WARPS
 #define EMIA_PRESORT_WARPS 4
+#endif
 // Packed path: the serial phases (four Sklansky chains, hull assembly) used 4 and 1 lanes of the warp and were 60 % of the
 // kernel's issue slots.  A warp therefore takes EMIA_HULL_PACK work items: it pre-filters and sorts them one after the other
 // (all lanes), parks each sorted key list (<= EMIA_HULL_FAST_MAX survivors, 32-bit compact keys) in a small shared-memory slot,
@@ -368,9 +370,12 @@ __global__ void __launch_bounds__(EMIA_PRESORT_WARPS * 32) k_contour_hull(int64_
         fast |= 1u << j;
         __syncwarp();
     }
-    // phase 2: the four chains of every parked item at once (lane = item * 4 + chain)
+    // phase 2: the chains of every parked item at once.  Lane = item * LPI + sub; with two lanes per item one lane runs the two
+    // upper chains and the other the two lower ones — each pair covers the whole sorted array once, so the lanes of an item
+    // are balanced by construction.
     {
-        const int j = lane >> 2, c = lane & 3;
+        constexpr int LPI = 32 / EMIA_HULL_PACK, CPL = 4 / LPI;      // lanes per item, chains per lane
+        const int j = lane / LPI, sub = lane % LPI;
         EmiaHullSlot& S = W.packed.slot[j];
         const bool mine = (fast >> j) & 1u;
         bool degenerate = false;
@@ -378,17 +383,21 @@ __global__ void __launch_bounds__(EMIA_PRESORT_WARPS * 32) k_contour_hull(int64_
             const int m = S.m;
             degenerate = (emia_kx(S.keys[0]) == emia_kx(S.keys[m - 1]) && emia_ky(S.keys[0]) == emia_ky(S.keys[m - 1]));
             if (!degenerate) {
-                const int start = (c & 1) ? m - 1 : 0;
-                const int end = (c < 2) ? S.maxy : S.miny;
-                const int nsign = (c < 2) ? -1 : 1;
-                const int sign2 = (c == 0 || c == 3) ? 1 : -1;
-                S.cnt[c] = emia_sklansky(S.keys, start, end, S.stacks[c], nsign, sign2);
+#pragma unroll
+                for (int cc = 0; cc < CPL; ++cc) {
+                    const int c = sub * CPL + cc;
+                    const int start = (c & 1) ? m - 1 : 0;
+                    const int end = (c < 2) ? S.maxy : S.miny;
+                    const int nsign = (c < 2) ? -1 : 1;
+                    const int sign2 = (c == 0 || c == 3) ? 1 : -1;
+                    S.cnt[c] = emia_sklansky(S.keys, start, end, S.stacks[c], nsign, sign2);
+                }
             }
         }
         __syncwarp();
         // phase 3: assembly, one lane per item
         int nout = 0;
-        if (mine && c == 0) {
+        if (mine && sub == 0) {
             if (degenerate) { S.hull[0] = 0; nout = 1; }
             else {
                 const int stop_idx = emia_hull_emit_upper(S.keys, 0, S.stacks[0], S.cnt[0], S.stacks[1], S.cnt[1], S.hull, &nout);
@@ -396,15 +405,15 @@ __global__ void __launch_bounds__(EMIA_PRESORT_WARPS * 32) k_contour_hull(int64_
                 emia_hull_cyclic_shift(S.hull, nout, S.tmp);
             }
         }
-        nout = __shfl_sync(0xffffffffu, nout, lane & ~3);
+        nout = __shfl_sync(0xffffffffu, nout, lane - sub);
         __syncwarp();
         // phase 4: the hull points (original vertices, packed) into shared memory — over the chain stacks, which are dead — and
         // the rotating calipers on them, one lane per item; the result goes to the item's scratch block where
         // emia_measure_contour(prepared = 3) expects it (emia_measure_rect_off)
         uint32_t* hq = (uint32_t*)&S.stacks[0][0];
-        if (mine) for (int t = c; t < nout; t += 4) hq[t] = S.p[S.hull[t]];
+        if (mine) for (int t = sub; t < nout; t += LPI) hq[t] = S.p[S.hull[t]];
         __syncwarp();
-        if (mine && c == 0) {
+        if (mine && sub == 0) {
             int* r = (int*)(scratch + S.scratch_off + emia_measure_rect_off(S.len));
             r[0] = nout;
             if (nout > 2) {
