@@ -338,15 +338,30 @@ __global__ void __launch_bounds__(EMIA_PRESORT_WARPS * 32) k_contour_hull(int64_
     EmiaHullWarpSmem& W = s_all[warp];
     uint32_t* stage = (uint32_t*)W.packed.staging;
     unsigned fast = 0u, slow = 0u;                    // warp-uniform item masks
+    // phase 0: lane j < PACK looks item j up (a chain of four dependent global loads: list entry -> contour table -> vertex
+    // offset) and touches its vertices, so that the warp pays that latency once and not once per item
+    int my_nc = 0, my_len = 0;
+    const uint32_t* my_p = nullptr;
+    long long my_sc = 0;
+    if (lane < EMIA_HULL_PACK) {
+        const int32_t* cs;
+        my_nc = emia_hull_item(it0 + lane, n, item_inst, rec_off, inst_cont_off, pt_off, cstart, cstart_stride, pts, &cs, &my_p);
+        if (my_nc) {
+            my_len = cs[1] - cs[0];
+            my_p += cs[0];
+            my_sc = (long long)scratch_off[it0 + lane];
+            for (int t = 0; t < my_len && t < EMIA_PRESORT_MAX; t += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(my_p + t));
+        }
+    }
     // phase 1: pre-filter + sort, one item after the other, all lanes
     for (int j = 0; j < EMIA_HULL_PACK; ++j) {
-        const uint32_t* p; const int32_t* cs;
-        const int nc = emia_hull_item(it0 + j, n, item_inst, rec_off, inst_cont_off, pt_off, cstart, cstart_stride, pts, &cs, &p);
+        const int nc = __shfl_sync(0xffffffffu, my_nc, j);
         if (nc == 0) continue;
-        const int len = cs[1] - cs[0];
+        const int len = __shfl_sync(0xffffffffu, my_len, j);
+        const uint32_t* p = (const uint32_t*)__shfl_sync(0xffffffffu, (unsigned long long)my_p, j);
+        const long long sc_off = __shfl_sync(0xffffffffu, my_sc, j);
         if (nc > 1) { slow |= 1u << j; continue; }                 // several contours: one after the other in phase 5
         if (len > EMIA_PRESORT_MAX || len < 1) continue;           // k_contour_measure runs the serial hull itself
-        p += cs[0];
         const EmiaHullQuad Q = emia_hull_extremes(p, len, lane);
         if (!Q.compact) { slow |= 1u << j; continue; }
         const int m = emia_hull_prefilter<uint32_t, int>(stage, p, len, lane, Q);
@@ -366,7 +381,7 @@ __global__ void __launch_bounds__(EMIA_PRESORT_WARPS * 32) k_contour_hull(int64_
         EmiaHullSlot& S = W.packed.slot[j];
         S.keys[lane] = k0;
         if (m > 32) S.keys[lane + 32] = k1;
-        if (lane == 0) { S.m = m; S.miny = mn & 511; S.maxy = mx & 511; S.len = len; S.scratch_off = (long long)scratch_off[it0 + j]; S.p = p; }
+        if (lane == 0) { S.m = m; S.miny = mn & 511; S.maxy = mx & 511; S.len = len; S.scratch_off = sc_off; S.p = p; }
         fast |= 1u << j;
         __syncwarp();
     }
