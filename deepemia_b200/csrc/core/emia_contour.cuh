@@ -28,7 +28,6 @@ struct EmiaContourOut {
     int n_contours;
     int n_pts;
     int overflow;      // set when a capacity was exceeded (results invalid)
-    int max_len;       // longest contour (vertices)
     int store;         // 0: count only (pts / cstart untouched, capacities ignored)
     // optional running cv2.arcLength of the contour being followed (track != 0): perim_last = arcLength(closed) of the most
     // recently completed contour, i.e. of contours[0] in OpenCV's (reverse discovery) order once the crop is done
@@ -108,7 +107,7 @@ struct EmiaTraceState {
     EmiaContourOut o;
     int y, c;                 // scan position (row, word)
     uint32_t done_mask;       // bits of the current word already examined
-    int x0, y0, x1, y1, x3, y3, s, prev_s, before;
+    int x0, y0, x1, y1, x3, y3, s, prev_s;
     // 3 x 64-pixel window of the crop around the border pixel being followed: rows wy-1, wy, wy+1, word columns wc, wc+1
     // (wc = (x - 1) >> 5, i.e. -1 when x == 0; words outside the crop read as 0).  A border step moves by one pixel, so the next
     // step reuses two of the three rows (or all of them) instead of re-loading six words.
@@ -120,11 +119,11 @@ struct EmiaTraceState {
 #define EMIA_TRACE_DONE 2
 
 EMIA_HD void emia_trace_begin(EmiaTraceState& T) {
-    T.o.n_contours = 0; T.o.n_pts = 0; T.o.overflow = 0; T.o.max_len = 0;
+    T.o.n_contours = 0; T.o.n_pts = 0; T.o.overflow = 0;
     T.o.per = 0.0; T.o.perim_last = 0.0; T.o.cur_n = 0;
     if (T.o.store) T.o.cstart[0] = 0;
     T.y = 0; T.c = 0; T.done_mask = 0u;
-    T.x0 = T.y0 = T.x1 = T.y1 = T.x3 = T.y3 = T.s = T.prev_s = T.before = 0;
+    T.x0 = T.y0 = T.x1 = T.y1 = T.x3 = T.y3 = T.s = T.prev_s = 0;
     T.wu0 = T.wu1 = T.wm0 = T.wm1 = T.wd0 = T.wd1 = 0u;
     T.wc = -2; T.wy = -4;                       // no window yet
 }
@@ -236,7 +235,6 @@ EMIA_HD int emia_trace_scan_step(EmiaTraceState& T) {
     }
     EmiaContourOut& o = T.o;
     if (o.store && o.n_contours >= o.cap_contours) { o.overflow = 1; return EMIA_TRACE_DONE; }
-    T.before = o.n_pts;
     emia_win_move(T, x, y);
     const uint32_t N8 = emia_win_nbr8(T, x);
     // first neighbour clockwise from W: directions 3,2,1,0,7,6,5 -> bit k of M
@@ -249,7 +247,6 @@ EMIA_HD int emia_trace_scan_step(EmiaTraceState& T) {
         emia_contour_emit(o, v.x_origin + x, v.y_origin + y);
         emia_contour_close(o);
         o.n_contours++;
-        if (o.n_pts - T.before > o.max_len) o.max_len = o.n_pts - T.before;
         if (o.store) o.cstart[o.n_contours] = o.n_pts;
         return o.overflow ? EMIA_TRACE_DONE : EMIA_TRACE_SCAN;
     }
@@ -282,7 +279,6 @@ EMIA_HD int emia_trace_follow_step(EmiaTraceState& T) {
     if (x4 == T.x0 && y4 == T.y0 && T.x3 == T.x1 && T.y3 == T.y1) {
         emia_contour_close(o);
         o.n_contours++;
-        if (o.n_pts - T.before > o.max_len) o.max_len = o.n_pts - T.before;
         if (o.store) o.cstart[o.n_contours] = o.n_pts;
         T.s = s;
         return o.overflow ? EMIA_TRACE_DONE : EMIA_TRACE_SCAN;
