@@ -126,7 +126,7 @@ struct EmiaHullSlot {
 union EmiaHullWarpSmem {
     EmiaHullSmem one;                                         // one-item path
     struct {
-        uint64_t staging[EMIA_PRESORT_MAX];                   // same bytes as one.keys: pre-filter / sort area of the current item
+        uint32_t staging[EMIA_PRESORT_MAX];                   // the first bytes of one.keys: pre-filter area of the current item (32-bit keys)
         EmiaHullSlot slot[EMIA_HULL_PACK];
     } packed;
 };
@@ -322,7 +322,10 @@ __device__ __forceinline__ int emia_hull_item(int64_t it, int64_t n, const int32
     return nc;
 }
 
-__global__ void __launch_bounds__(EMIA_PRESORT_WARPS * 32) k_contour_hull(int64_t n, const int32_t* __restrict__ item_inst,
+#ifndef EMIA_HULL_MIN_CTAS
+#define EMIA_HULL_MIN_CTAS 8
+#endif
+__global__ void __launch_bounds__(EMIA_PRESORT_WARPS * 32, EMIA_HULL_MIN_CTAS) k_contour_hull(int64_t n, const int32_t* __restrict__ item_inst,
                                                                          const int64_t* __restrict__ rec_off,
                                                                          const int64_t* __restrict__ inst_cont_off,
                                                                          const int64_t* __restrict__ pt_off,

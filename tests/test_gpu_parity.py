@@ -174,6 +174,11 @@ def test_contours_and_measurements_match_opencv(cuda_device, single_pass):
             assert r[engine.REC_NVERT] == len(c)
     exact, total = _check_records(iset, masks, classes, H, W, 0.5)
     assert exact >= 0.95 * total, f"only {exact}/{total} rows bit-exact"
+    # contours below the area gate are skipped before calculate_measurements (src/functions/inference.py:1176-1190): their records
+    # carry area / perimeter / vertex count (checked above) and nothing else
+    below = rec[rec[:, engine.REC_MEASURED] != 1.0]
+    assert len(below) >= 2 and not below[:, :12].any()
+    assert (below[:, engine.REC_AREA] < engine.default_min_area(H, W)).all()
     ar = iset.area.cpu().numpy()
     assert np.array_equal(ar, np.array([int(mk.sum()) for mk in masks]))
 
