@@ -275,25 +275,55 @@ __global__ void __launch_bounds__(EMIA_FUSED_THREADS) k_group_fused(
         }
     }
     __syncthreads();
+    // ---- ranks with any suppression edge.  The bit matrix is symmetric before the replay masks it, so a rank with an empty row
+    // neither suppresses nor can be suppressed: it is kept unconditionally and the sequential replay only visits the others
+    // (typically 10-20 % of a tile's members; the replay was 35 % of this kernel's stall samples).
+    uint32_t* act = S.xs;                                      // the sweep keys are dead
+    for (int p0 = warp * 32; p0 < nok; p0 += nwarps * 32) {
+        const int p = p0 + lane;
+        uint32_t any = 0u;
+        if (p < nok) for (int w = 0; w < stride; ++w) any |= S.bm[p * stride + w];
+        const unsigned b = __ballot_sync(0xffffffffu, any != 0u);
+        if (lane == 0) act[p0 >> 5] = b;
+    }
+    __syncthreads();
     // ---- greedy replay (warp 0): lane w keeps word w of the removed set in a register (stride <= 32)
     if (warp == 0) {
         const int q2 = (mode == 0), ordered_out = (mode != 2);
-        uint32_t removed = 0u;
+        uint32_t removed = 0u, kept = 0u;                        // word `lane` of the removed set / of the visited-and-kept set
+        const uint32_t my_act = (lane << 5) < nok ? act[lane] : 0u;
+        for (int w = 0; (w << 5) < nok; ++w) {
+            uint32_t aw = __shfl_sync(0xffffffffu, my_act, w);   // warp-uniform
+            while (aw) {
+                const int bit = __ffs((int)aw) - 1;
+                aw &= aw - 1u;
+                const int p = (w << 5) + bit;
+                const uint32_t rw = __shfl_sync(0xffffffffu, removed, w);
+                if ((rw >> bit) & 1u) continue;
+                if (lane == w) kept |= 1u << bit;                    // decided now: a later Q2 "removal" of an earlier rank has no effect
+                const int s = S.order[p];
+                const int first = q2 ? (S.fidx[s] + 1) : (p + 1);    // suppress ranks >= first
+                if (lane < stride) {
+                    const int lo = lane << 5;
+                    uint32_t mask;
+                    if (lo + 31 < first) mask = 0u;
+                    else if (lo >= first) mask = 0xffffffffu;
+                    else mask = 0xffffffffu << (first - lo);
+                    removed |= S.bm[p * stride + lane] & mask;
+                }
+            }
+        }
+        const uint32_t keepw = ~my_act | kept;                    // ranks without edges are kept unconditionally
         int nk = 0;
-        for (int p = 0; p < nok; ++p) {
-            const uint32_t rw = __shfl_sync(0xffffffffu, removed, p >> 5);
-            if ((rw >> (p & 31)) & 1u) continue;                 // warp-uniform
-            const int s = S.order[p];
-            if (ordered_out && lane == 0) out_idx[base + nk] = S.inst[s];
-            ++nk;
-            const int first = q2 ? (S.fidx[s] + 1) : (p + 1);    // suppress ranks >= first
-            if (lane < stride) {
-                const int lo = lane << 5;
-                uint32_t mask;
-                if (lo + 31 < first) mask = 0u;
-                else if (lo >= first) mask = 0xffffffffu;
-                else mask = 0xffffffffu << (first - lo);
-                removed |= S.bm[p * stride + lane] & mask;
+        if (ordered_out) {
+            // survivors in rank order
+            for (int p0 = 0; p0 < nok; p0 += 32) {
+                const int p = p0 + lane;
+                const uint32_t kw = __shfl_sync(0xffffffffu, keepw, p0 >> 5);
+                const int keep = (p < nok) && ((kw >> lane) & 1u);
+                const unsigned bmask = __ballot_sync(0xffffffffu, keep);
+                if (keep) out_idx[base + nk + __popc(bmask & ((1u << lane) - 1u))] = S.inst[S.order[p]];
+                nk += __popc(bmask);
             }
         }
         if (ordered_out) {
@@ -303,8 +333,8 @@ __global__ void __launch_bounds__(EMIA_FUSED_THREADS) k_group_fused(
             for (int k0 = 0; k0 < cap; k0 += 32) {
                 const int k = k0 + lane;
                 const int p = (k < cap) ? S.pos[k] : -1;
-                const uint32_t rw = __shfl_sync(0xffffffffu, removed, (p >= 0 ? p : 0) >> 5);
-                const int keep = (p >= 0) && !((rw >> (p & 31)) & 1u);
+                const uint32_t kw = __shfl_sync(0xffffffffu, keepw, (p >= 0 ? p : 0) >> 5);
+                const int keep = (p >= 0) && ((kw >> (p & 31)) & 1u);
                 const unsigned bmask = __ballot_sync(0xffffffffu, keep);
                 if (keep) out_idx[base + run + __popc(bmask & ((1u << lane) - 1u))] = S.inst[k];
                 run += __popc(bmask);
