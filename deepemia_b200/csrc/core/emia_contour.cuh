@@ -113,6 +113,10 @@ struct EmiaTraceState {
     // step reuses two of the three rows (or all of them) instead of re-loading six words.
     uint32_t wu0, wu1, wm0, wm1, wd0, wd1;
     int wc, wy;
+    // the row that enters the window on a vertical move is loaded when the move is known but rotated in only when the window
+    // is next used (wpend = dy, 0 = nothing pending): nothing depends on the load until then
+    uint32_t wn0, wn1;
+    int wpend;
 };
 #define EMIA_TRACE_SCAN 0
 #define EMIA_TRACE_FOLLOW 1
@@ -125,7 +129,8 @@ EMIA_HD void emia_trace_begin(EmiaTraceState& T) {
     T.y = 0; T.c = 0; T.done_mask = 0u;
     T.x0 = T.y0 = T.x1 = T.y1 = T.x3 = T.y3 = T.s = T.prev_s = 0;
     T.wu0 = T.wu1 = T.wm0 = T.wm1 = T.wd0 = T.wd1 = 0u;
-    T.wc = -2; T.wy = -4;                       // no window yet
+    T.wc = -2; T.wy = -4; T.wpend = 0;          // no window yet
+    T.wn0 = T.wn1 = 0u;
 }
 
 EMIA_HD void emia_win_load_row(const EmiaBitView& v, int ly, int c, uint32_t* w0, uint32_t* w1) {
@@ -136,21 +141,26 @@ EMIA_HD void emia_win_load_row(const EmiaBitView& v, int ly, int c, uint32_t* w0
 }
 // Centre the window on local pixel (x, y); called as soon as the next pixel is known, so that the loads are in flight while the
 // other lanes of the warp take their turn.
+EMIA_HD void emia_win_settle(EmiaTraceState& T) {
+    if (T.wpend == 0) return;
+    const bool down = T.wpend > 0;
+    const uint32_t m0 = T.wm0, m1 = T.wm1;
+    T.wm0 = down ? T.wd0 : T.wu0; T.wm1 = down ? T.wd1 : T.wu1;
+    T.wu0 = down ? m0 : T.wn0;    T.wu1 = down ? m1 : T.wn1;
+    T.wd0 = down ? T.wn0 : m0;    T.wd1 = down ? T.wn1 : m1;
+    T.wpend = 0;
+}
 EMIA_HD void emia_win_move(EmiaTraceState& T, int x, int y) {
+    emia_win_settle(T);
     const int c = (x - 1) >> 5;
     const int dy = y - T.wy;
     if (c == T.wc) {
         if (dy == 0) return;
         if (dy == 1 || dy == -1) {
             // one row enters the window: a single load site for both directions (SIMT: the lanes that moved up and the lanes
-            // that moved down execute it together), the register rotation is a handful of selects
-            uint32_t n0, n1;
-            emia_win_load_row(T.v, y + dy, c, &n0, &n1);
-            const bool down = dy > 0;
-            const uint32_t m0 = T.wm0, m1 = T.wm1;
-            T.wm0 = down ? T.wd0 : T.wu0; T.wm1 = down ? T.wd1 : T.wu1;
-            T.wu0 = down ? m0 : n0;       T.wu1 = down ? m1 : n1;
-            T.wd0 = down ? n0 : m0;       T.wd1 = down ? n1 : m1;
+            // that moved down execute it together)
+            emia_win_load_row(T.v, y + dy, c, &T.wn0, &T.wn1);
+            T.wpend = dy;
             T.wy = y;
             return;
         }
@@ -168,7 +178,8 @@ EMIA_HD uint32_t emia_win_row3(uint32_t w0, uint32_t w1, int sh) {
 #endif
 }
 // 8-bit neighbour mask of the pixel the window is centred on: bit s set <=> the neighbour in direction s is foreground
-EMIA_HD uint32_t emia_win_nbr8(const EmiaTraceState& T, int x) {
+EMIA_HD uint32_t emia_win_nbr8(EmiaTraceState& T, int x) {
+    emia_win_settle(T);
     const int sh = (x - 1) & 31;
     const uint32_t up = emia_win_row3(T.wu0, T.wu1, sh), mid = emia_win_row3(T.wm0, T.wm1, sh), dn = emia_win_row3(T.wd0, T.wd1, sh);
     return ((mid >> 2) & 1u) | (((up >> 2) & 1u) << 1) | (((up >> 1) & 1u) << 2) | ((up & 1u) << 3) | ((mid & 1u) << 4) |
