@@ -572,11 +572,28 @@ def infer_image(predictors, image, num_classes, small_classes, class_specific_se
     return _lists(final)
 
 
+# class colours of the overlay / legend, BGR (src/functions/inference.py:972-981)
+CLASS_COLORS_BGR = [(0, 255, 0), (255, 0, 0), (0, 0, 255), (255, 255, 0), (255, 0, 255), (0, 255, 255), (128, 0, 128), (255, 165, 0)]
+
+
+def write_class_color_legend(output_dir, thing_classes):
+    """class_color_legend.txt as run_inference writes it (src/functions/inference.py:1302-1314): one line per class with the
+    overlay colour converted from BGR to RGB."""
+    path = os.path.join(output_dir, "class_color_legend.txt")
+    with open(path, "w") as f:
+        f.write("Class Color Legend:\n")
+        f.write("==================\n")
+        for i, class_name in enumerate(thing_classes):
+            b, g, r = CLASS_COLORS_BGR[i % len(CLASS_COLORS_BGR)]
+            f.write(f"Class {i} ({class_name}): RGB{(r, g, b)}\n")
+    return path
+
+
 def run_inference(dataset_name, output_dir, visualize=True, threshold=0.65, draw_id=False, dataset_format="json", draw_scalebar=False,
                   *, images=None, predictors=None, thing_classes=None, small_classes=(), scale_bar_fn=None, **infer_kwargs):
     """run_inference (inference.py:499-507) reduced to the hot path: for every (name, BGR image) of `images` run infer_image,
-    write R50_flip_results.csv (ImageId, EncodedPixels) and measurements_results.csv (the 20-column schema of :987-1010) into
-    output_dir.  Model construction, dataset listing, scale-bar OCR and the visualisation overlays are the reference's own
+    write R50_flip_results.csv (ImageId, EncodedPixels), measurements_results.csv (the 20-column schema of :987-1010) and
+    class_color_legend.txt into output_dir.  Model construction, dataset listing, scale-bar OCR and the visualisation overlays are the reference's own
     subsystems (out of scope): the caller passes `predictors`, `images`, and `scale_bar_fn(image) -> (psum, um_pix)`
     (default: ("0", 1.0), the reference's fallback when no scale bar is found)."""
     if images is None or predictors is None:
@@ -605,4 +622,5 @@ def run_inference(dataset_name, output_dir, visualize=True, threshold=0.65, draw
             for row in measure_masks(r["masks"], r["classes"], image.shape, um_pix, name, psum, class_names=thing_classes,
                                      original_image=image):
                 w.writerow(row)
+    write_class_color_legend(output_dir, thing_classes)
     return None
