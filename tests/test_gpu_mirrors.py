@@ -139,6 +139,8 @@ def test_run_inference_writes_reference_csv_schema(cuda_device, tmp_path):
     # every RLE row decodes to a mask whose measurement rows exist
     ids = {r[0].rsplit("_", 1)[0] for r in rows[1:]}
     assert ids <= {"a.png", "b.png"}
+    legend = open(os.path.join(tmp_path, "class_color_legend.txt")).read().splitlines()
+    assert legend[2:] == ["Class 0 (pore): RGB(0, 255, 0)", "Class 1 (throat): RGB(0, 0, 255)"]
 
 
 def test_adaptive_confidence_threshold(cuda_device):
