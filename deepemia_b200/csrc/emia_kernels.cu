@@ -769,3 +769,4 @@ extern "C" int emia_paste_threshold_bitpack(const float* probs, const float* box
 #include "emia_group_kernels.cuh"
 #include "emia_morph_kernels.cuh"
 #include "emia_tile_kernels.cuh"
+#include "emia_flow_kernels.cuh"

@@ -7,7 +7,7 @@
 //   postprocess_masks_universal  src/functions/inference.py:1778-1806 fill -> erode [-> dilate], keep if sum >= min size
 //
 // One warp per instance.  The crop is copied into a padded plane (one extra row above/below, one extra WORD left/right)
-// in a global workspace; lanes own rows.  All operators are word-parallel shifts / AND / OR; fill-holes and the
+// in SHARED memory (global workspace only for masks larger than ~1000 words); lanes own rows.  All operators are word-parallel shifts / AND / OR; fill-holes and the
 // connected-component test are flood fills iterated to a fixed point (row-local run flooding by carry propagation, so the
 // iteration count is the number of direction changes of the longest path, not its length).
 #pragma once
@@ -117,20 +117,55 @@ __device__ void emia_cross_op(const EmiaPad& dst, const EmiaPad& src, int dilate
     __syncwarp();
 }
 
-// ops: up to 4 operator codes.  out crops have the input geometry; area_out/keep are optional.
-__global__ void __launch_bounds__(32) k_morph(const uint32_t* __restrict__ crops, const emia_inst_meta* __restrict__ meta,
-                                              const int64_t* __restrict__ crop_off, int64_t n, int H, int W, int op0, int op1, int op2,
-                                              int op3, const int64_t* __restrict__ pad_off, uint32_t* __restrict__ work,
-                                              const emia_inst_meta* __restrict__ meta_out, const int64_t* __restrict__ crop_off_out,
-                                              uint32_t* __restrict__ crops_out) {
-    const int lane = threadIdx.x;
-    const int64_t inst = blockIdx.x;
+// Planes of one instance: shared memory when a padded plane fits EMIA_MORPH_SMEM_WORDS words (every particle-sized mask does:
+// a 120 x 120-px mask is 122 x 6 = 732 words), else the caller's global workspace at pad_off[inst] (emia_morph_plan counts
+// only those instances).  EMIA_MORPH_WARPS instances per CTA, one warp each, no CTA-wide barrier.
+#define EMIA_MORPH_WARPS 4
+#define EMIA_MORPH_SMEM_WORDS 1024
+#define EMIA_MORPH_SMEM_BYTES (EMIA_MORPH_WARPS * 3 * EMIA_MORPH_SMEM_WORDS * 4)
+
+// bbox / area of a crop-shaped output held in registers across the lanes (called by all 32 lanes)
+struct EmiaStat { int a, ymin, xmin, ymax, xmax; };
+__device__ __forceinline__ void emia_stat_init(EmiaStat& s) { s.a = 0; s.ymin = s.xmin = 0x7fffffff; s.ymax = s.xmax = -1; }
+__device__ __forceinline__ void emia_stat_word(EmiaStat& s, uint32_t w, int y, int xword) {
+    if (!w) return;
+    s.a += __popc(w);
+    s.ymin = min(s.ymin, y); s.ymax = max(s.ymax, y);
+    s.xmin = min(s.xmin, xword * 32 + (__ffs((int)w) - 1));
+    s.xmax = max(s.xmax, xword * 32 + (31 - __clz((int)w)));
+}
+__device__ __forceinline__ void emia_stat_store(EmiaStat s, int lane, int64_t inst, int32_t* bbox, int32_t* area) {
+    for (int o = 16; o > 0; o >>= 1) {
+        s.a += __shfl_xor_sync(0xffffffffu, s.a, o);
+        s.ymin = min(s.ymin, __shfl_xor_sync(0xffffffffu, s.ymin, o)); s.xmin = min(s.xmin, __shfl_xor_sync(0xffffffffu, s.xmin, o));
+        s.ymax = max(s.ymax, __shfl_xor_sync(0xffffffffu, s.ymax, o)); s.xmax = max(s.xmax, __shfl_xor_sync(0xffffffffu, s.xmax, o));
+    }
+    if (lane == 0) {
+        if (area) area[inst] = s.a;
+        if (bbox) ((int4*)bbox)[inst] = s.a > 0 ? make_int4(s.ymin, s.xmin, s.ymax, s.xmax) : make_int4(-1, -1, -1, -1);
+    }
+}
+
+// ops: up to 4 operator codes.  apply (optional): instances with apply[inst] == 0 are copied unchanged (the reference runs
+// process_masks_parallel only on lists of more than two masks, src/functions/inference.py:1443).  bbox_out / area_out
+// (optional): bbox / popcount of the result, so no separate statistics pass is needed.
+__global__ void __launch_bounds__(32 * EMIA_MORPH_WARPS) k_morph(
+    const uint32_t* __restrict__ crops, const emia_inst_meta* __restrict__ meta, const int64_t* __restrict__ crop_off, int64_t n,
+    int H, int W, int op0, int op1, int op2, int op3, const int64_t* __restrict__ pad_off, uint32_t* __restrict__ work,
+    const emia_inst_meta* __restrict__ meta_out, const int64_t* __restrict__ crop_off_out, uint32_t* __restrict__ crops_out,
+    const int32_t* __restrict__ apply, int32_t* __restrict__ bbox_out, int32_t* __restrict__ area_out) {
+    extern __shared__ uint32_t s_planes[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t inst = (int64_t)blockIdx.x * EMIA_MORPH_WARPS + warp;
     if (inst >= n) return;
     const emia_inst_meta m = meta[inst];
-    if (m.ch <= 0 || m.cw <= 0) return;
+    const emia_inst_meta mo = meta_out[inst];
+    EmiaStat st;
+    emia_stat_init(st);
+    if (m.ch <= 0 || m.cw <= 0) { emia_stat_store(st, lane, inst, bbox_out, area_out); return; }
     const int rows = m.ch + 2, words = m.cw + 2;
     const int plane = rows * words;
-    uint32_t* base = work + 3 * pad_off[inst];
+    uint32_t* base = (plane <= EMIA_MORPH_SMEM_WORDS) ? (s_planes + warp * 3 * EMIA_MORPH_SMEM_WORDS) : (work + 3 * pad_off[inst]);
     EmiaPad A{base, rows, words}, B{base + plane, rows, words}, C{base + 2 * plane, rows, words};
     const uint32_t* crop = crops + crop_off[inst];
     for (int k = lane; k < plane; k += 32) {
@@ -142,7 +177,8 @@ __global__ void __launch_bounds__(32) k_morph(const uint32_t* __restrict__ crops
     __syncwarp();
     const int ops[4] = {op0, op1, op2, op3};
     EmiaPad cur = A, other = B;
-    for (int o = 0; o < 4; ++o) {
+    const bool on = (apply == nullptr) || (apply[inst] != 0);
+    for (int o = 0; on && o < 4; ++o) {
         const int op = ops[o];
         if (op == 0) break;
         if (op == EMIA_MORPH_FILL) {
@@ -168,31 +204,38 @@ __global__ void __launch_bounds__(32) k_morph(const uint32_t* __restrict__ crops
     }
     // output geometry: the input's, or (a chain that dilates first) the crop grown by one pixel towards every frame border —
     // out-of-frame neighbours are ignored by the erosion, so a closing can grow a mask that ends one pixel short of the border
-    const emia_inst_meta mo = meta_out[inst];
     uint32_t* out = crops_out + crop_off_out[inst];
     for (int k = lane; k < mo.ch * mo.cw; k += 32) {
         const int r = k / mo.cw, c = k - r * mo.cw;
-        out[k] = emia_pad_at(cur, mo.ry0 + r - (m.ry0 - 1), mo.wc0 + c - (m.wc0 - 1));
+        const uint32_t v = emia_pad_at(cur, mo.ry0 + r - (m.ry0 - 1), mo.wc0 + c - (m.wc0 - 1));
+        out[k] = v;
+        emia_stat_word(st, v, mo.ry0 + r, mo.wc0 + c);
     }
+    emia_stat_store(st, lane, inst, bbox_out, area_out);
 }
 
-// first-come overlap removal + "more than one 8-connected component => zero" (postprocess_masks tail), one warp per instance
-__global__ void __launch_bounds__(32) k_overlap_first_come(const uint32_t* __restrict__ crops, const emia_inst_meta* __restrict__ meta,
-                                                           const int64_t* __restrict__ crop_off, const int32_t* __restrict__ bbox,
-                                                           const int32_t* __restrict__ cap_off, int G, const int32_t* __restrict__ in_len,
-                                                           const int32_t* __restrict__ in_idx, const int64_t* __restrict__ pad_off,
-                                                           uint32_t* __restrict__ work, uint32_t* __restrict__ crops_out) {
-    const int lane = threadIdx.x;
-    const int s = blockIdx.x;                       // list slot
+// first-come overlap removal + "more than one 8-connected component => zero" (postprocess_masks tail), one warp per list slot.
+// The result (and its bbox / area when asked for) is written for list members only.
+__global__ void __launch_bounds__(32 * EMIA_MORPH_WARPS) k_overlap_first_come(
+    const uint32_t* __restrict__ crops, const emia_inst_meta* __restrict__ meta, const int64_t* __restrict__ crop_off,
+    const int32_t* __restrict__ bbox, const int32_t* __restrict__ cap_off, int G, int total_cap, const int32_t* __restrict__ in_len,
+    const int32_t* __restrict__ in_idx, const int64_t* __restrict__ pad_off, uint32_t* __restrict__ work,
+    uint32_t* __restrict__ crops_out, int32_t* __restrict__ bbox_out, int32_t* __restrict__ area_out) {
+    extern __shared__ uint32_t s_planes[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s = blockIdx.x * EMIA_MORPH_WARPS + warp;                       // list slot
+    if (s >= total_cap) return;
     int lo = 0, hi = G;
     while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (cap_off[mid] <= s) lo = mid; else hi = mid; }
     const int g = lo, base = cap_off[g];
     if (s - base >= in_len[g]) return;
     const int inst = in_idx[s];
     const emia_inst_meta m = meta[inst];
-    if (m.ch <= 0 || m.cw <= 0) return;
+    EmiaStat st;
+    emia_stat_init(st);
+    if (m.ch <= 0 || m.cw <= 0) { emia_stat_store(st, lane, inst, bbox_out, area_out); return; }
     const int rows = m.ch + 2, words = m.cw + 2, plane = rows * words;
-    uint32_t* wb = work + 3 * pad_off[inst];
+    uint32_t* wb = (plane <= EMIA_MORPH_SMEM_WORDS) ? (s_planes + warp * 3 * EMIA_MORPH_SMEM_WORDS) : (work + 3 * pad_off[inst]);
     EmiaPad A{wb, rows, words}, R{wb + plane, rows, words};
     const uint32_t* crop = crops + crop_off[inst];
     for (int k = lane; k < plane; k += 32) {
@@ -202,22 +245,34 @@ __global__ void __launch_bounds__(32) k_overlap_first_come(const uint32_t* __res
         A.p[k] = v; R.p[k] = 0u;
     }
     __syncwarp();
-    // remove what earlier list members cover
-    const int* bi = bbox + 4 * inst;
-    for (int k = 0; k < s - base; ++k) {
-        const int j = in_idx[base + k];
-        const int* bj = bbox + 4 * j;
-        if (!emia_bbox_overlap(bi, bj)) continue;
-        const emia_inst_meta mj = meta[j];
-        const uint32_t* cj = crops + crop_off[j];
-        const int r0 = max(m.ry0, mj.ry0), r1 = min(m.ry0 + m.ch, mj.ry0 + mj.ch);
-        const int c0 = max(m.wc0, mj.wc0), c1 = min(m.wc0 + m.cw, mj.wc0 + mj.cw);
-        const int nw = (r1 - r0) * (c1 - c0);
-        for (int t = lane; t < nw; t += 32) {
-            const int r = r0 + t / (c1 - c0), c = c0 + t % (c1 - c0);
-            emia_pad_at(A, r - m.ry0 + 1, c - m.wc0 + 1) &= ~cj[(size_t)(r - mj.ry0) * mj.cw + (c - mj.wc0)];
+    // remove what earlier list members cover: lanes test 32 earlier members' bboxes at once, the warp then ANDs out each hit
+    const int4 bi = ((const int4*)bbox)[inst];
+    const int bia[4] = {bi.x, bi.y, bi.z, bi.w};
+    for (int k0 = 0; k0 < s - base; k0 += 32) {
+        const int k = k0 + lane;
+        int j = -1;
+        if (k < s - base) {
+            j = in_idx[base + k];
+            const int4 bj = ((const int4*)bbox)[j];
+            const int bja[4] = {bj.x, bj.y, bj.z, bj.w};
+            if (!emia_bbox_overlap(bia, bja)) j = -1;
         }
-        __syncwarp();
+        unsigned hits = __ballot_sync(0xffffffffu, j >= 0);
+        while (hits) {
+            const int l = __ffs((int)hits) - 1;
+            hits &= hits - 1u;
+            const int jj = __shfl_sync(0xffffffffu, j, l);
+            const emia_inst_meta mj = meta[jj];
+            const uint32_t* cj = crops + crop_off[jj];
+            const int r0 = max(m.ry0, mj.ry0), r1 = min(m.ry0 + m.ch, mj.ry0 + mj.ch);
+            const int c0 = max(m.wc0, mj.wc0), c1 = min(m.wc0 + m.cw, mj.wc0 + mj.cw);
+            const int nw = (r1 - r0) * (c1 - c0);
+            for (int t = lane; t < nw; t += 32) {
+                const int r = r0 + t / (c1 - c0), c = c0 + t % (c1 - c0);
+                emia_pad_at(A, r - m.ry0 + 1, c - m.wc0 + 1) &= ~cj[(size_t)(r - mj.ry0) * mj.cw + (c - mj.wc0)];
+            }
+            __syncwarp();
+        }
     }
     // seed = first set pixel in raster order
     int first = 0x7fffffff;
@@ -235,8 +290,11 @@ __global__ void __launch_bounds__(32) k_overlap_first_come(const uint32_t* __res
     uint32_t* out = crops_out + crop_off[inst];
     for (int k = lane; k < m.ch * m.cw; k += 32) {
         const int r = k / m.cw, c = k - r * m.cw;
-        out[k] = multi ? 0u : emia_pad_at(A, r + 1, c + 1);
+        const uint32_t v = multi ? 0u : emia_pad_at(A, r + 1, c + 1);
+        out[k] = v;
+        emia_stat_word(st, v, m.ry0 + r, m.wc0 + c);
     }
+    emia_stat_store(st, lane, inst, bbox_out, area_out);
 }
 
 // bbox + area of bit-packed crops (after morphology), one warp per instance
@@ -274,7 +332,8 @@ __global__ void k_morph_plan(const emia_inst_meta* __restrict__ meta, int64_t n,
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const emia_inst_meta m = meta[i];
-    pad_words[i] = (m.ch > 0 && m.cw > 0) ? (int64_t)(m.ch + 2) * (m.cw + 2) : 0;
+    const int64_t plane = (m.ch > 0 && m.cw > 0) ? (int64_t)(m.ch + 2) * (m.cw + 2) : 0;
+    pad_words[i] = plane > EMIA_MORPH_SMEM_WORDS ? plane : 0;     // smaller planes live in shared memory
 }
 // geometry of the result of a chain that may grow the mask by one pixel (see k_morph)
 __global__ void k_morph_grow_plan(const emia_inst_meta* __restrict__ meta, int64_t n, int H, int W, emia_inst_meta* __restrict__ meta_out,
@@ -307,9 +366,18 @@ extern "C" int emia_morph_plan(const emia_inst_meta* meta, int64_t n, int64_t* p
     k_morph_plan<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(meta, n, pad_words);
     return emia_check_launch("emia_morph_plan launch: %s");
 }
+static void emia_morph_smem_attr() {
+    static bool done = false;
+    if (!done) {
+        cudaFuncSetAttribute(k_morph, cudaFuncAttributeMaxDynamicSharedMemorySize, EMIA_MORPH_SMEM_BYTES);
+        cudaFuncSetAttribute(k_overlap_first_come, cudaFuncAttributeMaxDynamicSharedMemorySize, EMIA_MORPH_SMEM_BYTES);
+        done = true;
+    }
+}
 extern "C" int emia_morph(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n, int H, int W,
                           const int32_t* ops_host, int32_t n_ops, const int64_t* pad_off, uint32_t* work,
-                          const emia_inst_meta* meta_out, const int64_t* crop_off_out, uint32_t* crops_out, void* stream) {
+                          const emia_inst_meta* meta_out, const int64_t* crop_off_out, uint32_t* crops_out,
+                          const int32_t* apply_flag, int32_t* bbox_out, int32_t* area_out, void* stream) {
     if (n < 0 || n_ops < 1 || n_ops > 4 || !ops_host) return emia_fail(EMIA_ERR_BAD_ARG, "emia_morph: %s", "bad argument");
     if (n == 0) return EMIA_OK;
     if (!crops || !meta || !crop_off || !pad_off || !work || !crops_out) return emia_fail(EMIA_ERR_BAD_ARG, "emia_morph: %s", "null pointer");
@@ -320,20 +388,24 @@ extern "C" int emia_morph(const uint32_t* crops, const emia_inst_meta* meta, con
         if (ops_host[i] < 1 || ops_host[i] > 3) return emia_fail(EMIA_ERR_BAD_ARG, "emia_morph: %s", "unknown operator");
         ops[i] = ops_host[i];
     }
-    k_morph<<<(unsigned)n, 32, 0, (cudaStream_t)stream>>>(crops, meta, crop_off, n, H, W, ops[0], ops[1], ops[2], ops[3], pad_off, work,
-                                                          meta_out, crop_off_out, crops_out);
+    emia_morph_smem_attr();
+    k_morph<<<(unsigned)((n + EMIA_MORPH_WARPS - 1) / EMIA_MORPH_WARPS), 32 * EMIA_MORPH_WARPS, EMIA_MORPH_SMEM_BYTES, (cudaStream_t)stream>>>(
+        crops, meta, crop_off, n, H, W, ops[0], ops[1], ops[2], ops[3], pad_off, work, meta_out, crop_off_out, crops_out, apply_flag,
+        bbox_out, area_out);
     return emia_check_launch("emia_morph launch: %s");
 }
 extern "C" int emia_overlap_first_come(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, const int32_t* bbox,
                                        const int32_t* cap_off, int32_t G, int32_t total_cap, const int32_t* in_len,
                                        const int32_t* in_idx, const int64_t* pad_off, uint32_t* work, uint32_t* crops_out,
-                                       void* stream) {
+                                       int32_t* bbox_out, int32_t* area_out, void* stream) {
     if (G < 0 || total_cap < 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_overlap_first_come: %s", "bad argument");
     if (G == 0 || total_cap == 0) return EMIA_OK;
     if (!crops || !meta || !crop_off || !bbox || !cap_off || !in_len || !in_idx || !pad_off || !work || !crops_out)
         return emia_fail(EMIA_ERR_BAD_ARG, "emia_overlap_first_come: %s", "null pointer");
-    k_overlap_first_come<<<(unsigned)total_cap, 32, 0, (cudaStream_t)stream>>>(crops, meta, crop_off, bbox, cap_off, G, in_len, in_idx, pad_off,
-                                                                            work, crops_out);
+    emia_morph_smem_attr();
+    k_overlap_first_come<<<(unsigned)((total_cap + EMIA_MORPH_WARPS - 1) / EMIA_MORPH_WARPS), 32 * EMIA_MORPH_WARPS, EMIA_MORPH_SMEM_BYTES,
+                           (cudaStream_t)stream>>>(crops, meta, crop_off, bbox, cap_off, G, total_cap, in_len, in_idx, pad_off, work,
+                                                   crops_out, bbox_out, area_out);
     return emia_check_launch("emia_overlap_first_come launch: %s");
 }
 extern "C" int emia_crop_stats(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n, int32_t* bbox,

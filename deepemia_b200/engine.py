@@ -3,6 +3,7 @@
 PyTorch is used only for device memory, streams and (in bench.py) torch.distributed; every computation on the path is
 a kernel of libemia.so called through the C ABI (include/emia.h) with raw tensor pointers.
 """
+import math
 from dataclasses import dataclass, field
 from typing import Optional
 
@@ -76,6 +77,64 @@ def exclusive_scan_(t):
     _lib.check(lib.emia_exclusive_scan_i64(_ptr(t), n, _ptr(ws), nb, _stream()), "emia_exclusive_scan_i64")
     LAUNCHES["count"] += 3
     return t
+
+
+class Arena:
+    """Capacities of the variable-size device buffers of a flow (crop words, contour vertices, records, ...).
+
+    A flow is enqueued WITHOUT reading any size back: every variable-size output goes into a buffer of the arena's current
+    capacity, a device-side guard (emia_capacity_guard) compares the real total with it, and on overflow raises the abort
+    flag and empties the geometry of the affected instance set, so that no later kernel touches memory outside the buffers.
+    finish() is the one host synchronisation of a run: it reads the flag and the recorded totals, grows the capacities that
+    were too small and tells the caller to run again.  Capacities only grow, in 25 % steps: shards of similar size keep
+    running sync-free whatever their exact instance counts are."""
+
+    def __init__(self, device, margin=1.25):
+        self.dev = torch.device(device)
+        self.margin = margin
+        self.caps = {}
+        self.abort = None
+        self._totals = []
+        self.runs = 0
+        self.aborts = 0
+
+    def begin(self):
+        self.abort = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self._totals = []
+        self.runs += 1
+        return self.abort
+
+    def cap(self, name, default):
+        c = self.caps.get(name)
+        if c is None or c < 1:
+            c = max(int(default), 1)
+            self.caps[name] = c
+        return c
+
+    def guard(self, name, total, poison_meta=None, poison_n=0):
+        """total: int64 device tensor view of ONE element (e.g. crop_off[n:]).  Enqueues the device-side check."""
+        lib = _lib.load()
+        cap = self.caps[name]
+        _lib.check(lib.emia_capacity_guard(_ptr(total), cap, _ptr(self.abort), _ptr(poison_meta), int(poison_n), _stream()),
+                   "emia_capacity_guard")
+        LAUNCHES["count"] += 1
+        self._totals.append((name, total))
+
+    def finish(self):
+        """One host synchronisation: True when the run is valid; False when a guard tripped (capacities grown: run again)."""
+        vals = torch.cat([self.abort.to(torch.int64)] + [t.reshape(-1)[:1] for _, t in self._totals]).tolist()
+        if not vals[0]:
+            return True
+        self.aborts += 1
+        grown = False
+        for (name, _), v in zip(self._totals, vals[1:]):
+            if v > self.caps[name]:
+                self.caps[name] = int(v * self.margin) + 64
+                grown = True
+        if not grown:       # the flag came from a kernel-side overflow (contour slab): give everything more room
+            for k in self.caps:
+                self.caps[k] = int(self.caps[k] * 2)
+        return False
 
 
 @dataclass
@@ -216,8 +275,9 @@ def unpack_masks(iset, idx=None):
 MORPH_FILL, MORPH_ERODE, MORPH_DILATE = 1, 2, 3
 
 
-def _pad_plan(iset):
-    """Padded-plane offsets ((ch+2) x (cw+2) words per instance) and the 3-plane work buffer of the K2 kernels."""
+def _pad_plan(iset, arena=None, tag="k2"):
+    """Global work planes of the K2 kernels: only instances whose padded plane exceeds 1024 words need them (the others use
+    shared memory), so the buffer is usually empty.  With an arena nothing is read back (capacity + device-side guard)."""
     cached = iset.extra.get("pad_plan")
     if cached is not None:
         return cached
@@ -226,22 +286,27 @@ def _pad_plan(iset):
     _lib.check(lib.emia_morph_plan(_ptr(iset.meta), iset.n, _ptr(pad_off), _stream()), "emia_morph_plan")
     exclusive_scan_(pad_off)
     LAUNCHES["count"] += 1
-    total = int(pad_off[iset.n].item()) if iset.n else 0
+    if arena is not None:
+        total = arena.cap(tag + ".work", 1 << 18)
+        arena.guard(tag + ".work", pad_off[iset.n:], iset.meta, iset.n)
+    else:
+        total = int(pad_off[iset.n].item()) if iset.n else 0
     work = torch.empty(max(3 * total, 1), dtype=torch.int32, device=iset.device)
     iset.extra["pad_plan"] = (pad_off, work)
     return pad_off, work
 
 
-def _derived(iset, crops, geometry=None):
+def _derived(iset, crops, geometry=None, bbox=None, area=None):
     """A new InstanceSet with new crop bits in the geometry (meta, crop_off, total words) of `iset` or the given one; bbox/area
-    recomputed."""
+    as computed by the producing kernel, or recomputed here."""
     lib = _lib.load()
     meta, crop_off, total = geometry if geometry is not None else (iset.meta, iset.crop_off, iset.total_crop_words)
-    bbox = torch.empty_like(iset.bbox)
-    area = torch.empty_like(iset.area)
-    _lib.check(lib.emia_crop_stats(_ptr(crops), _ptr(meta), _ptr(crop_off), iset.n, _ptr(bbox), _ptr(area), _stream()),
-               "emia_crop_stats")
-    LAUNCHES["count"] += 1
+    if bbox is None:
+        bbox = torch.empty_like(iset.bbox)
+        area = torch.empty_like(iset.area)
+        _lib.check(lib.emia_crop_stats(_ptr(crops), _ptr(meta), _ptr(crop_off), iset.n, _ptr(bbox), _ptr(area), _stream()),
+                   "emia_crop_stats")
+        LAUNCHES["count"] += 1
     out = InstanceSet(n=iset.n, H=iset.H, W=iset.W, meta=meta, crop_off=crop_off, crops=crops, bbox=bbox, area=area,
                       scores=iset.scores, classes=iset.classes, total_crop_words=total)
     if geometry is None and "pad_plan" in iset.extra:
@@ -249,12 +314,13 @@ def _derived(iset, crops, geometry=None):
     return out
 
 
-def morph(iset, ops):
-    """K2: apply `ops` (MORPH_FILL / MORPH_ERODE / MORPH_DILATE, 3x3 cross, at most 4) to every instance.  The result has
-    the geometry of the input (every chain the reference uses — closing, opening, erosion — stays inside the crop)."""
+def morph(iset, ops, apply=None, arena=None, tag="k2"):
+    """K2: apply `ops` (MORPH_FILL / MORPH_ERODE / MORPH_DILATE, 3x3 cross, at most 4) to every instance (apply: optional int32
+    flag per instance, 0 = pass through unchanged).  The result has the geometry of the input, or — a chain that dilates
+    first — the crop grown by one pixel.  bbox / area of the result come from the same kernel.  With an arena: no host sync."""
     lib = _lib.load()
     ops = np.ascontiguousarray(ops, dtype=np.int32)
-    pad_off, work = _pad_plan(iset)
+    pad_off, work = _pad_plan(iset, arena, tag)
     structuring = [int(o) for o in ops if int(o) != MORPH_FILL]
     grows = bool(structuring) and structuring[0] == MORPH_DILATE
     geometry = None
@@ -267,41 +333,53 @@ def morph(iset, ops):
                    "emia_morph_grow_plan")
         exclusive_scan_(crop_off_out)
         LAUNCHES["count"] += 1
-        total = int(crop_off_out[iset.n].item())
+        if arena is not None:
+            total = arena.cap(tag + ".grown", int(iset.total_crop_words * 1.5) + 4 * iset.n + 1024)
+            arena.guard(tag + ".grown", crop_off_out[iset.n:], meta_out, iset.n)
+        else:
+            total = int(crop_off_out[iset.n].item())
         geometry = (meta_out, crop_off_out, total)
         crops = torch.empty(max(total, 1), dtype=torch.int32, device=iset.device)
     else:
         crops = torch.empty_like(iset.crops)
+    bbox = torch.empty_like(iset.bbox)
+    area = torch.empty_like(iset.area)
     if iset.n:
         with _stage("k2_morph"):
             _lib.check(lib.emia_morph(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), iset.n, iset.H, iset.W, ops.ctypes.data,
-                                      len(ops), _ptr(pad_off), _ptr(work), _ptr(meta_out), _ptr(crop_off_out), _ptr(crops), _stream()),
-                       "emia_morph")
+                                      len(ops), _ptr(pad_off), _ptr(work), _ptr(meta_out), _ptr(crop_off_out), _ptr(crops),
+                                      _ptr(apply), _ptr(bbox), _ptr(area), _stream()), "emia_morph")
         LAUNCHES["count"] += 1
-    return _derived(iset, crops, geometry)
+    return _derived(iset, crops, geometry, bbox, area)
 
 
-def overlap_first_come(iset, groups):
+def overlap_first_come(iset, groups, arena=None, tag="k2"):
     """Tail of postprocess_masks (src/utils/mask_utils.py:77-82): list member k loses the pixels earlier members cover, then is
-    zeroed if it has more than one 8-connected component.  Members keep their list position (Q6)."""
+    zeroed if it has more than one 8-connected component.  Members keep their list position (Q6); instances outside the
+    lists are unchanged."""
     lib = _lib.load()
-    pad_off, work = _pad_plan(iset)
+    pad_off, work = _pad_plan(iset, arena, tag)
     crops = iset.crops.clone()
+    bbox = iset.bbox.clone()
+    area = iset.area.clone()
     if iset.n and groups.total_cap:
         with _stage("k2_overlap_first_come"):
             _lib.check(lib.emia_overlap_first_come(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), _ptr(iset.bbox),
                                                    _ptr(groups.cap_off), groups.G, groups.total_cap, _ptr(groups.length),
-                                                   _ptr(groups.idx), _ptr(pad_off), _ptr(work), _ptr(crops), _stream()),
+                                                   _ptr(groups.idx), _ptr(pad_off), _ptr(work), _ptr(crops), _ptr(bbox), _ptr(area),
+                                                   _stream()),
                        "emia_overlap_first_come")
         LAUNCHES["count"] += 1
-    return _derived(iset, crops)
+    return _derived(iset, crops, None, bbox, area)
 
 
-def filter_area(iset, groups, min_area):
+def filter_area(iset, groups, min_area, out=None):
+    """List members with area >= min_area (`np.sum(final_mask) >= min_crys_size`, src/functions/inference.py:1800).  Areas are
+    integers, so a fractional threshold is rounded UP (area >= 5.5 <=> area >= 6)."""
     lib = _lib.load()
-    out = _new_groups_like(groups)
+    out = out if out is not None else _new_groups_like(groups)
     _lib.check(lib.emia_group_filter_area(_ptr(groups.cap_off), groups.G, _ptr(groups.length), _ptr(groups.idx), _ptr(iset.area),
-                                          int(min_area), _ptr(out.length), _ptr(out.idx), _stream()), "emia_group_filter_area")
+                                          int(math.ceil(min_area)), _ptr(out.length), _ptr(out.idx), _stream()), "emia_group_filter_area")
     LAUNCHES["count"] += 1
     return out
 
@@ -309,33 +387,61 @@ def filter_area(iset, groups, min_area):
 def column_gate(iset, groups, min_size):
     lib = _lib.load()
     out = _new_groups_like(groups)
+    # `column total > min_size` on integers: a fractional threshold is rounded DOWN (total > 5.5 <=> total > 5)
     _lib.check(lib.emia_column_gate(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), _ptr(groups.cap_off), groups.G,
-                                    _ptr(groups.length), _ptr(groups.idx), iset.W, int(min_size), _ptr(out.length), _ptr(out.idx),
+                                    _ptr(groups.length), _ptr(groups.idx), iset.W, int(math.floor(min_size)), _ptr(out.length), _ptr(out.idx),
                                     _stream()), "emia_column_gate")
     LAUNCHES["count"] += 1
     return out
 
 
-def postprocess_masks(iset, groups, min_crys_size=2):
+def filter_heads(iset, groups, target_class, min_score, zero_score_empties=False, out=None):
+    """The class / confidence filter of the flows (src/functions/inference.py:1411-1420, :1519-1523, :2146-2151) on every list:
+    members that survived Boxes.nonempty(), have class == target_class (None: any) and score >= min_score (float32 compare, as
+    numpy does for a float32 array against a Python float).  zero_score_empties: postprocess_masks' `ori_score.all() < 0.5`
+    early exit (src/utils/mask_utils.py:59) — a list that still holds a score of exactly 0 becomes empty."""
+    lib = _lib.load()
+    out = out if out is not None else _new_groups_like(groups)
+    _lib.check(lib.emia_group_filter_heads(_ptr(groups.cap_off), groups.G, _ptr(groups.length), _ptr(groups.idx), _ptr(iset.meta),
+                                           _ptr(iset.classes), _ptr(iset.scores), -1 if target_class is None else int(target_class),
+                                           float(np.float32(min_score)), 1 if zero_score_empties else 0, _ptr(out.length), _ptr(out.idx),
+                                           _stream()), "emia_group_filter_heads")
+    LAUNCHES["count"] += 1
+    return out
+
+
+def mark_members(iset, groups, min_len):
+    """int32 [n] flag: 1 for the members of lists longer than min_len (the `len(processed_masks) > 2` gate of
+    process_masks_parallel, src/functions/inference.py:1443)."""
+    lib = _lib.load()
+    flag = torch.empty(max(iset.n, 1), dtype=torch.int32, device=iset.device)
+    _lib.check(lib.emia_group_mark_members(_ptr(groups.cap_off), groups.G, groups.total_cap, _ptr(groups.length), _ptr(groups.idx),
+                                           int(min_len), _ptr(flag), iset.n, _stream()), "emia_group_mark_members")
+    LAUNCHES["count"] += 2
+    return flag
+
+
+def postprocess_masks(iset, groups, min_crys_size=2, arena=None, tag="k2"):
     """postprocess_masks (src/utils/mask_utils.py:38-84) on every group: column gate (Q5) -> fill holes -> closing ->
     first-come overlap removal -> multi-component masks zeroed (kept in the list, Q6).  Returns (InstanceSet, Groups)."""
     gated = column_gate(iset, groups, min_crys_size)
-    closed = morph(iset, [MORPH_FILL, MORPH_DILATE, MORPH_ERODE])
-    return overlap_first_come(closed, gated), gated
+    closed = morph(iset, [MORPH_FILL, MORPH_DILATE, MORPH_ERODE], arena=arena, tag=tag + ".close")
+    return overlap_first_come(closed, gated, arena=arena, tag=tag + ".ofc"), gated
 
 
-def process_masks_parallel(iset):
+def process_masks_parallel(iset, apply=None, arena=None, tag="k2"):
     """process_masks_parallel (src/functions/inference.py:170-213): fill holes -> erosion(disk 1) -> dilation(disk 1)."""
-    return morph(iset, [MORPH_FILL, MORPH_ERODE, MORPH_DILATE])
+    return morph(iset, [MORPH_FILL, MORPH_ERODE, MORPH_DILATE], apply=apply, arena=arena, tag=tag + ".open")
 
 
-def postprocess_masks_universal(iset, groups, is_small_class, min_crys_size=None):
+def postprocess_masks_universal(iset, groups, is_small_class, min_crys_size=None, arena=None, tag="k2", out=None):
     """postprocess_masks_universal (src/functions/inference.py:1739-1813).  Returns (InstanceSet, Groups of survivors)."""
     if min_crys_size is None:
         a = iset.H * iset.W
         min_crys_size = max(3, int(a * 0.000005)) if is_small_class else max(25, int(a * 0.0001))
-    out = morph(iset, [MORPH_FILL, MORPH_ERODE] if is_small_class else [MORPH_FILL, MORPH_ERODE, MORPH_DILATE])
-    return out, filter_area(out, groups, min_crys_size)
+    res = morph(iset, [MORPH_FILL, MORPH_ERODE] if is_small_class else [MORPH_FILL, MORPH_ERODE, MORPH_DILATE], arena=arena,
+                tag=tag + ".univ")
+    return res, filter_area(res, groups, min_crys_size, out=out)
 
 
 CAP_CONTOURS = 8   # contours per instance held by the single-pass slab layout
@@ -368,6 +474,11 @@ def trace(iset, single_pass=True, marks=None, abort=None):
         if cap_total is None:
             # capacity is a pure function of the crop sizes: 4 * (sum ch + 32 * sum cw) + 32 * n_live
             cap_total = int(sizes[1, n].item())
+        elif abort is not None:
+            # sync-free: the caller sized the vertex buffer; the device checks it and the trace kernel honours the flag
+            _lib.check(lib.emia_capacity_guard(_ptr(sizes[1, n:]), int(cap_total), _ptr(abort), 0, 0, st), "emia_capacity_guard")
+            LAUNCHES["count"] += 1
+            iset.extra["pt_total"] = sizes[1, n:]
         pts = torch.empty(max(cap_total, 1), dtype=torch.int32, device=dev)
         cstart = torch.empty(n * (CAP_CONTOURS + 1) + 1, dtype=torch.int32, device=dev)
         with _stage("k5_trace"):
@@ -456,10 +567,12 @@ def measure_list(iset, groups, um_pix=1.0, min_area=None, capacity=None, abort=N
     flag = iset.extra.get("overflow")
     if capacity is not None:
         n_rec, n_scr = int(capacity[0]), int(capacity[1])
-        over = (offs[0, L] > n_rec) | (offs[1, L] > n_scr)
+        # device-side checks, stream-ordered before the kernels that honour the flag (a slab overflow of the trace counts too)
+        _lib.check(lib.emia_capacity_guard(_ptr(offs[0, L:]), n_rec, _ptr(abort), 0, 0, st), "emia_capacity_guard")
+        _lib.check(lib.emia_capacity_guard(_ptr(offs[1, L:]), n_scr, _ptr(abort), 0, 0, st), "emia_capacity_guard")
+        LAUNCHES["count"] += 2
         if flag is not None:
-            over = over | (flag[0] != 0)
-        abort.logical_or_(over)          # int32 flag, stays 0 / 1; stream-ordered before the kernels that honour it
+            abort.logical_or_(flag)
     else:
         tot = torch.stack([offs[0, L], offs[1, L], flag[0].to(torch.int64) if flag is not None else offs[0, 0]]).tolist()
         n_rec, n_scr, overflow = int(tot[0]), int(tot[1]), int(tot[2])
@@ -605,6 +718,89 @@ def groups_from_lists(lists, device):
                   idx=torch.as_tensor(flat, device=device))
 
 
+class GroupSpace:
+    """One (length, idx) allocation shared by several SECTIONS of groups (e.g. the full-image lists and the tile lists of a
+    batch).  Each section is an ordinary Groups object over views of the shared arrays, so the last kernel of a flow stage can
+    write its surviving lists straight into the space, and flatten() can then concatenate lists of different sections
+    (`full_image_masks + all_tile_masks`, src/functions/inference.py:2452) without moving any instance data."""
+
+    def __init__(self, section_caps, device):
+        self.dev = torch.device(device)
+        caps = [np.asarray(c, dtype=np.int64).reshape(-1) for c in section_caps]
+        self.g0 = np.concatenate([[0], np.cumsum([len(c) for c in caps])]).astype(np.int64)
+        allc = np.concatenate(caps) if caps else np.zeros(0, np.int64)
+        self.cap_abs = np.concatenate([[0], np.cumsum(allc)]).astype(np.int32)
+        G, L = len(allc), int(self.cap_abs[-1])
+        self.length = torch.zeros(max(G, 1), dtype=torch.int32, device=self.dev)
+        self.idx = torch.empty(max(L, 1), dtype=torch.int32, device=self.dev)
+        self.cap_off = torch.as_tensor(self.cap_abs, device=self.dev)
+        self._sections = {}
+
+    def fresh(self):
+        """The same layout with new (length, idx) arrays (a new run of the flow); the device offset tables are shared."""
+        o = object.__new__(GroupSpace)
+        o.dev, o.g0, o.cap_abs, o.cap_off = self.dev, self.g0, self.cap_abs, self.cap_off
+        o.length = torch.zeros_like(self.length)
+        o.idx = torch.empty_like(self.idx)
+        o._sections = {}
+        o._rebased = self._rebased_tables()
+        return o
+
+    def _rebased_tables(self):
+        r = getattr(self, "_rebased", None)
+        if r is None:
+            r = {}
+            self._rebased = r
+        return r
+
+    def section(self, k):
+        sec = self._sections.get(k)
+        if sec is None:
+            a, b = int(self.g0[k]), int(self.g0[k + 1])
+            l0, l1 = int(self.cap_abs[a]), int(self.cap_abs[b])
+            host = (self.cap_abs[a:b + 1] - self.cap_abs[a]).astype(np.int32)
+            tabs = self._rebased_tables()
+            dev_tab = tabs.get(k)
+            if dev_tab is None:
+                dev_tab = torch.as_tensor(host, device=self.dev)
+                tabs[k] = dev_tab
+            sec = Groups(cap_off_host=host, cap_off=dev_tab, length=self.length[a:max(b, a + 1)] if b > a else self.length[a:a],
+                         idx=self.idx[l0:max(l1, l0 + 1)] if l1 > l0 else self.idx[l0:l0])
+            self._sections[k] = sec
+        return sec
+
+    def group_index(self, k, j=0):
+        return int(self.g0[k]) + j
+
+
+def flatten(space, grp_lists, id_add=None, cache=None):
+    """New Groups with one list per entry of grp_lists: list s = the members of the space's groups grp_lists[s] (global group
+    indices, in that order) one after the other.  id_add: per group of the space, added to its member ids (host int array)."""
+    lib = _lib.load()
+    dev = space.dev
+    key = None if cache is None else "flatten"
+    tabs = None if cache is None else cache.get(key)
+    if tabs is None:
+        seg = np.zeros(len(grp_lists) + 1, np.int32)
+        seg[1:] = np.cumsum([len(g) for g in grp_lists])
+        flat = np.concatenate([np.asarray(g, np.int32) for g in grp_lists]) if seg[-1] else np.zeros(1, np.int32)
+        caps = np.array([int(sum(int(space.cap_abs[g + 1] - space.cap_abs[g]) for g in gl)) for gl in grp_lists], np.int64)
+        out_off = np.concatenate([[0], np.cumsum(caps)]).astype(np.int32)
+        tabs = (seg, torch.as_tensor(seg, device=dev), torch.as_tensor(flat, device=dev), out_off, torch.as_tensor(out_off, device=dev),
+                None if id_add is None else torch.as_tensor(np.asarray(id_add, np.int32), device=dev))
+        if cache is not None:
+            cache[key] = tabs
+    seg, seg_t, flat_t, out_off, out_off_t, add_t = tabs
+    S = len(seg) - 1
+    out = Groups(cap_off_host=out_off, cap_off=out_off_t, length=torch.empty(max(S, 1), dtype=torch.int32, device=dev),
+                 idx=torch.empty(max(int(out_off[-1]), 1), dtype=torch.int32, device=dev))
+    _lib.check(lib.emia_group_flatten(_ptr(space.cap_off), len(space.cap_abs) - 1, _ptr(space.length), _ptr(space.idx), _ptr(flat_t),
+                                      _ptr(seg_t), S, _ptr(add_t), _ptr(out_off_t), _ptr(out.length), _ptr(out.idx), _stream()),
+               "emia_group_flatten")
+    LAUNCHES["count"] += 1
+    return out
+
+
 _ws_cache = {}
 
 
@@ -625,12 +821,12 @@ def _new_groups_like(g):
     return Groups(cap_off_host=g.cap_off_host, cap_off=g.cap_off, length=torch.empty_like(g.length), idx=torch.empty_like(g.idx))
 
 
-def dedup_smart(iset, groups, iou_threshold=0.4, max_aspect_ratio=None):
+def dedup_smart(iset, groups, iou_threshold=0.4, max_aspect_ratio=None, out=None):
     """deduplicate_masks_smart (src/functions/inference.py:2552) on every group.  Needs measure() first (compactness)."""
     lib = _lib.load()
     assert iset.perim0 is not None, "run trace() before dedup_smart (the pre-filter needs contour perimeters)"
     ws, nb = _workspace(groups, iset.device)
-    out = _new_groups_like(groups)
+    out = out if out is not None else _new_groups_like(groups)
     ncont = iset.extra["n_contours"]
     with _stage("k4_dedup_smart"):
       _lib.check(lib.emia_dedup_smart(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), _ptr(iset.bbox), _ptr(iset.area),
@@ -642,11 +838,11 @@ def dedup_smart(iset, groups, iou_threshold=0.4, max_aspect_ratio=None):
     return out
 
 
-def dedup_inorder(iset, groups, iou_threshold):
+def dedup_inorder(iset, groups, iou_threshold, out=None):
     """Greedy in-order de-dup with iou() (src/functions/inference.py:1453-1459)."""
     lib = _lib.load()
     ws, nb = _workspace(groups, iset.device)
-    out = _new_groups_like(groups)
+    out = out if out is not None else _new_groups_like(groups)
     _lib.check(lib.emia_dedup_inorder(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), _ptr(iset.bbox), _ptr(iset.area),
                                       _ptr(groups.cap_off), groups.G, groups.total_cap, groups.fused_cap, _ptr(groups.length), _ptr(groups.idx),
                                       float(iou_threshold), _ptr(out.length), _ptr(out.idx), _ptr(ws), nb, _stream()),
@@ -655,11 +851,11 @@ def dedup_inorder(iset, groups, iou_threshold):
     return out
 
 
-def dedup_sorted(iset, groups, iou_threshold):
+def dedup_sorted(iset, groups, iou_threshold, out=None):
     """Score-sorted greedy de-dup with iou() (run_adaptive_multiscale_inference, src/functions/inference.py:1964-1978)."""
     lib = _lib.load()
     ws, nb = _workspace(groups, iset.device)
-    out = _new_groups_like(groups)
+    out = out if out is not None else _new_groups_like(groups)
     _lib.check(lib.emia_dedup_sorted(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), _ptr(iset.bbox), _ptr(iset.area),
                                      _ptr(iset.scores), _ptr(groups.cap_off), groups.G, groups.total_cap, groups.fused_cap,
                                      _ptr(groups.length), _ptr(groups.idx), float(iou_threshold), _ptr(out.length), _ptr(out.idx),
@@ -668,10 +864,10 @@ def dedup_sorted(iset, groups, iou_threshold):
     return out
 
 
-def filter_flag(groups, flag, keep_value=0):
+def filter_flag(groups, flag, keep_value=0, out=None):
     """List members whose flag[inst] == keep_value (e.g. the edge filter of the tile pipeline)."""
     lib = _lib.load()
-    out = _new_groups_like(groups)
+    out = out if out is not None else _new_groups_like(groups)
     _lib.check(lib.emia_group_filter_flag(_ptr(groups.cap_off), groups.G, _ptr(groups.length), _ptr(groups.idx), _ptr(flag),
                                           int(keep_value), _ptr(out.length), _ptr(out.idx), _stream()), "emia_group_filter_flag")
     LAUNCHES["count"] += 1
@@ -712,6 +908,98 @@ def resize_place(iset, th, tw, Hd, Wd, off_xy=None, tile_size=None, overlap_rati
     out = InstanceSet(n=n, H=Hd, W=Wd, meta=meta, crop_off=crop_off, crops=crops, bbox=bbox, area=area, scores=iset.scores,
                       classes=iset.classes, total_crop_words=total)
     return out, edge
+
+
+class Combined:
+    """A destination InstanceSet assembled by K3 from several source sets (the full-image pass and every tile of a micrograph;
+    every scale of a multi-scale pass; every model of an ensemble), all back-projected into ONE H x W frame.  The reference
+    allocates one full-frame array per instance for this (src/functions/inference.py:2413); here every part writes its
+    word-aligned crops into a slice of shared arrays: plan all parts -> one scan -> (guarded) crop buffer -> place all parts.
+    Part p owns the instance ids [start[p], start[p + 1])."""
+
+    def __init__(self, part_sizes, H, W, device):
+        dev = torch.device(device)
+        self.H, self.W, self.dev = H, W, dev
+        self.start = np.concatenate([[0], np.cumsum(part_sizes)]).astype(np.int64)
+        n = int(self.start[-1])
+        self.n = n
+        self.meta = torch.empty((n, 8), dtype=torch.int32, device=dev)
+        self.crop_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        self.bbox = torch.empty((n, 4), dtype=torch.int32, device=dev)
+        self.area = torch.empty(n, dtype=torch.int32, device=dev)
+        self.scores = torch.empty(n, dtype=torch.float32, device=dev)
+        self.classes = torch.empty(n, dtype=torch.int32, device=dev)
+        self.edge = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
+        self.crops = None
+        self.total = 0
+        self._parts = []
+
+    def plan(self, p, src, th, tw, off_xy=None):
+        """Part p <- cv2.resize(mask, (tw, th), INTER_NEAREST) of every instance of `src`, placed at off_xy[i] (int32 [n,2] device
+        tensor of (x, y) offsets, or None).  Only the geometry is computed here."""
+        lib = _lib.load()
+        a, b = int(self.start[p]), int(self.start[p + 1])
+        assert b - a == src.n
+        if src.n:
+            _lib.check(lib.emia_resize_place_plan(_ptr(src.bbox), src.n, src.H, src.W, th, tw, _ptr(off_xy), self.H, self.W,
+                                                  _ptr(self.meta[a:]), _ptr(self.crop_off[a:]), _stream()), "emia_resize_place_plan")
+            LAUNCHES["count"] += 1
+        self._parts.append((p, src, th, tw, off_xy))
+
+    def place(self, arena=None, tag="k3", edge=None):
+        """Scan the crop sizes of all planned parts, size the crop buffer (exactly, or arena capacity + device-side guard) and
+        run the placement kernels.  edge: {part: (tile_size, overlap_ratio)} -> is_edge_mask flags in self.edge."""
+        lib = _lib.load()
+        n = self.n
+        exclusive_scan_(self.crop_off)
+        if arena is not None:
+            total = arena.cap(tag + ".crops", sum(int(src.total_crop_words) for _, src, _, _, _ in self._parts) + 64 * n + 1024)
+            arena.guard(tag + ".crops", self.crop_off[n:], self.meta, n)
+        else:
+            total = int(self.crop_off[n].item()) if n else 0
+        self.total = total
+        self.crops = torch.empty(max(total, 1), dtype=torch.int32, device=self.dev)
+        st = _stream()
+        for p, src, th, tw, off_xy in self._parts:
+            a = int(self.start[p])
+            if not src.n:
+                continue
+            ew = ts = 0
+            ef = None
+            if edge and p in edge:
+                ts = int(edge[p][0])
+                ew = int(edge[p][0] * edge[p][1] / 2)
+                ef = self.edge[a:]
+            with _stage("k3_resize_place"):
+                _lib.check(lib.emia_resize_nearest_place(_ptr(src.crops), _ptr(src.meta), _ptr(src.crop_off), _ptr(src.bbox), src.n, src.H,
+                                                         src.W, th, tw, _ptr(off_xy), self.H, self.W, ew, ts, _ptr(self.meta[a:]),
+                                                         _ptr(self.crop_off[a:]), _ptr(self.crops), _ptr(self.bbox[a:]), _ptr(self.area[a:]),
+                                                         _ptr(ef), st), "emia_resize_nearest_place")
+            LAUNCHES["count"] += 1
+            if src.scores is not None:
+                self.scores[a:a + src.n].copy_(src.scores)
+            if src.classes is not None:
+                self.classes[a:a + src.n].copy_(src.classes)
+        return InstanceSet(n=n, H=self.H, W=self.W, meta=self.meta, crop_off=self.crop_off, crops=self.crops, bbox=self.bbox,
+                           area=self.area, scores=self.scores, classes=self.classes, total_crop_words=total)
+
+
+def unit_broadcast(unit_off_t, U, n, vals_t, k):
+    """int32 [n, k]: the per-unit constants vals_t [U, k] expanded to the instances of every unit (device)."""
+    lib = _lib.load()
+    out = torch.empty((max(n, 1), k), dtype=torch.int32, device=vals_t.device)
+    _lib.check(lib.emia_unit_broadcast_i32(_ptr(unit_off_t), U, n, _ptr(vals_t), k, _ptr(out), _stream()), "emia_unit_broadcast_i32")
+    LAUNCHES["count"] += 1
+    return out
+
+
+def scale_scores(scores, weight, out=None):
+    """score * weight in float32 (run_ensemble_inference, src/functions/inference.py:1553)."""
+    lib = _lib.load()
+    out = out if out is not None else torch.empty_like(scores)
+    _lib.check(lib.emia_scale_f32(_ptr(scores), float(np.float32(weight)), scores.numel(), _ptr(out), _stream()), "emia_scale_f32")
+    LAUNCHES["count"] += 1
+    return out
 
 
 def select(iset, idx):
@@ -930,7 +1218,8 @@ class TilePipeline:
         self.k1_events = []
         # sizes of the previous run per shard shape: the next run of that shape is enqueued without reading anything back
         self.sync_free, self.hint_margin = sync_free, hint_margin
-        self._hints, self._ib_cache, self._abort, self._last_hkey = {}, {}, None, None
+        self._hints, self._ib_cache, self._abort, self._last_hkey, self._stale = {}, {}, None, None, None
+        self.exact_runs = 0      # runs that read sizes back (host synchronisations); the others are enqueued sync-free
 
     def _groups(self, offs):
         key = offs.tobytes()
@@ -972,30 +1261,36 @@ class TilePipeline:
         # ---- shard-wide plan: crop geometry + vertex capacities, one read of the per-batch totals
         lib = _lib.load()
         meta, crop_off = paste_plan(d_boxes, self.H, self.W)
-        cap_off = torch.empty(n + 1, dtype=torch.int64, device=dev)
-        _lib.check(lib.emia_contour_trace_plan(_ptr(meta), n, _ptr(cap_off), _stream()), "emia_contour_trace_plan")
-        exclusive_scan_(cap_off)
-        LAUNCHES["count"] += 1
-        # Sizes: read back once (first run of this shard shape), afterwards taken from the previous run ("hints") and only
-        # CHECKED on the device: the whole step is then enqueued without a single host synchronisation, the abort flag is
-        # looked at when the results are consumed (aborted()).  A tripped guard makes the paste / trace / measure kernels
-        # write nothing; the caller re-runs, which takes the exact-size path again.
-        hkey = (n, offs.tobytes(), B)
+        # Sizes: read back once (the first run of this pipeline, or after a guard tripped); afterwards the buffers take the
+        # CAPACITIES remembered from earlier runs (grown in 25 % steps, independent of the exact per-tile instance counts) and the
+        # real totals are only CHECKED on the device: the whole step is enqueued without a single host synchronisation, the
+        # abort flag is looked at when the results are consumed (aborted()).  A tripped guard makes the paste / trace /
+        # measure kernels write nothing; the caller re-runs, which takes the exact-size path again and raises the capacities.
+        hkey = B
         hints = self._hints.get(hkey) if self.sync_free else None
-        ib_t = self._ib_cache.get(hkey)
+        ikey = offs.tobytes()
+        ib_t = self._ib_cache.get(ikey)           # batch boundaries as a device array (an upload, not a size read-back)
         if ib_t is None:
+            if len(self._ib_cache) > 256:
+                self._ib_cache.clear()
             ib_t = torch.as_tensor(ib, device=dev)
-            self._ib_cache[hkey] = ib_t
+            self._ib_cache[ikey] = ib_t
         abort = torch.zeros(1, dtype=torch.int32, device=dev)
+        cap_off = None
         if hints is None:
+            self.exact_runs += 1
+            cap_off = torch.empty(n + 1, dtype=torch.int64, device=dev)
+            _lib.check(lib.emia_contour_trace_plan(_ptr(meta), n, _ptr(cap_off), _stream()), "emia_contour_trace_plan")
+            exclusive_scan_(cap_off)
+            LAUNCHES["count"] += 1
             bounds = torch.stack([crop_off[ib_t], cap_off[ib_t]]).cpu().numpy()
             total_words = int(bounds[0, -1])
             pt_caps = [int(bounds[1, b + 1] - bounds[1, b]) for b in range(B)]
             meas_caps = [None] * B
         else:
-            total_words, pt_caps, meas_caps, caps_t = hints["total_words"], hints["pt_caps"], hints["meas_caps"], hints["pt_caps_t"]
-            over = (crop_off[n] > total_words) | ((cap_off[ib_t[1:]] - cap_off[ib_t[:-1]]) > caps_t).any()
-            abort.logical_or_(over)
+            total_words, pt_caps, meas_caps = hints["total_words"], [hints["pt_cap"]] * B, [hints["meas_cap"]] * B
+            _lib.check(lib.emia_capacity_guard(_ptr(crop_off[n:]), total_words, _ptr(abort), 0, 0, _stream()), "emia_capacity_guard")
+            LAUNCHES["count"] += 1
         crops = torch.empty(max(total_words, 1), dtype=torch.int32, device=dev)
         marks = torch.empty(max(2 * total_words, 1), dtype=torch.int32, device=dev)
         self.s_paste.wait_stream(main); self.s_post.wait_stream(main)
@@ -1038,8 +1333,7 @@ class TilePipeline:
                         if meas is not None:
                             break
                         single_pass = False
-                    meas_caps[b] = (max(int(meas.totals[0] * self.hint_margin) + 16, 16), max(int(meas.totals[1] * self.hint_margin) + 64, 64)) \
-                        if single_pass else None
+                    meas_caps[b] = (int(meas.totals[0]), int(meas.totals[1])) if single_pass else None
                 res = {"tiles": (int(tb[b]), int(tb[b + 1])), "inst0": int(ib[b]), "iset": it, "kept": kept, "meas": meas}
                 if to_host:
                     res["host"] = {k: self._pinned_like(b, k, v).copy_(v, non_blocking=True)
@@ -1053,11 +1347,12 @@ class TilePipeline:
         self._abort = abort
         if hints is None and self.sync_free and all(c is not None for c in meas_caps):
             m = self.hint_margin
-            caps = [int(c * m) + 64 for c in pt_caps]
-            if len(self._hints) > 64:
-                self._hints.clear()
-            self._hints[hkey] = {"total_words": int(total_words * m) + 64, "pt_caps": caps, "meas_caps": meas_caps,
-                                 "pt_caps_t": torch.as_tensor(np.asarray(caps, np.int64), device=dev)}
+            old = self._hints.get(hkey, {"total_words": 0, "pt_cap": 0, "meas_cap": (0, 0)})
+            bucket = lambda v, prev: max(prev, int(v * m) + 64)        # capacities only grow
+            self._hints[hkey] = {"total_words": bucket(total_words, old["total_words"]),
+                                 "pt_cap": bucket(max(pt_caps), old["pt_cap"]),
+                                 "meas_cap": (bucket(max(c[0] for c in meas_caps), old["meas_cap"][0]),
+                                              bucket(max(c[1] for c in meas_caps), old["meas_cap"][1]))}
         self._last_hkey = hkey
         return out
 
@@ -1066,7 +1361,7 @@ class TilePipeline:
         of that shard shape are dropped and the caller runs again (exact-size path).  One host synchronisation."""
         if self._abort is None or not bool(self._abort.item()):
             return False
-        self._hints.pop(self._last_hkey, None)
+        self._stale = self._hints.pop(self._last_hkey, None)      # the next run re-measures and raises the capacities
         return True
 
     def _pinned_like(self, b, name, t):

@@ -122,3 +122,107 @@ class FakeHeadPredictor:
         dev = torch.device("cuda", torch.cuda.current_device())
         t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
         return HeadOutputs(t(probs), t(boxes), t(scores), t(classes), in_size)
+
+
+# =================================================================================================================
+# BASELINE configs 3 and 4 as concrete synthetic inputs.  Host-side numpy; bench.py, tests.
+# =================================================================================================================
+def _tile_origins(h, w, tile_size, overlap_ratio):
+    stride = int(tile_size * (1 - overlap_ratio))
+    return [(x, y) for y in range(0, h, stride) for x in range(0, w, stride)]
+
+
+def _make_distinct(sc):
+    """float32 scores made pairwise distinct: ties are pushed up by single ulps in sorted order (order otherwise unchanged)."""
+    sc = np.asarray(sc, np.float32).copy()
+    o = np.argsort(sc, kind="stable")
+    v = sc[o]
+    for k in range(1, len(v)):
+        if v[k] <= v[k - 1]:
+            v[k] = np.nextafter(v[k - 1], np.float32(2.0))
+    sc[o] = v
+    return sc
+
+
+def micrograph_heads(seed, h, w, n_particles, tile_size, overlap_ratio, upscale, cap=100, rmin=8.0, rmax=30.0):
+    """Config 3: one particle field cut into tiles.  Every particle has ONE 28 x 28 probability map (so its re-detections in
+    overlapping tiles and in the full-image pass are near-identical masks), a class and a base score.  A tile detects the
+    particles whose centre lies inside it (at most `cap`, highest score first — Detectron2 returns its detections sorted by
+    score and capped at DETECTIONS_PER_IMAGE); boxes are given in the UPSCALED tile's coordinates with a sub-pixel jitter and
+    every detection gets its own distinct score.  The full-image pass sees the `cap` highest-scoring particles.
+    Returns dict(full=(probs, boxes, scores, classes, unit_off), tiles=(...), tile_xy [T, 2], hw=(h, w))."""
+    rng = np.random.default_rng(seed)
+    polys = particle_field(rng, n_particles, h, w, rmin=rmin, rmax=rmax, margin=int(rmax) + 4)
+    protos = np.zeros((n_particles, MASK_SIDE, MASK_SIDE), np.float32)
+    pbox = np.zeros((n_particles, 4), np.float32)
+    for i, p in enumerate(polys):
+        protos[i], pbox[i] = head_from_poly(rng, p)
+    base = rng.uniform(0.3, 0.95, n_particles)
+    classes = (rng.random(n_particles) < 0.5).astype(np.int32)
+    cx, cy = 0.5 * (pbox[:, 0] + pbox[:, 2]), 0.5 * (pbox[:, 1] + pbox[:, 3])
+    origins = _tile_origins(h, w, tile_size, overlap_ratio)
+
+    def detections(ids, ox, oy, s):
+        k = len(ids)
+        b = (pbox[ids] - np.array([ox, oy, ox, oy], np.float32)) * np.float32(s) + rng.uniform(-0.4, 0.4, (k, 4)).astype(np.float32)
+        sc = (base[ids] + rng.uniform(-0.04, 0.04, k)).astype(np.float32)
+        order = np.argsort(-sc, kind="stable")[:cap]
+        return ids[order], b[order].astype(np.float32), sc[order]
+
+    t_ids, t_boxes, t_scores, t_off = [], [], [], [0]
+    for (x, y) in origins:
+        inside = np.nonzero((cx >= x) & (cx < x + tile_size) & (cy >= y) & (cy < y + tile_size))[0]
+        ids, b, sc = detections(inside, x, y, upscale)
+        t_ids.append(ids); t_boxes.append(b); t_scores.append(sc); t_off.append(t_off[-1] + len(ids))
+    f_ids, f_boxes, f_scores = detections(np.arange(n_particles), 0.0, 0.0, 1.0)
+    # distinct scores over the whole micrograph (ties would make the reference's argsort order platform-dependent)
+    all_sc = np.concatenate(t_scores + [f_scores])
+    all_sc = _make_distinct(all_sc)
+    # keep every unit sorted by its (now final) scores, descending
+    pos = 0
+    for k in range(len(t_ids) + 1):
+        ids, b = (t_ids[k], t_boxes[k]) if k < len(t_ids) else (f_ids, f_boxes)
+        sc = all_sc[pos:pos + len(ids)]
+        pos += len(ids)
+        o = np.argsort(-sc, kind="stable")
+        if k < len(t_ids):
+            t_ids[k], t_boxes[k], t_scores[k] = ids[o], b[o], sc[o]
+        else:
+            f_ids, f_boxes, f_scores = ids[o], b[o], sc[o]
+    tid = np.concatenate(t_ids) if t_ids else np.zeros(0, np.int64)
+    tiles = (protos[tid], np.concatenate(t_boxes).astype(np.float32), np.concatenate(t_scores).astype(np.float32), classes[tid],
+             np.asarray(t_off, np.int64))
+    full = (protos[f_ids], f_boxes.astype(np.float32), f_scores.astype(np.float32), classes[f_ids], np.array([0, len(f_ids)], np.int64))
+    return dict(full=full, tiles=tiles, tile_xy=np.asarray(origins, np.int32).reshape(-1, 2), hw=(h, w), n_particles=n_particles)
+
+
+def ensemble_multiscale_heads(seed0, n_images, h, w, n_particles=100, scales=(0.7, 1.0, 1.5), n_models=2, cap=100):
+    """Config 4: per image one particle set; model m sees a jittered copy of it (box jitter +-1.5 px, score jitter, 10 % of the
+    particles dropped) and every scale s the same detections in the frame int(h * s) x int(w * s).
+    Returns {scale: [(probs, boxes, scores, classes, unit_off) per model]}, unit = image."""
+    out = {float(s): [[[], [], [], [], [0]] for _ in range(n_models)] for s in scales}
+    for i in range(n_images):
+        rng = np.random.default_rng(seed0 + i)
+        polys = particle_field(rng, n_particles, h, w)
+        protos = np.zeros((n_particles, MASK_SIDE, MASK_SIDE), np.float32)
+        pbox = np.zeros((n_particles, 4), np.float32)
+        for k, p in enumerate(polys):
+            protos[k], pbox[k] = head_from_poly(rng, p)
+        base = rng.uniform(0.3, 0.95, n_particles)
+        classes = (rng.random(n_particles) < 0.5).astype(np.int32)
+        for m in range(n_models):
+            keep = np.nonzero(rng.random(n_particles) >= 0.1)[0]
+            jit = rng.uniform(-1.5, 1.5, (len(keep), 4)).astype(np.float32)
+            for s in scales:
+                sh, sw = int(h * s), int(w * s)
+                b = (pbox[keep] + jit) * np.array([sw / w, sh / h, sw / w, sh / h], np.float32)
+                sc = _make_distinct((base[keep] + rng.uniform(-0.05, 0.05, len(keep))).astype(np.float32))
+                o = np.argsort(-sc, kind="stable")[:cap]
+                rec = out[float(s)][m]
+                rec[0].append(protos[keep][o]); rec[1].append(b[o].astype(np.float32)); rec[2].append(sc[o]); rec[3].append(classes[keep][o])
+                rec[4].append(rec[4][-1] + len(o))
+    res = {}
+    for s, per_model in out.items():
+        res[s] = [(np.concatenate(r[0]), np.concatenate(r[1]), np.concatenate(r[2]).astype(np.float32), np.concatenate(r[3]),
+                   np.asarray(r[4], np.int64)) for r in per_model]
+    return res

@@ -166,7 +166,9 @@ int emia_contour_measure_list(int64_t n_items, const int32_t* item_inst, const i
  * Workspace size: emia_group_workspace_bytes (pass exactly that many bytes: the tail is cleared per call).
  * max_cap = largest group capacity if the caller knows it (0 = unknown): groups of <= 1024 slots take the fast path — one
  *   CTA per group with the member tables, the suppression bit matrix and the candidate-pair queue in shared memory and
- *   one warp per candidate pair for the mask intersection; larger groups use the staged global-memory kernels.
+ *   eight lanes per candidate pair for the mask intersection; larger groups (the global de-dup of a whole micrograph,
+ *   inference.py:2472) take the sparse path: rank by counting, x-sorted sweep with one warp per member, a sparse edge list and a
+ *   fixed-point resolution of the greedy loop (csrc/emia_group_sparse.cuh).
  * emia_dedup_smart       : deduplicate_masks_smart, src/functions/inference.py:2552-2677 (+ :2680-2733), incl. the
  *                          artifact pre-filter (empty / aspect / compactness < 0.15) and quirks Q1, Q2, Q10.
  *                          Output in keep order (score descending).
@@ -205,7 +207,8 @@ int emia_containment_rules(const uint32_t* crops, const emia_inst_meta* meta, co
  * Replaces scipy.ndimage.binary_fill_holes + skimage erosion/dilation (3x3 cross, out-of-frame neighbours ignored) +
  * skimage.measure.label in postprocess_masks (src/utils/mask_utils.py:70-84), process_masks_parallel
  * (src/functions/inference.py:189-203) and postprocess_masks_universal (inference.py:1778-1806).
- * emia_morph_plan: padded plane size per instance (caller scans -> pad_off); work = 3 * pad_off[n] words.
+ * The work planes of an instance live in shared memory when its padded crop ((ch + 2) x (cw + 2) words) has at most 1024 words;
+ * emia_morph_plan: global plane size of the LARGER instances only (0 for the others; caller scans -> pad_off); work = 3 * pad_off[n] words.
  * emia_morph: applies n_ops (<= 4) operators in order (1 = fill holes, 2 = erode, 3 = dilate) to every crop.
  * emia_overlap_first_come: list member k loses the pixels of members 0..k-1 (in list order), then is zeroed when it has
  *   more than one 8-connected component (mask_utils.py:77-82); members keep their place in the list (Q6).
@@ -219,13 +222,17 @@ int emia_morph_plan(const emia_inst_meta* meta, int64_t n, int64_t* pad_words, v
  * erosion ignores out-of-frame neighbours — so its result needs the grown geometry of emia_morph_grow_plan (caller scans). */
 int emia_morph_grow_plan(const emia_inst_meta* meta, int64_t n, int H, int W, emia_inst_meta* meta_out, int64_t* crop_words,
                          void* stream);
+/* apply_flag (optional): instances with apply_flag[i] == 0 pass through unchanged (process_masks_parallel only runs on lists of
+ * more than two masks, inference.py:1443; see emia_group_mark_members).  bbox_out / area_out (optional): bbox / popcount of
+ * the result (emia_overlap_first_come: of the list members only), which saves the emia_crop_stats pass. */
 int emia_morph(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n, int H, int W,
                const int32_t* ops_host, int32_t n_ops, const int64_t* pad_off, uint32_t* work,
-               const emia_inst_meta* meta_out, const int64_t* crop_off_out, uint32_t* crops_out, void* stream);
+               const emia_inst_meta* meta_out, const int64_t* crop_off_out, uint32_t* crops_out,
+               const int32_t* apply_flag, int32_t* bbox_out, int32_t* area_out, void* stream);
 int emia_overlap_first_come(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off,
                             const int32_t* bbox, const int32_t* cap_off, int32_t G, int32_t total_cap,
                             const int32_t* in_len, const int32_t* in_idx, const int64_t* pad_off, uint32_t* work,
-                            uint32_t* crops_out, void* stream);
+                            uint32_t* crops_out, int32_t* bbox_out, int32_t* area_out, void* stream);
 int emia_crop_stats(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n,
                     int32_t* bbox, int32_t* area, void* stream);
 /* list members with area >= min_area, list order kept (inference.py:1800 `np.sum(final_mask) >= min_crys_size`). */
@@ -276,6 +283,45 @@ int emia_gray_hist(const uint32_t* crops, const emia_inst_meta* meta, const int6
 /* 256-bin grey-level histogram of a whole H x W x channels image (same grey conversion as emia_gray_hist): the brightness / contrast
  * statistics of calculate_image_quality_score (src/functions/inference.py:256-283) follow exactly from the counts. */
 int emia_image_gray_hist(const uint8_t* image, int H, int W, int channels, uint64_t* hist, void* stream);
+
+/* ---- batched flows: list / unit plumbing and sync-free capacity guards (csrc/emia_flow_kernels.cuh) ---------------------------
+ * The reference walks its flows one predictor call at a time (run_class_specific_inference src/functions/inference.py:1353-1461,
+ * tile_based_inference_pipeline :2299-2485, run_ensemble_inference :1464-1598, run_adaptive_multiscale_inference :1833-1984); here
+ * the head outputs of all units (tiles / images / scales / models) of a batch are processed by one launch per step.
+ * emia_group_filter_heads : members with meta.valid (Boxes.nonempty()), class == target_class (< 0: any) and score >= min_score
+ *   (inference.py:1411-1420, :1519-1523); zero_score_empties: a list still holding a score == 0 becomes empty (mask_utils.py:59).
+ * emia_group_mark_members : flag[inst] = 1 for members of lists longer than min_len, 0 elsewhere (inference.py:1443 `len > 2`).
+ * emia_group_flatten      : output list s = members of the groups grp_list[seg_start[s] .. seg_start[s+1]) concatenated
+ *   (`full_image_masks + all_tile_masks` :2452; `all_masks.extend` :1563, :1958); its slots start at out_cap_off[s]; id_add[g]
+ *   (optional, per input group) is added to the member ids of group g.
+ * emia_unit_broadcast_i32 : out[i*k + c] = vals[u*k + c] for unit_off[u] <= i < unit_off[u+1] (tile offsets :2411-2414).
+ * emia_scale_f32          : out = in * w in float32 (`score * weight` :1553).
+ * emia_gather_plan / emia_gather_crops / emia_gather_b32 : dst instance j = src instance idx[j] (idx NULL: identity); crop sizes
+ *   for the caller's scan, then crop words + bbox + area; 32-bit payloads (scores, classes).
+ * emia_capacity_guard     : if *total > capacity (or *abort_flag already set): *abort_flag = 1 and the ch / cw of poison_meta[0..n)
+ *   are zeroed, so that no later kernel reads or writes crops of that set; emia_capacity_guard_ranges: the same test for
+ *   every range offsets[bounds[b+1]] - offsets[bounds[b]] (flag only). */
+int emia_group_filter_heads(const int32_t* cap_off, int32_t G, const int32_t* in_len, const int32_t* in_idx,
+                            const emia_inst_meta* meta, const int32_t* classes, const float* scores, int32_t target_class,
+                            float min_score, int32_t zero_score_empties, int32_t* out_len, int32_t* out_idx, void* stream);
+int emia_group_mark_members(const int32_t* cap_off, int32_t G, int32_t total_cap, const int32_t* in_len, const int32_t* in_idx,
+                            int32_t min_len, int32_t* flag, int64_t n_inst, void* stream);
+int emia_group_flatten(const int32_t* cap_off, int32_t G, const int32_t* in_len, const int32_t* in_idx, const int32_t* grp_list,
+                       const int32_t* seg_start, int32_t S, const int32_t* id_add, const int32_t* out_cap_off, int32_t* out_len,
+                       int32_t* out_idx, void* stream);
+int emia_unit_broadcast_i32(const int32_t* unit_off, int32_t U, int64_t n, const int32_t* vals, int32_t k, int32_t* out,
+                            void* stream);
+int emia_scale_f32(const float* in, float w, int64_t n, float* out, void* stream);
+int emia_gather_plan(const emia_inst_meta* src_meta, const int32_t* idx, int64_t k, emia_inst_meta* dst_meta,
+                     int64_t* dst_crop_words, void* stream);
+int emia_gather_crops(const uint32_t* src_crops, const int64_t* src_crop_off, const int32_t* src_bbox, const int32_t* src_area,
+                      const int32_t* idx, int64_t k, const emia_inst_meta* dst_meta, const int64_t* dst_crop_off,
+                      uint32_t* dst_crops, int32_t* dst_bbox, int32_t* dst_area, void* stream);
+int emia_gather_b32(const void* src, const int32_t* idx, int64_t k, void* dst, void* stream);
+int emia_capacity_guard(const int64_t* total, int64_t capacity, int32_t* abort_flag, emia_inst_meta* poison_meta,
+                        int64_t poison_n, void* stream);
+int emia_capacity_guard_ranges(const int64_t* offsets, const int64_t* bounds, int32_t B, int64_t capacity, int32_t* abort_flag,
+                               void* stream);
 
 /* pairwise helpers (drop-in for iou / calculate_iou / calculate_containment on explicit pairs):
  * out[k] = {intersection, area_a, area_b} for pairs (pa[k], pb[k]). */

@@ -111,3 +111,58 @@ def test_misc_golden():
     xy = [(x, y) for _, x, y in tiles.generate_tiles_with_overlap(np.zeros((700, 900, 3), np.uint8), 256, 0.125)]
     assert np.array_equal(np.array(xy, np.int32), g["tiles_xy"])
     assert len(tiles.tile_origins(8192, 8192, 1024, 0.125)) == int(g["tiles_8192"]) == 100
+
+
+# ---- oracle/flows.py (the CPU restatement of the FLOWS used by bench.py's CPU legs and the batched-flow parity tests) against
+# the golden vectors produced by the UNMODIFIED reference functions (tests/golden/make_golden_flows.py) ------------------------
+def _flow_golden():
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import flow_cases
+    return flow_cases, np.load(os.path.join(here, "golden", "flows_golden.npz"), allow_pickle=False)
+
+
+def _instances(pred, image):
+    from oracle import flows
+    probs, boxes, scores, classes, (in_h, in_w) = pred.raw_heads(image)
+    H, W = image.shape[:2]
+    return flows.heads_to_instances(probs, boxes, scores, classes, H, W, W / in_w, H / in_h)
+
+
+def _check_flow(gold, name, masks, scores):
+    n = len(gold[f"{name}/scores"])
+    assert len(masks) == n
+    if n:
+        h, w = (int(v) for v in gold[f"{name}/shape"])
+        ref = np.unpackbits(gold[f"{name}/bits"], axis=1)[:, :h * w].reshape(n, h, w).astype(bool)
+        for i in range(n):
+            assert np.array_equal(np.asarray(masks[i]) != 0, ref[i]), (name, i)
+            assert float(scores[i]) == float(gold[f"{name}/scores"][i])
+
+
+def test_oracle_flows_match_reference_golden():
+    import cv2
+    from deepemia_b200 import synthetic as syn
+    from oracle import flows, tiles
+    fc, gold = _flow_golden()
+    for name, case in fc.CASES.items():
+        if case.get("ensemble") or case["fn"] not in ("run_class_specific_inference", "tile_based_inference_pipeline"):
+            continue
+        image = fc.make_image(case["image_seed"], *case["shape"])
+        pred = syn.FakeHeadPredictor(**case["predictors"][0])
+        kw = case["kwargs"]
+        if case["fn"] == "run_class_specific_inference":
+            t, small = case["args"]
+            ms = (kw.get("class_specific_settings") or {}).get(f"class_{t}", {}).get("min_size")
+            m, s, c = flows.run_class_specific_inference(_instances(pred, image), t, small, kw.get("confidence_threshold", 0.3),
+                                                         kw.get("iou_threshold", 0.7), ms, case.get("parallel", True))
+        else:
+            t, small, conf = case["args"]
+            ts, ov, up = kw["tile_size"], kw["overlap_ratio"], kw["upscale_factor"]
+            tl = tiles.generate_tiles_with_overlap(image, ts, ov)
+            tinst = [_instances(pred, cv2.resize(ti, (int(ts * up), int(ts * up)), interpolation=cv2.INTER_LINEAR)) for ti, _, _ in tl]
+            m, s, c = flows.tile_based_inference_pipeline(_instances(pred, image), tinst, [(x, y) for _, x, y in tl], image.shape[:2], t,
+                                                          small, conf, ts, ov, kw.get("iou_threshold", 0.7),
+                                                          kw.get("edge_filter_enabled", True))
+        _check_flow(gold, name, m, s)
