@@ -351,3 +351,64 @@ def ensemble_multiscale(heads, weights, image_hw, params, arena, sorted_iou=0.4,
     kept = engine.apply_spatial_constraints(iset, kept, rules)
     meas = _measure(iset, kept, um_pix, min_area, arena, "k5") if measure else None
     return FlowResult(iset=iset, per_class=sp2.section(0), kept=kept, meas=meas, extra={"combined": comb, "posts": posts})
+
+
+# =================================================================================================================
+# static layouts + CUDA graphs: a flow over units padded to a fixed capacity is a FIXED sequence of launches — captured once,
+# replayed per batch (no Python, no launch gaps).  Padding heads carry a degenerate box: detector_postprocess' Boxes.nonempty()
+# drops them (meta.valid = 0), so they never enter a list.
+# =================================================================================================================
+def pad_units(probs, boxes, scores, classes, unit_off, cap):
+    """Host arrays of U units -> arrays of U * cap heads (unit u at [u * cap, u * cap + n_u), the rest padding)."""
+    unit_off = np.asarray(unit_off, np.int64)
+    U = len(unit_off) - 1
+    sizes = np.diff(unit_off)
+    assert sizes.max(initial=0) <= cap
+    dst = (np.repeat(np.arange(U, dtype=np.int64) * cap, sizes) + (np.arange(unit_off[-1]) - np.repeat(unit_off[:-1], sizes)))
+    P = np.zeros((U * cap,) + probs.shape[1:], probs.dtype); P[dst] = probs
+    Bx = np.zeros((U * cap, 4), np.float32); Bx[dst] = boxes
+    S = np.zeros(U * cap, np.float32); S[dst] = scores
+    C = np.full(U * cap, -1, np.int32); C[dst] = classes
+    return P, Bx, S, C, (np.arange(U + 1, dtype=np.int64) * cap), dst
+
+
+class GraphedFlow:
+    """fn(arena) -> FlowResult over STATIC input tensors, captured into a CUDA graph after the eager runs have filled the
+    layout caches and settled the arena's capacities.  replay() enqueues the whole flow as one graph launch; the abort flag
+    and the totals are read by finish() exactly as after an eager run."""
+
+    def __init__(self, fn, arena, pool=None):
+        self.fn, self.arena, self.pool = fn, arena, pool
+        self.graph = None
+        self.res = None
+        self.launches = 0
+
+    def settle(self, max_runs=12):
+        """Eager runs until no capacity guard trips (reads the totals back: set-up, not steady state)."""
+        for _ in range(max_runs):
+            self.arena.begin()
+            self.res = self.fn(self.arena)
+            if self.arena.finish():
+                return self.res
+        raise engine._lib.EmiaError("the arena did not converge")
+
+    def capture(self):
+        torch.cuda.synchronize()
+        l0 = engine.LAUNCHES["count"]
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, pool=self.pool):
+            self.arena.begin()
+            self.res = self.fn(self.arena)
+        self.abort = self.arena.abort
+        self.totals = list(self.arena._totals)
+        self.graph = g
+        self.launches = engine.LAUNCHES["count"] - l0
+        return self
+
+    def replay(self):
+        self.graph.replay()
+        return self.res
+
+    def finish(self):
+        self.arena.abort, self.arena._totals = self.abort, self.totals
+        return self.arena.finish()

@@ -36,6 +36,14 @@ EMIA_HD float emia_fmaf(float a, float b, float c) {
 #endif
 }
 
+EMIA_HD double emia_fma(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+    return __fma_rn(a, b, c);
+#else
+    return fma(a, b, c);
+#endif
+}
+
 EMIA_HD int emia_popc(uint32_t v) {
 #if defined(__CUDA_ARCH__)
     return __popc(v);

@@ -154,8 +154,11 @@ static int emia_group_pipeline(int mode, const uint32_t* crops, const emia_inst_
     k_sp_keys<<<gl, T, 0, st>>>(cap_off, G, in_idx, L, rank_mode, pair_mode == 2 ? 2 : 0, scores, classes, bbox, area, rule_active,
                                 num_classes, ws.ok, ws.fidx, ws.k1, ws.k2, ws.kx, ws.nx);
     const unsigned gr = (unsigned)((L + EMIA_SP_THREADS - 1) / EMIA_SP_THREADS);
-    k_sp_rank<<<gr, EMIA_SP_THREADS, 0, st>>>(cap_off, G, L, in_len, rank_mode != 1, ws.fidx, ws.k1, ws.k2, ws.kx, ws.pos, ws.order,
-                                              ws.xorder);
+    const int big = max_cap > 0 ? max_cap : L;
+    const unsigned gy = (unsigned)std::min(16, std::max(1, (big + EMIA_SP_TILE - 1) / EMIA_SP_TILE));
+    cudaMemsetAsync(ws.racc, 0, (size_t)((unsigned char*)ws.k1 - (unsigned char*)ws.racc), st);        // racc, xacc
+    k_sp_rank<<<dim3(gr, gy), EMIA_SP_THREADS, 0, st>>>(cap_off, G, L, in_len, rank_mode != 1, ws.k1, ws.k2, ws.kx, ws.racc, ws.xacc);
+    k_sp_rank_finish<<<gl, T, 0, st>>>(cap_off, G, L, rank_mode != 1, ws.ok, ws.fidx, ws.kx, ws.racc, ws.xacc, ws.pos, ws.order, ws.xorder);
     const unsigned gp = (unsigned)(((size_t)L * 32 + EMIA_SP_THREADS - 1) / EMIA_SP_THREADS);
     k_sp_pairs<<<gp, EMIA_SP_THREADS, 0, st>>>(crops, meta, crop_off, bbox, area, classes, cap_off, G, in_idx, L, pair_mode, thr,
                                                rule_max_iou, nullptr, ws.xorder, ws.nx, ws.pos, ws.edges, ws.ecount, nullptr);
@@ -273,7 +276,11 @@ extern "C" int emia_containment_rules(const uint32_t* crops, const emia_inst_met
                 k_sp_contain_prepare<<<gl, T, 0, st>>>(cap_off, G, in_len, in_idx, L, classes, bbox, area, child, parent, rem_a, role, ws.best,
                                                        ws.kx, ws.nx, ws.anyp);
                 const unsigned gr = (unsigned)((L + EMIA_SP_THREADS - 1) / EMIA_SP_THREADS);
-                k_sp_rank<<<gr, EMIA_SP_THREADS, 0, st>>>(cap_off, G, L, in_len, 0, nullptr, ws.k1, ws.k2, ws.kx, nullptr, nullptr, ws.xorder);
+                const int big = max_cap > 0 ? max_cap : L;
+                const unsigned gy = (unsigned)std::min(16, std::max(1, (big + EMIA_SP_TILE - 1) / EMIA_SP_TILE));
+                cudaMemsetAsync(ws.racc, 0, (size_t)((unsigned char*)ws.k1 - (unsigned char*)ws.racc), st);
+                k_sp_rank<<<dim3(gr, gy), EMIA_SP_THREADS, 0, st>>>(cap_off, G, L, in_len, 0, ws.k1, ws.k2, ws.kx, ws.racc, ws.xacc);
+                k_sp_rank_finish<<<gl, T, 0, st>>>(cap_off, G, L, 0, nullptr, nullptr, ws.kx, ws.racc, ws.xacc, nullptr, nullptr, ws.xorder);
                 const unsigned gp = (unsigned)(((size_t)L * 32 + EMIA_SP_THREADS - 1) / EMIA_SP_THREADS);
                 k_sp_pairs<<<gp, EMIA_SP_THREADS, 0, st>>>(crops, meta, crop_off, bbox, area, classes, cap_off, G, in_idx, L, 4, 0.0, nullptr,
                                                            role, ws.xorder, ws.nx, nullptr, nullptr, nullptr, ws.best);

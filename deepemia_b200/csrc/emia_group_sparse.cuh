@@ -18,7 +18,7 @@
 #define EMIA_SP_THREADS 256
 
 struct EmiaSparseWs {
-    int32_t *ok, *fidx, *pos, *order, *xorder, *rem, *best;   // L each
+    int32_t *ok, *fidx, *pos, *order, *xorder, *rem, *best, *racc, *xacc;   // L each
     uint64_t *k1, *kx;                                         // L each
     uint32_t* k2;                                              // L
     int32_t *nok, *nx, *ecount, *anyp;                         // G each
@@ -28,7 +28,7 @@ struct EmiaSparseWs {
 
 static size_t emia_sparse_ws_bytes(size_t L, size_t G) {
     size_t b = 0;
-    b += 7 * emia_align_up(L * 4 + 16, 256);
+    b += 9 * emia_align_up(L * 4 + 16, 256);
     b += 2 * emia_align_up(L * 8 + 16, 256);
     b += emia_align_up(L * 4 + 16, 256);
     b += 4 * emia_align_up(G * 4 + 16, 256);
@@ -44,6 +44,8 @@ static int emia_sparse_carve(void* workspace, size_t bytes, size_t L, size_t G, 
     ws->ok = (int32_t*)take(L * 4 + 16); ws->fidx = (int32_t*)take(L * 4 + 16); ws->pos = (int32_t*)take(L * 4 + 16);
     ws->order = (int32_t*)take(L * 4 + 16); ws->xorder = (int32_t*)take(L * 4 + 16); ws->rem = (int32_t*)take(L * 4 + 16);
     ws->best = (int32_t*)take(L * 4 + 16);
+    // racc / xacc are contiguous (one memset clears both)
+    ws->racc = (int32_t*)take(L * 4 + 16); ws->xacc = (int32_t*)take(L * 4 + 16);
     ws->k1 = (uint64_t*)take(L * 8 + 16); ws->kx = (uint64_t*)take(L * 8 + 16);
     ws->k2 = (uint32_t*)take(L * 4 + 16);
     // the four per-group counters are contiguous (one memset clears them)
@@ -122,31 +124,33 @@ __global__ void k_sp_keys(const int32_t* __restrict__ cap_off, int G, const int3
     k1[s] = a; k2[s] = b; kx[s] = x;
 }
 
-// rank by counting over shared-memory key tiles.  A CTA covers 256 consecutive slots, which may belong to several groups: the
-// tiles of every group the CTA touches are streamed through shared memory, a thread only counts in its own group's tiles.
+// rank by counting over shared-memory key tiles, split two ways for parallelism: blockIdx.x = 256 consecutive slots (which may
+// belong to several groups: the tiles of every group the CTA touches are streamed through shared memory, a thread only counts
+// in its own group's tiles), blockIdx.y = every gridDim.y-th key tile.  Partial counts are accumulated with atomicAdd into
+// racc / xacc (cleared by the caller); k_sp_rank_finish turns them into pos / order / xorder.
 __global__ void __launch_bounds__(EMIA_SP_THREADS) k_sp_rank(const int32_t* __restrict__ cap_off, int G, int L,
                                                              const int32_t* __restrict__ in_len, int do_rank,
-                                                             const int32_t* __restrict__ fidx, const uint64_t* __restrict__ k1,
-                                                             const uint32_t* __restrict__ k2, const uint64_t* __restrict__ kx,
-                                                             int32_t* __restrict__ pos, int32_t* __restrict__ order,
-                                                             int32_t* __restrict__ xorder) {
+                                                             const uint64_t* __restrict__ k1, const uint32_t* __restrict__ k2,
+                                                             const uint64_t* __restrict__ kx, int32_t* __restrict__ racc,
+                                                             int32_t* __restrict__ xacc) {
     __shared__ uint64_t s1[EMIA_SP_TILE];
     __shared__ uint64_t sx[EMIA_SP_TILE];
     __shared__ uint32_t s2[EMIA_SP_TILE];
     const int s_lo = blockIdx.x * EMIA_SP_THREADS;
     const int s_hi = min(L, s_lo + EMIA_SP_THREADS) - 1;
     const int s = s_lo + threadIdx.x;
-    const int g_lo = emia_find_group(cap_off, G, s_lo), g_hi = emia_find_group(cap_off, G, s_hi);
     int my_g = -1;
     uint64_t m1 = 0ull, mx = ~0ull;
     uint32_t m2 = 0u;
-    if (s < L) { my_g = emia_find_group(cap_off, G, s); m1 = k1[s]; m2 = k2[s]; mx = kx[s]; }
-    const bool mine_ok = (m1 != 0ull), mine_part = (mx != ~0ull);
+    if (s < L) { my_g = emia_find_group(cap_off, G, s); m1 = do_rank ? k1[s] : 0ull; m2 = do_rank ? k2[s] : 0u; mx = kx[s]; }
+    const bool mine_ok = do_rank && (m1 != 0ull), mine_part = (mx != ~0ull);
+    if (!__syncthreads_or(mine_ok || mine_part)) return;            // a chunk of dead slots
+    const int g_lo = emia_find_group(cap_off, G, s_lo), g_hi = emia_find_group(cap_off, G, s_hi);
     int rank = 0, xr = 0;
     for (int g = g_lo; g <= g_hi; ++g) {
         const int base = cap_off[g];
         const int len = in_len[g];                                   // slots beyond the live length carry null keys
-        for (int t0 = 0; t0 < len; t0 += EMIA_SP_TILE) {
+        for (int t0 = blockIdx.y * EMIA_SP_TILE; t0 < len; t0 += gridDim.y * EMIA_SP_TILE) {
             const int cnt = min(EMIA_SP_TILE, len - t0);
             for (int j = threadIdx.x; j < cnt; j += EMIA_SP_THREADS) {
                 if (do_rank) { s1[j] = k1[base + t0 + j]; s2[j] = k2[base + t0 + j]; }
@@ -154,15 +158,15 @@ __global__ void __launch_bounds__(EMIA_SP_THREADS) k_sp_rank(const int32_t* __re
             }
             __syncthreads();
             if (my_g == g) {
-                if (do_rank && mine_ok) {
-#pragma unroll 4
+                if (mine_ok) {
+#pragma unroll 8
                     for (int j = 0; j < cnt; ++j) {
                         const uint64_t a = s1[j];
                         rank += (a > m1) || (a == m1 && s2[j] > m2);
                     }
                 }
                 if (mine_part) {
-#pragma unroll 4
+#pragma unroll 8
                     for (int j = 0; j < cnt; ++j) xr += (sx[j] < mx);
                 }
             }
@@ -170,15 +174,27 @@ __global__ void __launch_bounds__(EMIA_SP_THREADS) k_sp_rank(const int32_t* __re
         }
     }
     if (s >= L) return;
-    const int base = cap_off[my_g];
+    if (rank) atomicAdd(&racc[s], rank);
+    if (xr) atomicAdd(&xacc[s], xr);
+}
+__global__ void k_sp_rank_finish(const int32_t* __restrict__ cap_off, int G, int L, int do_rank, const int32_t* __restrict__ ok,
+                                 const int32_t* __restrict__ fidx, const uint64_t* __restrict__ kx, const int32_t* __restrict__ racc,
+                                 const int32_t* __restrict__ xacc, int32_t* __restrict__ pos, int32_t* __restrict__ order,
+                                 int32_t* __restrict__ xorder) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= L) return;
+    const bool part = (kx[s] != ~0ull);
+    const bool live = pos ? (ok[s] != 0) : false;
+    if (!part && !live) { if (pos) pos[s] = -1; return; }
+    const int base = cap_off[emia_find_group(cap_off, G, s)];
     if (pos) {
-        if (mine_ok) {
-            const int r = do_rank ? rank : fidx[s];
+        if (live) {
+            const int r = do_rank ? racc[s] : fidx[s];
             pos[s] = r;
             order[base + r] = s;
         } else pos[s] = -1;
     }
-    if (mine_part) xorder[base + xr] = s;
+    if (part) xorder[base + xacc[s]] = s;
 }
 
 // candidate pairs: one warp per member in x_min order; it meets the members that start before its x_max.

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include "../../include/emia.h"
 #include "core/emia_common.cuh"
 #include "core/emia_contour.cuh"
@@ -14,6 +15,7 @@
 #include "core/emia_measure.cuh"
 #include "core/emia_paste.cuh"
 #include "core/emia_nms.cuh"
+#include "core/emia_moments.cuh"
 
 static thread_local char g_err[512] = "";
 static int emia_fail(int code, const char* fmt, const char* detail) {

@@ -47,8 +47,55 @@ __device__ __forceinline__ uint32_t emia_flood_word(uint32_t s, uint32_t m) {
     return r;
 }
 
-// R <- flood of seeds (already in R) through ALLOWED, 4- or 8-connected, to a fixed point.  Lanes own rows.
+// R <- flood of seeds (already in R) through ALLOWED, 4- or 8-connected, to a fixed point.
+// Planes up to 32 words wide (every shared-memory plane): LANES OWN WORD COLUMNS and the rows are walked top-down, then
+// bottom-up (Gauss-Seidel: a row sees the final value of the row before it, so one sweep carries a front across the whole
+// plane; the number of sweeps is the number of direction changes of the longest path — 2-3 for particle-like shapes — instead
+// of the number of rows).  Inside a row the front runs along the allowed runs by carry propagation in the word and by
+// shuffles across word boundaries.  Wider planes (global workspace) keep the row-per-lane Jacobi sweep.
+__device__ __forceinline__ uint32_t emia_flood_row(uint32_t in, uint32_t allow, int lane, int words) {
+    uint32_t nv = emia_flood_word(in & allow, allow);
+    for (;;) {
+        uint32_t l = __shfl_up_sync(0xffffffffu, nv, 1) >> 31;
+        uint32_t r = __shfl_down_sync(0xffffffffu, nv, 1) << 31;
+        if (lane == 0) l = 0u;
+        if (lane >= words - 1) r = 0u;
+        const uint32_t add = (l | r) & allow & ~nv;
+        if (!__any_sync(0xffffffffu, add != 0u)) break;
+        nv = emia_flood_word(nv | add, allow);
+    }
+    return nv;
+}
+__device__ void emia_flood_cols(const EmiaPad& R, const EmiaPad& ALLOWED, int conn8, int lane) {
+    const int words = R.words, rows = R.rows;
+    const bool act = lane < words;
+    for (;;) {
+        bool changed = false;
+        for (int dir = 0; dir < 2; ++dir) {
+            uint32_t prev = 0u;                                   // final value of the row visited before this one
+            for (int k = 0; k < rows; ++k) {
+                const int pr = dir ? (rows - 1 - k) : k;
+                const uint32_t allow = act ? emia_pad_at(ALLOWED, pr, lane) : 0u;
+                const uint32_t cur = act ? emia_pad_at(R, pr, lane) : 0u;
+                uint32_t from = prev;
+                if (conn8) {
+                    uint32_t l = prev << 1, r = prev >> 1;
+                    const uint32_t pl = __shfl_up_sync(0xffffffffu, prev, 1), pn = __shfl_down_sync(0xffffffffu, prev, 1);
+                    if (lane > 0) l |= pl >> 31;
+                    if (lane < words - 1) r |= pn << 31;
+                    from |= l | r;
+                }
+                const uint32_t nv = emia_flood_row(cur | from, allow, lane, words) | cur;
+                if (act && nv != cur) { emia_pad_at(R, pr, lane) = nv; changed = true; }
+                prev = act ? nv : 0u;
+            }
+        }
+        __syncwarp();
+        if (!__any_sync(0xffffffffu, changed)) break;
+    }
+}
 __device__ void emia_flood(const EmiaPad& R, const EmiaPad& ALLOWED, int conn8, int lane) {
+    if (R.words <= 32) { emia_flood_cols(R, ALLOWED, conn8, lane); return; }
     for (;;) {
         bool changed = false;
         for (int pr = lane; pr < R.rows; pr += 32) {
@@ -456,19 +503,13 @@ __global__ void __launch_bounds__(256) k_column_gate(const uint32_t* __restrict_
         const int inst = in_idx[base + k];
         const emia_inst_meta m = meta[inst];
         const uint32_t* crop = crops + crop_off[inst];
-        // lanes own word columns; the per-bit column totals of one word column are accumulated over the rows first
-        for (int c = lane; c < m.cw; c += 32) {
-            for (int b0 = 0; b0 < 32; b0 += 8) {
-                int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                for (int r = 0; r < m.ch; ++r) {
-                    const uint32_t w = crop[(size_t)r * m.cw + c] >> b0;
-                    for (int j = 0; j < 8; ++j) cnt[j] += (w >> j) & 1u;
-                }
-                for (int j = 0; j < 8; ++j) {
-                    const int x = (m.wc0 + c) * 32 + b0 + j;
-                    if (cnt[j] && x < W) atomicAdd(&s_col[x], cnt[j]);
-                }
-            }
+        // lane j counts bit j of one word column over the rows (every load is a warp-wide broadcast of one word)
+        for (int c = 0; c < m.cw; ++c) {
+            int cnt = 0;
+#pragma unroll 4
+            for (int r = 0; r < m.ch; ++r) cnt += (crop[(size_t)r * m.cw + c] >> lane) & 1u;
+            const int x = (m.wc0 + c) * 32 + lane;
+            if (cnt && x < W) atomicAdd(&s_col[x], cnt);
         }
     }
     __syncthreads();

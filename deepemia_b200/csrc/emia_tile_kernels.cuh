@@ -318,6 +318,71 @@ extern "C" int emia_moments01(const uint32_t* crops, const emia_inst_meta* meta,
     return emia_check_launch("emia_moments01 launch: %s");
 }
 
+// ---- all image moments up to order 3 (cv2.moments: raw m_pq exact, central mu_pq and normalised nu_pq as OpenCV computes them) ----
+__global__ void __launch_bounds__(128) k_moments(const uint32_t* __restrict__ crops, const emia_inst_meta* __restrict__ meta,
+                                                 const int64_t* __restrict__ crop_off, int64_t n, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
+    const emia_inst_meta m = meta[i];
+    const uint32_t* crop = crops + crop_off[i];
+    long long acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = lane; k < m.ch * m.cw; k += 32) {
+        const int r = k / m.cw, c = k - r * m.cw;
+        emia_word_moments(crop[k], (m.wc0 + c) * 32, m.ry0 + r, acc);
+    }
+    for (int q = 0; q < 10; ++q)
+        for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+    if (lane == 0) emia_complete_moments(acc, out + i * EMIA_MOMENT_FIELDS);
+}
+extern "C" int emia_moments(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n, double* out,
+                            void* stream) {
+    if (n < 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_moments: %s", "bad n");
+    if (n == 0) return EMIA_OK;
+    if (!crops || !meta || !crop_off || !out) return emia_fail(EMIA_ERR_BAD_ARG, "emia_moments: %s", "null pointer");
+    k_moments<<<(unsigned)((n * 32 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(crops, meta, crop_off, n, out);
+    return emia_check_launch("emia_moments launch: %s");
+}
+
+// ---- colour sums of the image pixels under every instance: out[i] = (sum B, sum G, sum R, pixel count) as exact integers ----------
+// (mean colour -> rgb_to_wavelength, src/utils/measurements.py:32-111; the README's "Wavelength_nm" that no reference code writes, Q9)
+__global__ void __launch_bounds__(128) k_color_sums(const uint32_t* __restrict__ crops, const emia_inst_meta* __restrict__ meta,
+                                                    const int64_t* __restrict__ crop_off, int64_t n, const uint8_t* __restrict__ image,
+                                                    int H, int W, int64_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
+    const emia_inst_meta m = meta[i];
+    const uint32_t* crop = crops + crop_off[i];
+    long long sb = 0, sg = 0, sr = 0, cnt = 0;
+    for (int k = lane; k < m.ch * m.cw; k += 32) {
+        uint32_t w = crop[k];
+        const int r = k / m.cw, c = k - r * m.cw;
+        const int y = m.ry0 + r;
+        while (w) {
+            const int b = __ffs((int)w) - 1;
+            w &= w - 1;
+            const int x = (m.wc0 + c) * 32 + b;
+            if (x >= W || y >= H) continue;
+            const uint8_t* px = image + ((size_t)y * W + x) * 3;
+            sb += px[0]; sg += px[1]; sr += px[2]; cnt += 1;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        sb += __shfl_xor_sync(0xffffffffu, sb, o); sg += __shfl_xor_sync(0xffffffffu, sg, o);
+        sr += __shfl_xor_sync(0xffffffffu, sr, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if (lane == 0) { out[4 * i] = sb; out[4 * i + 1] = sg; out[4 * i + 2] = sr; out[4 * i + 3] = cnt; }
+}
+extern "C" int emia_color_sums(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n,
+                               const uint8_t* image_bgr, int H, int W, int64_t* out, void* stream) {
+    if (n < 0 || H <= 0 || W <= 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_color_sums: %s", "bad argument");
+    if (n == 0) return EMIA_OK;
+    if (!crops || !meta || !crop_off || !image_bgr || !out) return emia_fail(EMIA_ERR_BAD_ARG, "emia_color_sums: %s", "null pointer");
+    k_color_sums<<<(unsigned)((n * 32 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(crops, meta, crop_off, n, image_bgr, H, W, out);
+    return emia_check_launch("emia_color_sums launch: %s");
+}
+
 // ---- masked grey-level histogram (contrast d10 / d50 / d90, src/utils/measurements.py:195-215) ---------------------------
 // gray = cv2.cvtColor(BGR2GRAY) for 8-bit images: (B * 3735 + G * 19235 + R * 9798 + 16384) >> 15 (OpenCV 4.13; verified
 // exhaustively against cv2 on a 3-step colour grid); np.histogram(bins = 256,

@@ -1097,6 +1097,32 @@ def moments01(iset):
     return out[:iset.n]
 
 
+MOMENT_NAMES = ("m00", "m10", "m01", "m20", "m11", "m02", "m30", "m21", "m12", "m03", "mu20", "mu11", "mu02", "mu30", "mu21", "mu12",
+                "mu03", "nu20", "nu11", "nu02", "nu30", "nu21", "nu12", "nu03")
+
+
+def moments(iset):
+    """float64 [n, 24]: every entry of cv2.moments(mask.astype(np.uint8)) (src/functions/inference.py:1101) in MOMENT_NAMES order —
+    raw moments exact, central / normalised ones with OpenCV's arithmetic."""
+    lib = _lib.load()
+    out = torch.empty((max(iset.n, 1), len(MOMENT_NAMES)), dtype=torch.float64, device=iset.device)
+    _lib.check(lib.emia_moments(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), iset.n, _ptr(out), _stream()), "emia_moments")
+    LAUNCHES["count"] += 1
+    return out[:iset.n]
+
+
+def color_sums(iset, image):
+    """int64 [n, 4]: (sum B, sum G, sum R, pixel count) of the BGR image pixels under every instance."""
+    lib = _lib.load()
+    img = torch.as_tensor(np.ascontiguousarray(image) if isinstance(image, np.ndarray) else image, device=iset.device).contiguous()
+    assert img.dtype == torch.uint8 and img.dim() == 3 and img.shape[2] == 3 and img.shape[0] == iset.H and img.shape[1] == iset.W
+    out = torch.empty((max(iset.n, 1), 4), dtype=torch.int64, device=iset.device)
+    _lib.check(lib.emia_color_sums(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), iset.n, _ptr(img), iset.H, iset.W, _ptr(out),
+                                   _stream()), "emia_color_sums")
+    LAUNCHES["count"] += 1
+    return out[:iset.n]
+
+
 _rule_cache = {}
 
 
@@ -1293,30 +1319,38 @@ class TilePipeline:
             LAUNCHES["count"] += 1
         crops = torch.empty(max(total_words, 1), dtype=torch.int32, device=dev)
         marks = torch.empty(max(2 * total_words, 1), dtype=torch.int32, device=dev)
-        self.s_paste.wait_stream(main); self.s_post.wait_stream(main)
+        # under CUDA-graph capture (or with one batch and device inputs there is nothing to overlap) everything runs on the
+        # caller's stream: the captured step is a single chain of kernel nodes
+        capturing = torch.cuda.is_current_stream_capturing()
+        s_paste = main if capturing else self.s_paste
+        s_post = main if capturing else self.s_post
+        if capturing:
+            assert hints is not None and not host_in, "capture needs the sync-free path: run the shard once eagerly first"
+            time_k1 = False
+        s_paste.wait_stream(main); s_post.wait_stream(main)
         isets, ev_paste = [], []
         self.k1_events = []
-        with torch.cuda.stream(self.s_paste):
+        with torch.cuda.stream(s_paste):
             for b in range(B):
                 i0, i1 = int(ib[b]), int(ib[b + 1])
                 if host_in:
-                    self.s_paste.wait_event(ev_copy[b])
+                    s_paste.wait_event(ev_copy[b])
                 if time_k1:
-                    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e0.record(self.s_paste)
+                    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e0.record(s_paste)
                 it = paste(d_probs[i0:i1], d_boxes[i0:i1], self.H, self.W, scores=d_scores[i0:i1], classes=d_classes[i0:i1],
                            frames=self.frames, variant=self.variant, crops_out=crops,
                            plan=(meta[i0:i1], crop_off[i0:i1 + 1], total_words), ctas_per_sm=self.paste_ctas,
                            abort=abort if hints is not None else None)
                 if time_k1:
-                    e1.record(self.s_paste); self.k1_events.append((e0, e1))
+                    e1.record(s_paste); self.k1_events.append((e0, e1))
                 it.extra["pt_cap_total"] = pt_caps[b]
-                e = torch.cuda.Event(); e.record(self.s_paste); ev_paste.append(e)
+                e = torch.cuda.Event(); e.record(s_paste); ev_paste.append(e)
                 isets.append(it)
         out = []
-        with torch.cuda.stream(self.s_post):
+        with torch.cuda.stream(s_post):
             for b in range(B):
                 it = isets[b]
-                self.s_post.wait_event(ev_paste[b])
+                s_post.wait_event(ev_paste[b])
                 groups = self._groups(offs[tb[b]:tb[b + 1] + 1] - ib[b])
                 if hints is not None:
                     trace(it, single_pass=True, marks=marks, abort=abort)
@@ -1340,7 +1374,7 @@ class TilePipeline:
                                    for k, v in (("records", meas.records), ("rec_inst", meas.rec_inst), ("rec_off", meas.rec_off),
                                                 ("kept_len", kept.length), ("kept_idx", kept.idx))}
                 out.append(res)
-        main.wait_stream(self.s_post); main.wait_stream(self.s_paste)
+        main.wait_stream(s_post); main.wait_stream(s_paste)
         if host_in:
             main.wait_stream(self.s_copy)
         self._keep = (crops, marks, meta, crop_off, cap_off, d_probs)

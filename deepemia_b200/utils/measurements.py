@@ -45,3 +45,53 @@ def calculate_measurements(c, single_im_mask, um_pix=1.0, pixelsPerMetric=1.0, o
         from .contrast import contrast_percentiles
         out["contrast_d10"], out["contrast_d50"], out["contrast_d90"] = contrast_percentiles(original_image, single_im_mask)
     return out
+
+
+# ---- colour -> wavelength helpers (src/utils/measurements.py:32-111; no caller in the reference, kept for API completeness) --------
+def rgb_to_hsv(r, g, b):
+    """src/utils/measurements.py:32-80: OpenCV-style HSV (hue halved to 0..180, s and v scaled to 0..255)."""
+    MAX_PIXEL_VALUE = 255.0
+    r = r / MAX_PIXEL_VALUE
+    g = g / MAX_PIXEL_VALUE
+    b = b / MAX_PIXEL_VALUE
+    max_val = max(r, g, b)
+    min_val = min(r, g, b)
+    v = max_val
+    if max_val == 0.0 or (max_val - min_val) == 0.0:
+        s = 0
+        h = 0
+    else:
+        s = (max_val - min_val) / max_val
+        if max_val == r:
+            h = 60 * ((g - b) / (max_val - min_val)) + 0
+        elif max_val == g:
+            h = 60 * ((b - r) / (max_val - min_val)) + 120
+        else:
+            h = 60 * ((r - g) / (max_val - min_val)) + 240
+    if h < 0:
+        h = h + 360.0
+    return h / 2, s * MAX_PIXEL_VALUE, v * MAX_PIXEL_VALUE
+
+
+def hue_to_wavelength(hue):
+    """src/utils/measurements.py:83-96."""
+    assert hue >= 0
+    assert hue <= 270
+    return 620 - 170 / 270 * hue
+
+
+def rgb_to_wavelength(r, g, b):
+    """src/utils/measurements.py:97-111."""
+    h, s, v = rgb_to_hsv(r, g, b)
+    return hue_to_wavelength(h)
+
+
+def instance_wavelengths(iset, image_bgr):
+    """Wavelength (nm) of the MEAN colour of the image pixels under every instance: the per-instance `Wavelength_nm` the
+    reference's README advertises but no reference code computes.  The colour sums come from the GPU
+    as exact integers (engine.color_sums); empty masks give None."""
+    sums = engine.color_sums(iset, image_bgr).cpu().numpy()
+    out = []
+    for sb, sg, sr, cnt in sums:
+        out.append(None if cnt == 0 else rgb_to_wavelength(int(sr) / int(cnt), int(sg) / int(cnt), int(sb) / int(cnt)))
+    return out

@@ -275,6 +275,15 @@ int emia_rle_encode(const uint32_t* crops, const emia_inst_meta* meta, const int
 int emia_moments01(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n, int64_t* out,
                    void* stream);
 
+/* all moments of cv2.moments(mask) (inference.py:1101): out[i][24] = m00 m10 m01 m20 m11 m02 m30 m21 m12 m03 (exact integer sums as
+ * doubles), mu20 mu11 mu02 mu30 mu21 mu12 mu03, nu20 nu11 nu02 nu30 nu21 nu12 nu03 (OpenCV's completeMomentState arithmetic). */
+#define EMIA_MOMENT_FIELDS 24
+int emia_moments(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n, double* out, void* stream);
+/* colour sums of the H x W x 3 (BGR, uint8) image pixels under every instance: out[i] = {sum B, sum G, sum R, pixel count} — the
+ * mean colour that rgb_to_wavelength (src/utils/measurements.py:32-111) turns into a wavelength. */
+int emia_color_sums(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n,
+                    const uint8_t* image_bgr, int H, int W, int64_t* out, void* stream);
+
 /* 256-bin grey-level histogram of the image pixels under every instance (contrast d10/d50/d90, src/utils/measurements.py:
  * 195-215): image = H x W x channels bytes (3: BGR -> cv2's 8-bit BGR2GRAY fixed-point formula; 1: grey), hist[n][256]. */
 int emia_gray_hist(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n,

@@ -10,6 +10,7 @@
 #include "../../deepemia_b200/csrc/core/emia_ellipse.cuh"
 #include "../../deepemia_b200/csrc/core/emia_measure.cuh"
 #include "../../deepemia_b200/csrc/core/emia_paste.cuh"
+#include "../../deepemia_b200/csrc/core/emia_moments.cuh"
 
 static void pack_bits(const uint8_t* mask, int H, int W, std::vector<uint32_t>& bits, int& ww) {
     ww = (W + 31) / 32;
@@ -85,5 +86,14 @@ int sim_paste(const float* prob, const float* box, float sx, float sy, int H, in
         }
     }
     return 1;
+}
+// cv2.moments of a 0/1 byte mask: out[24] (see emia_moments.cuh)
+void sim_moments(const uint8_t* mask, int H, int W, double* out) {
+    std::vector<uint32_t> bits; int ww;
+    pack_bits(mask, H, W, bits, ww);
+    long long acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int y = 0; y < H; ++y)
+        for (int c = 0; c < ww; ++c) emia_word_moments(bits[(size_t)y * ww + c], c * 32, y, acc);
+    emia_complete_moments(acc, out);
 }
 }  // extern "C"

@@ -168,3 +168,48 @@ def test_paste_core_bit_exact_vs_torch(L):
         assert v == len(ref)
         if v:
             assert np.array_equal(ref[0], out.astype(bool))
+
+
+def test_moments_bit_exact_vs_opencv(L):
+    """cv2.moments(mask) (src/functions/inference.py:1101): the 10 raw moments and the 3 second-order central moments bit for
+    bit; third-order central and normalised moments (differences of numbers ~1e6 x larger) to 1e-9 of their natural scale —
+    on random shapes, also far from the origin of a large frame."""
+    from deepemia_b200.engine import MOMENT_NAMES
+    rng = np.random.default_rng(11)
+    n = 0
+    for m in _shapes(rng, 150):
+        for big in (False, True):
+            mask = m
+            if big:
+                mask = np.zeros((1400, 2100), np.uint8)
+                oy, ox = int(rng.integers(0, 1200)), int(rng.integers(0, 1840))
+                mask[oy:oy + m.shape[0], ox:ox + m.shape[1]] = m
+            mask = np.ascontiguousarray(mask)
+            out = np.zeros(24, np.float64)
+            L.sim_moments(_p(mask), mask.shape[0], mask.shape[1], _p(out))
+            ref = cv2.moments(mask)
+            want = np.array([ref[k] for k in MOMENT_NAMES])
+            assert np.array_equal(out[:13], want[:13]), (n, [(k, a, b) for k, a, b in zip(MOMENT_NAMES, out, want) if a != b][:4])
+            ext = max(mask.shape)                                             # coordinates up to `ext`
+            assert np.allclose(out[13:17], want[13:17], rtol=1e-9, atol=1e-12 * want[0] * ext ** 3)
+            assert np.allclose(out[17:20], want[17:20], rtol=1e-12, atol=0) and np.allclose(out[20:], want[20:], rtol=1e-6, atol=1e-8)
+            n += 1
+    empty = np.zeros((20, 40), np.uint8)
+    out = np.ones(24, np.float64)
+    L.sim_moments(_p(empty), 20, 40, _p(out))
+    assert np.array_equal(out, np.array([cv2.moments(empty)[k] for k in MOMENT_NAMES]))
+
+
+def test_wavelength_mirror_matches_reference_text():
+    """rgb_to_hsv / hue_to_wavelength / rgb_to_wavelength (src/utils/measurements.py:32-111): known answers worked out from the
+    reference's formulas (hue halved OpenCV-style, 620 - 170/270 * hue)."""
+    from deepemia_b200.utils import measurements as M
+    assert M.rgb_to_hsv(255, 0, 0) == (0.0, 255.0, 255.0)
+    assert M.rgb_to_hsv(0, 255, 0) == (60.0, 255.0, 255.0)
+    assert M.rgb_to_hsv(0, 0, 255) == (120.0, 255.0, 255.0)
+    assert M.rgb_to_hsv(0, 0, 0) == (0.0, 0.0, 0.0) and M.rgb_to_hsv(7, 7, 7)[:2] == (0.0, 0.0)
+    assert M.rgb_to_hsv(255, 0, 255)[0] == 150.0            # magenta: -60 + 360 = 300 -> halved
+    assert M.rgb_to_wavelength(255, 0, 0) == 620
+    assert M.rgb_to_wavelength(0, 255, 0) == 620 - 170 / 270 * 60.0
+    assert M.rgb_to_wavelength(0, 0, 255) == 620 - 170 / 270 * 120.0
+    assert abs(M.rgb_to_wavelength(30, 200, 120) - (620 - 170 / 270 * (60 * ((120 / 255 - 30 / 255) / (200 / 255 - 30 / 255)) + 120) / 2)) < 1e-9
