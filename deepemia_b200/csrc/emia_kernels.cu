@@ -137,6 +137,30 @@ __global__ void __launch_bounds__(1024) k_exclusive_scan_i64_serial(int64_t* dat
     if (t == 1023) data[n] = part[1023];
 }
 
+// n <= 32 K: one CTA, one launch (1024 threads x 32 items, warp shuffles + one shared-memory pass)
+#define EMIA_SCAN_SMALL_MAX 32768
+__global__ void __launch_bounds__(1024) k_exclusive_scan_small(int64_t* __restrict__ data, int n) {
+    __shared__ int64_t s_warp[32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int per = (n + 1023) / 1024;                       // <= 32 consecutive items per thread
+    const int lo = t * per, hi = min(n, lo + per);
+    int64_t sum = 0;
+    for (int i = lo; i < hi; ++i) sum += data[i];
+    int64_t inc = sum;
+    for (int off = 1; off < 32; off <<= 1) { const int64_t v = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += v; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int64_t w = s_warp[lane];
+        for (int off = 1; off < 32; off <<= 1) { const int64_t v = __shfl_up_sync(0xffffffffu, w, off); if (lane >= off) w += v; }
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    int64_t run = (warp ? s_warp[warp - 1] : 0) + inc - sum;
+    for (int i = lo; i < hi; ++i) { const int64_t v = data[i]; data[i] = run; run += v; }
+    if (t == 1023) data[n] = s_warp[31];
+}
+
 extern "C" size_t emia_scan_workspace_bytes(int64_t n) {
     (void)n;
     return (size_t)EMIA_SCAN_MAX_TILES * sizeof(int64_t);
@@ -145,6 +169,10 @@ extern "C" size_t emia_scan_workspace_bytes(int64_t n) {
 extern "C" int emia_exclusive_scan_i64(int64_t* data, int64_t n, void* workspace, size_t workspace_bytes, void* stream) {
     if (!data || n < 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_exclusive_scan_i64: %s", "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
+    if (n <= EMIA_SCAN_SMALL_MAX) {
+        k_exclusive_scan_small<<<1, 1024, 0, st>>>(data, (int)n);
+        return emia_check_launch("emia_exclusive_scan_i64 launch: %s");
+    }
     const int64_t ntiles = (n + EMIA_SCAN_TILE - 1) / EMIA_SCAN_TILE;
     if (ntiles == 0 || ntiles > EMIA_SCAN_MAX_TILES || !workspace || workspace_bytes < (size_t)ntiles * sizeof(int64_t)) {
         k_exclusive_scan_i64_serial<<<1, 1024, 0, st>>>(data, n);

@@ -164,6 +164,75 @@ __device__ void emia_cross_op(const EmiaPad& dst, const EmiaPad& src, int dilate
     __syncwarp();
 }
 
+// true when some background pixel of M is enclosed by mask pixels both horizontally and vertically (a necessary condition for a
+// hole).  Lanes own word columns (M.words <= 32); T is scratch (the running OR of the rows above).  ~25 instructions per row.
+__device__ bool emia_may_have_holes(const EmiaPad& M, const EmiaPad& T, int lane) {
+    const int words = M.words, rows = M.rows;
+    const bool act = lane < words;
+    uint32_t run = 0u;
+    for (int r = 0; r < rows; ++r) {                       // T[r] = OR of rows 0 .. r-1
+        if (act) emia_pad_at(T, r, lane) = run;
+        run |= act ? emia_pad_at(M, r, lane) : 0u;
+    }
+    uint32_t below = 0u;
+    bool found = false;
+    for (int r = rows - 1; r >= 0; --r) {
+        const uint32_t m = act ? emia_pad_at(M, r, lane) : 0u;
+        const unsigned has = __ballot_sync(0xffffffffu, m != 0u);
+        if (has) {
+            const bool lower = (has & ((1u << lane) - 1u)) != 0u;            // a set pixel in a word column left of mine
+            const bool higher = lane < 31 ? ((has >> (lane + 1)) != 0u) : false;
+            uint32_t hull = 0xffffffffu;
+            if (!lower) hull &= m ? (0xffffffffu << (__ffs((int)m) - 1)) : 0u;
+            if (!higher) hull &= m ? (0xffffffffu >> __clz((int)m)) : 0u;
+            const uint32_t above = act ? emia_pad_at(T, r, lane) : 0u;
+            if (~m & hull & above & below) found = true;
+        }
+        below |= m;
+    }
+    __syncwarp();
+    return __any_sync(0xffffffffu, found);
+}
+
+// true when the mask in A is certainly ONE 8-connected component: every row is a single run of pixels, there is no empty row
+// between non-empty rows, and the runs of consecutive rows touch (also diagonally).  Lanes own rows.  (Sufficient, not necessary.)
+__device__ bool emia_single_blob(const EmiaPad& A, int lane) {
+    const int words = A.words, rows = A.rows;
+    bool ok = true;
+    int prev_f = 0, prev_l = -1, state = 0;                // carried across 32-row chunks (lane 31 -> lane 0): last row's run, 0 = before, 1 = inside, 2 = after
+    for (int r0 = 0; r0 < rows; r0 += 32) {
+        const int r = r0 + lane;
+        int f = 0x7fffffff, l = -1, c = 0;
+        if (r < rows) {
+            for (int w = 0; w < words; ++w) {
+                const uint32_t v = emia_pad_at(A, r, w);
+                if (v) {
+                    c += __popc(v);
+                    f = min(f, w * 32 + (__ffs((int)v) - 1));
+                    l = max(l, w * 32 + (31 - __clz((int)v)));
+                }
+            }
+        }
+        const bool nonempty = c > 0;
+        if (nonempty && c != l - f + 1) ok = false;          // more than one run in this row
+        // the row above (previous lane, or the carry for lane 0)
+        int pf = __shfl_up_sync(0xffffffffu, f, 1), pl = __shfl_up_sync(0xffffffffu, l, 1);
+        const unsigned ne = __ballot_sync(0xffffffffu, nonempty);
+        if (lane == 0) { pf = prev_f; pl = prev_l; }
+        const bool prev_nonempty = lane == 0 ? (prev_l >= 0) : ((ne >> (lane - 1)) & 1u);
+        if (nonempty && prev_nonempty && (f > pl + 1 || pf > l + 1)) ok = false;      // consecutive runs do not touch
+        // empty rows between non-empty ones: the non-empty rows of the whole plane must be consecutive
+        for (int k = 0; k < 32 && r0 + k < rows; ++k) {
+            const bool n_k = (ne >> k) & 1u;
+            if (state == 0 && n_k) state = 1;
+            else if (state == 1 && !n_k) state = 2;
+            else if (state == 2 && n_k) ok = false;
+        }
+        prev_f = __shfl_sync(0xffffffffu, f, 31); prev_l = __shfl_sync(0xffffffffu, l, 31);
+    }
+    return !__any_sync(0xffffffffu, !ok);
+}
+
 // Planes of one instance: shared memory when a padded plane fits EMIA_MORPH_SMEM_WORDS words (every particle-sized mask does:
 // a 120 x 120-px mask is 122 x 6 = 732 words), else the caller's global workspace at pad_off[inst] (emia_morph_plan counts
 // only those instances).  EMIA_MORPH_WARPS instances per CTA, one warp each, no CTA-wide barrier.
@@ -229,6 +298,15 @@ __global__ void __launch_bounds__(32 * EMIA_MORPH_WARPS) k_morph(
         const int op = ops[o];
         if (op == 0) break;
         if (op == EMIA_MORPH_FILL) {
+            // Shortcut (exact): a hole pixel has mask pixels to its left AND right in its row and above AND below in its column.
+            // When no background pixel is enclosed that way — every blob-like particle — there is nothing to fill and the
+            // flood is skipped.
+            if (words <= 32 && !emia_may_have_holes(cur, C, lane)) {
+                for (int k = lane; k < plane; k += 32) other.p[k] = cur.p[k];
+                __syncwarp();
+                EmiaPad t = cur; cur = other; other = t;
+                continue;
+            }
             // background reachable from the padded border (4-connected) ; holes = the rest of the background
             for (int k = lane; k < plane; k += 32) {
                 const int pr = k / words, pc = k - pr * words;
@@ -326,7 +404,7 @@ __global__ void __launch_bounds__(32 * EMIA_MORPH_WARPS) k_overlap_first_come(
     for (int k = lane; k < plane; k += 32) if (A.p[k]) { first = k; break; }
     for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
     bool multi = false;
-    if (first != 0x7fffffff) {
+    if (first != 0x7fffffff && !emia_single_blob(A, lane)) {
         if (lane == 0) R.p[first] = A.p[first] & (0u - A.p[first]);   // lowest set bit
         __syncwarp();
         emia_flood(R, A, 1, lane);

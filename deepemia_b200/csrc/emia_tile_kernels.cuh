@@ -102,18 +102,28 @@ __global__ void __launch_bounds__(128) k_resize_nearest_place(
     int tymin = 0x7fffffff, txmin = 0x7fffffff, tymax = -1, txmax = -1;           // unclipped mask, tile coordinates
     if (g.dy_lo <= g.dy_hi) {
         const int w0 = (ox + g.dx_lo) >> 5, w1 = (ox + g.dx_hi) >> 5;             // destination word columns (unclipped)
-        for (int dy = g.dy_lo; dy <= g.dy_hi; ++dy) {
-            const int sy = emia_nn_map(my, dy) - sm.ry0;
-            const int gy = oy + dy;
-            for (int w = w0; w <= w1; ++w) {
-                const int gx = w * 32 + lane;
-                const int dx = gx - ox;
+        // word column by word column: the source column of a destination pixel depends on the column only, so its (double
+        // precision) index map is evaluated once per lane and word column, not once per pixel
+        for (int w = w0; w <= w1; ++w) {
+            const int gx = w * 32 + lane;
+            const int dx = gx - ox;
+            const bool in_x = dx >= g.dx_lo && dx <= g.dx_hi;
+            int c = -1, sh = 0;
+            if (in_x) {
+                const int sx = emia_nn_map(mx, dx);
+                c = (sx >> 5) - sm.wc0;
+                sh = sx & 31;
+                if ((unsigned)c >= (unsigned)sm.cw) c = -1;
+            }
+            const bool stored_col = w >= dm.wc0 && w < dm.wc0 + dm.cw;
+            uint32_t colmask = 0xffffffffu;
+            const int lim = g.gx1 - w * 32;                                       // bits >= lim are outside the frame / tile
+            if (lim < 32) colmask = (lim <= 0) ? 0u : ((1u << lim) - 1u);
+            for (int dy = g.dy_lo; dy <= g.dy_hi; ++dy) {
+                const int sy = emia_nn_map(my, dy) - sm.ry0;
+                const int gy = oy + dy;
                 bool bit = false;
-                if (dx >= g.dx_lo && dx <= g.dx_hi && (unsigned)sy < (unsigned)sm.ch) {
-                    const int sx = emia_nn_map(mx, dx);
-                    const int c = (sx >> 5) - sm.wc0;
-                    if ((unsigned)c < (unsigned)sm.cw) bit = (sc[(size_t)sy * sm.cw + c] >> (sx & 31)) & 1u;
-                }
+                if (c >= 0 && (unsigned)sy < (unsigned)sm.ch) bit = (sc[(size_t)sy * sm.cw + c] >> sh) & 1u;
                 const uint32_t word = __ballot_sync(0xffffffffu, bit);
                 if (word) {
                     tymin = min(tymin, dy); tymax = max(tymax, dy);
@@ -121,10 +131,8 @@ __global__ void __launch_bounds__(128) k_resize_nearest_place(
                     txmax = max(txmax, w * 32 + (31 - __clz((int)word)) - ox);
                 }
                 // stored part: inside the clipped extent
-                if (gy >= g.gy0 && gy < g.gy1 && w >= dm.wc0 && w < dm.wc0 + dm.cw) {
-                    uint32_t keep = word;
-                    const int lim = g.gx1 - w * 32;                               // bits >= lim are outside the frame / tile
-                    if (lim < 32) keep &= (lim <= 0) ? 0u : ((1u << lim) - 1u);
+                if (stored_col && gy >= g.gy0 && gy < g.gy1) {
+                    const uint32_t keep = word & colmask;
                     if (lane == 0) dc[(size_t)(gy - dm.ry0) * dm.cw + (w - dm.wc0)] = keep;
                     if (keep) {
                         a += __popc(keep);
@@ -381,6 +389,76 @@ extern "C" int emia_color_sums(const uint32_t* crops, const emia_inst_meta* meta
     if (!crops || !meta || !crop_off || !image_bgr || !out) return emia_fail(EMIA_ERR_BAD_ARG, "emia_color_sums: %s", "null pointer");
     k_color_sums<<<(unsigned)((n * 32 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(crops, meta, crop_off, n, image_bgr, H, W, out);
     return emia_check_launch("emia_color_sums launch: %s");
+}
+
+// ---- visualisation overlay (src/functions/inference.py:1080-1145) ---------------------------------------------------------------
+// Per mask, IN LIST ORDER (later masks blend over earlier ones): colored_mask = color where mask; vis = cv2.addWeighted(vis, 1.0,
+// colored_mask, 0.5, 0) — i.e. every mask pixel becomes saturate(rint(v + 0.5 * color)) (round half to even), everything else is
+// unchanged — then cv2.drawContours(vis, contours, -1, color, 1): with CHAIN_APPROX_SIMPLE contours every segment is an axial or
+// diagonal run, so the drawn pixels are exactly the border-following chain, which is replayed here from the stored vertices.
+// One CTA walks the masks in order (the order is the semantics); its threads split the pixels / segments of the current mask.
+__global__ void __launch_bounds__(1024) k_overlay(uint8_t* __restrict__ image, int H, int W, const uint32_t* __restrict__ crops,
+                                                  const emia_inst_meta* __restrict__ meta, const int64_t* __restrict__ crop_off,
+                                                  const int32_t* __restrict__ order, int n, const int32_t* __restrict__ classes,
+                                                  const uint8_t* __restrict__ colors, int ncolors, const uint32_t* __restrict__ pts,
+                                                  const int64_t* __restrict__ pt_off, const int32_t* __restrict__ cstart, int cstart_stride,
+                                                  const int64_t* __restrict__ inst_cont_off, const int64_t* __restrict__ n_contours) {
+    for (int k = 0; k < n; ++k) {
+        const int i = order ? order[k] : k;
+        const emia_inst_meta m = meta[i];
+        const int cls = classes[i];
+        const uint8_t* col = colors + 3 * (((cls % ncolors) + ncolors) % ncolors);
+        const float cb = 0.5f * col[0], cg = 0.5f * col[1], cr = 0.5f * col[2];
+        const uint32_t* crop = crops + crop_off[i];
+        const int npx = m.ch * m.cw * 32;
+        for (int p = threadIdx.x; p < npx; p += blockDim.x) {
+            const int wi = p >> 5, b = p & 31;
+            if (!((crop[wi] >> b) & 1u)) continue;
+            const int r = wi / m.cw, c = wi - r * m.cw;
+            const int y = m.ry0 + r, x = (m.wc0 + c) * 32 + b;
+            if (x >= W || y >= H) continue;
+            uint8_t* px = image + ((size_t)y * W + x) * 3;
+            px[0] = (uint8_t)min(255.0f, rintf((float)px[0] + cb));
+            px[1] = (uint8_t)min(255.0f, rintf((float)px[1] + cg));
+            px[2] = (uint8_t)min(255.0f, rintf((float)px[2] + cr));
+        }
+        __syncthreads();
+        const int nc = (int)n_contours[i];
+        const int32_t* cs = cstart + (cstart_stride ? (size_t)i * cstart_stride : (size_t)(inst_cont_off[i] + i));
+        const uint32_t* pv = pts + pt_off[i];
+        for (int j = 0; j < nc; ++j) {
+            const int a = cs[j], mlen = cs[j + 1] - cs[j];
+            for (int sgm = threadIdx.x; sgm < mlen; sgm += blockDim.x) {
+                const uint32_t v0 = pv[a + sgm], v1 = pv[a + (sgm + 1 == mlen ? 0 : sgm + 1)];
+                int x = (int)(v0 & 0xFFFFu), y = (int)(v0 >> 16);
+                const int x1 = (int)(v1 & 0xFFFFu), y1 = (int)(v1 >> 16);
+                const int sx = (x1 > x) - (x1 < x), sy = (y1 > y) - (y1 < y);
+                const int steps = max(abs(x1 - x), abs(y1 - y));
+                for (int t = 0; t <= steps; ++t) {
+                    if ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H) {
+                        uint8_t* px = image + ((size_t)y * W + x) * 3;
+                        px[0] = col[0]; px[1] = col[1]; px[2] = col[2];
+                    }
+                    x += sx; y += sy;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+extern "C" int emia_overlay(uint8_t* image_bgr, int H, int W, const uint32_t* crops, const emia_inst_meta* meta,
+                            const int64_t* crop_off, const int32_t* order, int64_t n, const int32_t* classes,
+                            const uint8_t* colors_bgr, int32_t n_colors, const uint32_t* pts, const int64_t* pt_off,
+                            const int32_t* cstart, int32_t cstart_stride, const int64_t* inst_cont_off, const int64_t* n_contours,
+                            void* stream) {
+    if (n < 0 || H <= 0 || W <= 0 || n_colors <= 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_overlay: %s", "bad argument");
+    if (n == 0) return EMIA_OK;
+    if (!image_bgr || !crops || !meta || !crop_off || !classes || !colors_bgr || !pts || !pt_off || !cstart || !n_contours ||
+        (cstart_stride == 0 && !inst_cont_off))
+        return emia_fail(EMIA_ERR_BAD_ARG, "emia_overlay: %s", "null pointer");
+    k_overlay<<<1, 1024, 0, (cudaStream_t)stream>>>(image_bgr, H, W, crops, meta, crop_off, order, (int)n, classes, colors_bgr, n_colors, pts,
+                                                    pt_off, cstart, cstart_stride, inst_cont_off, n_contours);
+    return emia_check_launch("emia_overlay launch: %s");
 }
 
 // ---- masked grey-level histogram (contrast d10 / d50 / d90, src/utils/measurements.py:195-215) ---------------------------

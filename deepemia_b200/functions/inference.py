@@ -530,11 +530,10 @@ def measure_masks(masks, classes, image_shape, um_pix, test_img, psum, class_nam
     return rows
 
 
-def infer_image(predictors, image, num_classes, small_classes, class_specific_settings=None, confidence_mode='manual',
-                confidence_fn=None, tile_size=512, overlap_ratio=0.1, upscale_factor=2.0, edge_filter_enabled=True,
-                ensemble_enabled=True, ensemble_small_only=True, classes_to_infer=None, spatial_rules=None, dataset_name=None):
-    """The per-image body of run_inference (inference.py:776-905): per class tile_based_inference_pipeline, cross-class
-    deduplicate_masks_smart at 0.7, apply_spatial_constraints.  Returns (masks, scores, classes)."""
+def _infer_image_dev(predictors, image, num_classes, small_classes, class_specific_settings=None, confidence_mode='manual',
+                     confidence_fn=None, tile_size=512, overlap_ratio=0.1, upscale_factor=2.0, edge_filter_enabled=True,
+                     ensemble_enabled=True, ensemble_small_only=True, classes_to_infer=None, spatial_rules=None, dataset_name=None):
+    """The per-image body of run_inference (inference.py:776-905) with the result left on the device (_Dev)."""
     class_specific_settings = class_specific_settings or {}
     parts = []
     target_classes = range(num_classes) if classes_to_infer is None else [c for c in classes_to_infer if c < num_classes]
@@ -557,7 +556,7 @@ def infer_image(predictors, image, num_classes, small_classes, class_specific_se
                                                         class_specific_settings=class_specific_settings, confidence_mode=confidence_mode))
     allp = _concat(parts)
     if len(allp) == 0:
-        return [], [], []
+        return _EMPTY
     _with_scores(allp)
     keep = _dedup_smart_ids(allp.iset, 0.7)
     final = _select(allp, keep)
@@ -569,7 +568,13 @@ def infer_image(predictors, image, num_classes, small_classes, class_specific_se
             _with_scores(final)
             k2 = engine.apply_spatial_constraints(final.iset, _bridge.one_group(len(final), final.iset.device), rules).to_lists()[0]
             final = _select(final, k2)
-    return _lists(final)
+    return final
+
+
+def infer_image(predictors, image, num_classes, small_classes, **kwargs):
+    """The per-image body of run_inference (inference.py:776-905): per class tile_based_inference_pipeline, cross-class
+    deduplicate_masks_smart at 0.7, apply_spatial_constraints.  Returns (masks, scores, classes) as the reference's lists."""
+    return _lists(_infer_image_dev(predictors, image, num_classes, small_classes, **kwargs))
 
 
 # class colours of the overlay / legend, BGR (src/functions/inference.py:972-981)
@@ -589,26 +594,93 @@ def write_class_color_legend(output_dir, thing_classes):
     return path
 
 
+# ---- providers: what the reference's run_inference pulls from its own subsystems (config, dataset registry, model zoo, image
+# folder, scale-bar OCR).  A host application registers them once; run_inference is then callable exactly as main.py:480-488 does.
+_PROVIDERS = {"config": None, "thing_classes": None, "predictors": None, "images": None, "scale_bar": None}
+
+
+def set_providers(config=None, thing_classes=None, predictors=None, images=None, scale_bar=None):
+    """config(dataset_name) -> dict (the reference's get_config(dataset_name=...): `inference_settings` / `inference_overrides`,
+    `scale_bar_rois`); thing_classes(dataset_name) -> [names] (MetadataCatalog ...thing_classes); predictors(dataset_name,
+    threshold, thing_classes) -> [head adapters] (R50, R101 order; deepemia_b200.adapters); images(dataset_name) -> iterable of
+    (file name, BGR uint8 image); scale_bar(image, roi_config, dataset_name) -> (psum, um_pix) (detect_scale_bar).
+    Passing None leaves a provider unchanged; spatial rules come from utils.spatial_constraints.set_constraint_loader."""
+    for k, v in (("config", config), ("thing_classes", thing_classes), ("predictors", predictors), ("images", images),
+                 ("scale_bar", scale_bar)):
+        if v is not None:
+            _PROVIDERS[k] = v
+
+
+def clear_providers():
+    for k in _PROVIDERS:
+        _PROVIDERS[k] = None
+
+
 def run_inference(dataset_name, output_dir, visualize=True, threshold=0.65, draw_id=False, dataset_format="json", draw_scalebar=False,
-                  *, images=None, predictors=None, thing_classes=None, small_classes=(), scale_bar_fn=None, **infer_kwargs):
-    """run_inference (inference.py:499-507) reduced to the hot path: for every (name, BGR image) of `images` run infer_image,
-    write R50_flip_results.csv (ImageId, EncodedPixels), measurements_results.csv (the 20-column schema of :987-1010) and
-    class_color_legend.txt into output_dir.  Model construction, dataset listing, scale-bar OCR and the visualisation overlays are the reference's own
-    subsystems (out of scope): the caller passes `predictors`, `images`, and `scale_bar_fn(image) -> (psum, um_pix)`
-    (default: ("0", 1.0), the reference's fallback when no scale bar is found)."""
-    if images is None or predictors is None:
-        raise ValueError("run_inference needs `images` [(name, image), ...] and `predictors` (see the docstring)")
-    os.makedirs(output_dir, exist_ok=True)
+                  *, images=None, predictors=None, thing_classes=None, small_classes=None, scale_bar_fn=None, **infer_kwargs):
+    """run_inference (src/functions/inference.py:499-1351), same signature and call shape as main.py:480-488:
+
+        run_inference(dataset_name, output_dir, visualize=..., threshold=..., draw_id=..., dataset_format=..., draw_scalebar=...)
+
+    with the reference's own subsystems behind registered providers (set_providers) or the keyword-only overrides.  Settings are
+    read from the dataset config exactly as :517-556 does (confidence mode, class-specific settings, tile / ensemble settings,
+    classes_to_infer); small classes come from the mask-size heuristic (:719-723) unless given.  Per image: scale bar ->
+    per-class tile pipeline -> cross-class de-dup -> spatial constraints (:776-905), all on the device; the RLE rows of
+    R50_flip_results.csv and the rows of measurements_results.csv are produced from the SAME device-resident instance set (one
+    K6 and one K5 pass per image, no mask round trip).  Writes R50_flip_results.csv, measurements_results.csv,
+    class_color_legend.txt and, with visualize, <name>_predictions.png (overlay kernel + labels)."""
+    cfg_fn = _PROVIDERS["config"]
+    images = images if images is not None else (_PROVIDERS["images"](dataset_name) if _PROVIDERS["images"] else None)
+    if thing_classes is None and _PROVIDERS["thing_classes"]:
+        thing_classes = _PROVIDERS["thing_classes"](dataset_name)
     thing_classes = list(thing_classes or [])
-    num_classes = len(thing_classes) if thing_classes else int(infer_kwargs.pop("num_classes", 1))
-    conv = lambda l: " ".join(map(str, l))
-    img_ids, encoded, dedup_results = [], [], {}
+    if predictors is None and _PROVIDERS["predictors"]:
+        predictors = _PROVIDERS["predictors"](dataset_name, threshold, thing_classes)
+    if images is None or not predictors:
+        raise FileNotFoundError(f"No trained models / images registered for dataset '{dataset_name}': call "
+                                "deepemia_b200.functions.inference.set_providers(...) (or pass images= and predictors=)")
+    images = list(images)
+    dataset_config = cfg_fn(dataset_name) if cfg_fn else {}
+    inf_settings = dataset_config.get("inference_overrides", {}) or dataset_config.get("inference_settings", {})
+    tile_cfg = inf_settings.get("tile_settings", {})
+    ens_cfg = inf_settings.get("ensemble_settings", {})
+    kw = dict(class_specific_settings=inf_settings.get("class_specific_settings", {}),
+              confidence_mode=inf_settings.get("confidence_mode", "auto"),
+              tile_size=tile_cfg.get("tile_size", 512), overlap_ratio=tile_cfg.get("overlap_ratio", 0.1),
+              upscale_factor=tile_cfg.get("upscale_factor", 2.0), edge_filter_enabled=tile_cfg.get("edge_filter_enabled", True),
+              ensemble_enabled=ens_cfg.get("enabled", True), ensemble_small_only=ens_cfg.get("small_classes_only", True),
+              classes_to_infer=inf_settings.get("inference_settings", {}).get("classes_to_infer", None))
+    kw.update(infer_kwargs)
+    num_classes = len(thing_classes) if thing_classes else int(kw.pop("num_classes", 1))
+    kw.pop("num_classes", None)
+    if small_classes is None:
+        from ..adapters import calculate_average_mask_sizes, determine_small_classes
+        small_classes = determine_small_classes(calculate_average_mask_sizes(predictors, [im for _, im in images[:5]]), 50)
+    small_classes = set(small_classes)
+    rois = dataset_config.get("scale_bar_rois", {})
+    roi_config = rois.get(dataset_name, rois.get("default", {"x_start_factor": 0.667, "y_start_factor": 0.866, "width_factor": 1.0,
+                                                            "height_factor": 0.067}))
+    scale_bar = scale_bar_fn or ((lambda im: _PROVIDERS["scale_bar"](im, roi_config, dataset_name)) if _PROVIDERS["scale_bar"] else None)
+    os.makedirs(output_dir, exist_ok=True)
+    img_ids, encoded, meas_rows = [], [], []
     for name, image in images:
-        masks, scores, classes = infer_image(predictors, image, num_classes, set(small_classes), dataset_name=dataset_name, **infer_kwargs)
-        dedup_results[name] = {"masks": masks, "scores": scores, "classes": classes}
-        for mask in masks:
-            img_ids.append(name.rsplit(".", 1)[0])
-            encoded.append(conv(rle_encoding(mask)))
+        try:
+            psum, um_pix = scale_bar(image) if scale_bar is not None else ("0", 1.0)
+        except Exception:
+            psum, um_pix = "0", 1.0                                     # inference.py:767-773
+        d = _infer_image_dev(predictors, image, num_classes, small_classes, dataset_name=dataset_name, **kw)
+        if len(d) == 0:
+            continue
+        run_off, runs = engine.rle_encode(d.iset)                       # K6 over the final set, once
+        ro, rn = run_off.cpu().numpy(), runs.cpu().numpy()
+        stem = name.rsplit(".", 1)[0]
+        for i in range(len(d)):
+            img_ids.append(stem)
+            encoded.append(" ".join(str(int(v)) for v in rn[ro[i]:ro[i + 1]].reshape(-1)))
+        meas_rows += measure_masks(d.iset, d.classes, image.shape, um_pix, name, psum, class_names=thing_classes, original_image=image)
+        if visualize:
+            from ..utils.visualize import render_predictions
+            cv2.imwrite(os.path.join(output_dir, f"{name}_predictions.png"), render_predictions(image, d.iset, d.classes, thing_classes))
     with open(os.path.join(output_dir, "R50_flip_results.csv"), "w", newline="") as f:
         w = csv.writer(f)
         w.writerow(["ImageId", "EncodedPixels"])
@@ -616,11 +688,6 @@ def run_inference(dataset_name, output_dir, visualize=True, threshold=0.65, draw
     with open(os.path.join(output_dir, "measurements_results.csv"), "w", newline="") as f:
         w = csv.writer(f)
         w.writerow(CSV_HEADER)
-        for name, image in images:
-            psum, um_pix = scale_bar_fn(image) if scale_bar_fn is not None else ("0", 1.0)
-            r = dedup_results[name]
-            for row in measure_masks(r["masks"], r["classes"], image.shape, um_pix, name, psum, class_names=thing_classes,
-                                     original_image=image):
-                w.writerow(row)
+        w.writerows(meas_rows)
     write_class_color_legend(output_dir, thing_classes)
     return None

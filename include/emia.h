@@ -284,6 +284,15 @@ int emia_moments(const uint32_t* crops, const emia_inst_meta* meta, const int64_
 int emia_color_sums(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n,
                     const uint8_t* image_bgr, int H, int W, int64_t* out, void* stream);
 
+/* visualisation overlay of <name>_predictions.png (inference.py:1080-1100): for the n instances order[0..n) (NULL: 0..n-1), in that
+ * order: every mask pixel <- saturate(rint(v + 0.5 * colour)) (cv2.addWeighted(vis, 1.0, colored_mask, 0.5, 0)), then the external
+ * contours (vertex lists of emia_contour_trace_slab / emia_contour_store) drawn with the full colour (cv2.drawContours thickness 1).
+ * image_bgr: H x W x 3 bytes, modified in place; colours_bgr[n_colors][3], class c uses colour c % n_colors (:972-981). */
+int emia_overlay(uint8_t* image_bgr, int H, int W, const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off,
+                 const int32_t* order, int64_t n, const int32_t* classes, const uint8_t* colors_bgr, int32_t n_colors,
+                 const uint32_t* pts, const int64_t* pt_off, const int32_t* cstart, int32_t cstart_stride,
+                 const int64_t* inst_cont_off, const int64_t* n_contours, void* stream);
+
 /* 256-bin grey-level histogram of the image pixels under every instance (contrast d10/d50/d90, src/utils/measurements.py:
  * 195-215): image = H x W x channels bytes (3: BGR -> cv2's 8-bit BGR2GRAY fixed-point formula; 1: grey), hist[n][256]. */
 int emia_gray_hist(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n,
