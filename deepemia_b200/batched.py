@@ -214,8 +214,9 @@ def tile_pipeline(full_hb, tile_hb, tile_xy, image_hw, tile_size, overlap_ratio,
 
     xy_t, uoff_t = _layouts.get(key, make_xy)
     off_xy = engine.unit_broadcast(uoff_t, tile_hb.U, tile_hb.n, xy_t, 2)
-    comb.plan(0, post_f, h, w)
-    comb.plan(1, post_t, tile_size, tile_size, off_xy)
+    # only instances that are still in a list are back-projected (and later traced)
+    comb.plan(0, post_f, h, w, alive=engine.mark_members(post_f, _whole(kept_f), -1))
+    comb.plan(1, post_t, tile_size, tile_size, off_xy, alive=engine.mark_members(post_t, _whole(kept_t), -1))
     iset = comb.place(arena, tag="k3", edge={1: (tile_size, overlap_ratio)} if edge_filter_enabled else None)
     # ---- lists into the final space: full lists as they are, tile lists through the edge filter
     for c in range(C):
@@ -328,7 +329,8 @@ def ensemble_multiscale(heads, weights, image_hw, params, arena, sorted_iou=0.4,
             engine.filter_area(post, s1.section(c), min_size, out=final.section(pi * C + c))
         post.scores = engine.scale_scores(iset.scores, weights[m])
         posts.append(post)
-        comb.plan(pi, post, h, w)
+        alive = engine.mark_members(post, final.range(pi * C, (pi + 1) * C), -1)      # survivors of the size filter, any class
+        comb.plan(pi, post, h, w, alive=alive)
     iset = comb.place(arena, tag="k3")
     per_class_in = engine.flatten(final, lists, id_add, cache=tabs.setdefault("f1", {}))
     sp2 = _space_like(tabs, "sp2", per_class_in, dev)

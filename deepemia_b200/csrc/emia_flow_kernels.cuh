@@ -123,13 +123,13 @@ extern "C" int emia_group_mark_members(const int32_t* cap_off, int32_t G, int32_
 // output list s = the members of the groups grp_list[seg_start[s] .. seg_start[s+1]) one after the other (that order, list
 // order inside a group); its slots start at out_cap_off[s].  id_add[g] (optional, indexed by group) is added to every member id
 // of group g (instances that were re-numbered when their sets were combined).  One CTA per output list.
-__global__ void __launch_bounds__(256) k_group_flatten(const int32_t* __restrict__ cap_off, const int32_t* __restrict__ in_len,
+__global__ void __launch_bounds__(1024) k_group_flatten(const int32_t* __restrict__ cap_off, const int32_t* __restrict__ in_len,
                                                        const int32_t* __restrict__ in_idx, const int32_t* __restrict__ grp_list,
                                                        const int32_t* __restrict__ seg_start, const int32_t* __restrict__ id_add,
                                                        const int32_t* __restrict__ out_cap_off, int32_t* __restrict__ out_len,
                                                        int32_t* __restrict__ out_idx) {
-    __shared__ int s_off[256];
-    __shared__ int s_wsum[8];
+    __shared__ int s_off[1024];
+    __shared__ int s_wsum[32];
     __shared__ int s_run;
     const int sgm = blockIdx.x;
     const int ga = seg_start[sgm], gb = seg_start[sgm + 1];
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(256) k_group_flatten(const int32_t* __restrict
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_run = 0;
     __syncthreads();
-    for (int g0 = ga; g0 < gb; g0 += 256) {
+    for (int g0 = ga; g0 < gb; g0 += 1024) {
         const int gi = g0 + tid;
         const int len = (gi < gb) ? in_len[grp_list[gi]] : 0;
         int inc = len;
@@ -148,15 +148,15 @@ __global__ void __launch_bounds__(256) k_group_flatten(const int32_t* __restrict
         for (int w = 0; w < warp; ++w) wbase += s_wsum[w];
         s_off[tid] = wbase + inc - len;
         __syncthreads();
-        const int cnt = min(256, gb - g0);
-        for (int j = warp; j < cnt; j += 8) {
+        const int cnt = min(1024, gb - g0);
+        for (int j = warp; j < cnt; j += 32) {
             const int gj = grp_list[g0 + j];
             const int lj = in_len[gj], src = cap_off[gj], dst = obase + s_off[j];
             const int add = id_add ? id_add[gj] : 0;
             for (int k = lane; k < lj; k += 32) out_idx[dst + k] = in_idx[src + k] + add;
         }
         __syncthreads();
-        if (tid == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += s_wsum[w]; s_run += t; }
+        if (tid == 0) { int t = 0; for (int w = 0; w < 32; ++w) t += s_wsum[w]; s_run += t; }
         __syncthreads();
     }
     if (tid == 0) out_len[sgm] = s_run;
@@ -168,7 +168,7 @@ extern "C" int emia_group_flatten(const int32_t* cap_off, int32_t G, const int32
     if (S == 0) return EMIA_OK;
     if (!cap_off || !in_len || !in_idx || !grp_list || !seg_start || !out_cap_off || !out_len || !out_idx)
         return emia_fail(EMIA_ERR_BAD_ARG, "emia_group_flatten: %s", "null pointer");
-    k_group_flatten<<<(unsigned)S, 256, 0, (cudaStream_t)stream>>>(cap_off, in_len, in_idx, grp_list, seg_start, id_add, out_cap_off, out_len,
+    k_group_flatten<<<(unsigned)S, 1024, 0, (cudaStream_t)stream>>>(cap_off, in_len, in_idx, grp_list, seg_start, id_add, out_cap_off, out_len,
                                                                    out_idx);
     return emia_check_launch("emia_group_flatten launch: %s");
 }

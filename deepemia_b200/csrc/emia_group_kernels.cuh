@@ -97,24 +97,33 @@ __global__ void k_containment_rule_selfclass(const uint32_t* __restrict__ crops,
     }
 }
 
-// survivors (rem == 0) in list order, one warp per group
-__global__ void k_group_compact(const int32_t* __restrict__ cap_off, int G, const int32_t* __restrict__ in_len,
-                                const int32_t* __restrict__ in_idx, const int32_t* __restrict__ rem,
-                                int32_t* __restrict__ out_len, int32_t* __restrict__ out_idx) {
-    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (g >= G) return;
+// survivors (rem == 0) in list order, one CTA per group (block-wide ballot scan: a single list of a whole micrograph has
+// tens of thousands of slots)
+__global__ void __launch_bounds__(1024) k_group_compact(const int32_t* __restrict__ cap_off, int G, const int32_t* __restrict__ in_len,
+                                                        const int32_t* __restrict__ in_idx, const int32_t* __restrict__ rem,
+                                                        int32_t* __restrict__ out_len, int32_t* __restrict__ out_idx) {
+    __shared__ int s_w[32];
+    __shared__ int s_run;
+    const int g = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int base = cap_off[g], len = in_len[g];
-    int run = 0;
-    for (int k0 = 0; k0 < len; k0 += 32) {
-        const int k = k0 + lane;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (int k0 = 0; k0 < len; k0 += 1024) {
+        const int k = k0 + threadIdx.x;
         const int keep = (k < len) && !rem[base + k];
         const int inst = (k < len) ? in_idx[base + k] : 0;
         const unsigned b = __ballot_sync(0xffffffffu, keep);
-        if (keep) out_idx[base + run + __popc(b & ((1u << lane) - 1u))] = inst;
-        run += __popc(b);
+        if (lane == 0) s_w[warp] = __popc(b);
+        __syncthreads();
+        int before = s_run;
+        for (int w = 0; w < warp; ++w) before += s_w[w];
+        if (keep) out_idx[base + before + __popc(b & ((1u << lane) - 1u))] = inst;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 32; ++w) t += s_w[w]; s_run += t; }
+        __syncthreads();
     }
-    if (lane == 0) out_len[g] = run;
+    if (threadIdx.x == 0) out_len[g] = s_run;
 }
 
 #include "emia_group_fused.cuh"
@@ -157,7 +166,10 @@ static int emia_group_pipeline(int mode, const uint32_t* crops, const emia_inst_
     const int big = max_cap > 0 ? max_cap : L;
     const unsigned gy = (unsigned)std::min(16, std::max(1, (big + EMIA_SP_TILE - 1) / EMIA_SP_TILE));
     cudaMemsetAsync(ws.racc, 0, (size_t)((unsigned char*)ws.k1 - (unsigned char*)ws.racc), st);        // racc, xacc
-    k_sp_rank<<<dim3(gr, gy), EMIA_SP_THREADS, 0, st>>>(cap_off, G, L, in_len, rank_mode != 1, ws.k1, ws.k2, ws.kx, ws.racc, ws.xacc);
+    if (rank_mode != 2 && big <= 65536)
+        k_sp_rank<true><<<dim3(gr, gy), EMIA_SP_THREADS, 0, st>>>(cap_off, G, L, in_len, rank_mode != 1, ws.k1, ws.k2, ws.kx, ws.racc, ws.xacc);
+    else
+        k_sp_rank<false><<<dim3(gr, gy), EMIA_SP_THREADS, 0, st>>>(cap_off, G, L, in_len, rank_mode != 1, ws.k1, ws.k2, ws.kx, ws.racc, ws.xacc);
     k_sp_rank_finish<<<gl, T, 0, st>>>(cap_off, G, L, rank_mode != 1, ws.ok, ws.fidx, ws.kx, ws.racc, ws.xacc, ws.pos, ws.order, ws.xorder);
     const unsigned gp = (unsigned)(((size_t)L * 32 + EMIA_SP_THREADS - 1) / EMIA_SP_THREADS);
     k_sp_pairs<<<gp, EMIA_SP_THREADS, 0, st>>>(crops, meta, crop_off, bbox, area, classes, cap_off, G, in_idx, L, pair_mode, thr,
@@ -253,7 +265,6 @@ extern "C" int emia_containment_rules(const uint32_t* crops, const emia_inst_met
         return emia_fail(EMIA_ERR_WORKSPACE, "emia_containment_rules: %s", "workspace too small");
     const int T = 128;
     const unsigned gl = (unsigned)((L + T - 1) / T);
-    const unsigned gw = (unsigned)(((size_t)G * 32 + T - 1) / T);
     int32_t* rem_a = ws.rem;       // state before the current rule
     int32_t* rem_b = ws.ok;        // state after (children of this rule added)
     cudaMemsetAsync(rem_a, 0, (size_t)L * 4, st);
@@ -279,7 +290,10 @@ extern "C" int emia_containment_rules(const uint32_t* crops, const emia_inst_met
                 const int big = max_cap > 0 ? max_cap : L;
                 const unsigned gy = (unsigned)std::min(16, std::max(1, (big + EMIA_SP_TILE - 1) / EMIA_SP_TILE));
                 cudaMemsetAsync(ws.racc, 0, (size_t)((unsigned char*)ws.k1 - (unsigned char*)ws.racc), st);
-                k_sp_rank<<<dim3(gr, gy), EMIA_SP_THREADS, 0, st>>>(cap_off, G, L, in_len, 0, ws.k1, ws.k2, ws.kx, ws.racc, ws.xacc);
+                if (big <= 65536)
+                    k_sp_rank<true><<<dim3(gr, gy), EMIA_SP_THREADS, 0, st>>>(cap_off, G, L, in_len, 0, ws.k1, ws.k2, ws.kx, ws.racc, ws.xacc);
+                else
+                    k_sp_rank<false><<<dim3(gr, gy), EMIA_SP_THREADS, 0, st>>>(cap_off, G, L, in_len, 0, ws.k1, ws.k2, ws.kx, ws.racc, ws.xacc);
                 k_sp_rank_finish<<<gl, T, 0, st>>>(cap_off, G, L, 0, nullptr, nullptr, ws.kx, ws.racc, ws.xacc, nullptr, nullptr, ws.xorder);
                 const unsigned gp = (unsigned)(((size_t)L * 32 + EMIA_SP_THREADS - 1) / EMIA_SP_THREADS);
                 k_sp_pairs<<<gp, EMIA_SP_THREADS, 0, st>>>(crops, meta, crop_off, bbox, area, classes, cap_off, G, in_idx, L, 4, 0.0, nullptr,
@@ -289,7 +303,7 @@ extern "C" int emia_containment_rules(const uint32_t* crops, const emia_inst_met
             int32_t* t = rem_a; rem_a = rem_b; rem_b = t;
         }
     }
-    k_group_compact<<<gw, T, 0, st>>>(cap_off, G, in_len, in_idx, rem_a, out_len, out_idx);
+    k_group_compact<<<(unsigned)G, 1024, 0, st>>>(cap_off, G, in_len, in_idx, rem_a, out_len, out_idx);
     return emia_check_launch("emia_containment_rules launch: %s");
 }
 

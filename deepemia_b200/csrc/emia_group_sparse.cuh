@@ -128,23 +128,34 @@ __global__ void k_sp_keys(const int32_t* __restrict__ cap_off, int G, const int3
 // belong to several groups: the tiles of every group the CTA touches are streamed through shared memory, a thread only counts
 // in its own group's tiles), blockIdx.y = every gridDim.y-th key tile.  Partial counts are accumulated with atomicAdd into
 // racc / xacc (cleared by the caller); k_sp_rank_finish turns them into pos / order / xorder.
+// kNarrow: the keys are compared as 32-bit values in shared memory (score key; x_min << 16 | slot) — half the shared-memory
+// traffic and compare instructions; valid when the visit order does not involve the class (rank modes 0 / 1) and every group has
+// at most 65 536 slots.
+template <bool kNarrow>
 __global__ void __launch_bounds__(EMIA_SP_THREADS) k_sp_rank(const int32_t* __restrict__ cap_off, int G, int L,
                                                              const int32_t* __restrict__ in_len, int do_rank,
                                                              const uint64_t* __restrict__ k1, const uint32_t* __restrict__ k2,
                                                              const uint64_t* __restrict__ kx, int32_t* __restrict__ racc,
                                                              int32_t* __restrict__ xacc) {
-    __shared__ uint64_t s1[EMIA_SP_TILE];
-    __shared__ uint64_t sx[EMIA_SP_TILE];
+    typedef typename std::conditional<kNarrow, uint32_t, uint64_t>::type key_t;
+    __shared__ key_t s1[EMIA_SP_TILE];
+    __shared__ key_t sx[EMIA_SP_TILE];
     __shared__ uint32_t s2[EMIA_SP_TILE];
+    auto nar1 = [](uint64_t a) -> key_t { return kNarrow ? (key_t)(a > 0xFFFFFFFFull ? 0xFFFFFFFFull : a) : (key_t)a; };
+    auto narx = [](uint64_t x) -> key_t {
+        if (!kNarrow) return (key_t)x;
+        return x == ~0ull ? (key_t)0xFFFFFFFFu : (key_t)((((uint32_t)(x >> 32)) << 16) | ((uint32_t)x & 0xFFFFu));
+    };
     const int s_lo = blockIdx.x * EMIA_SP_THREADS;
     const int s_hi = min(L, s_lo + EMIA_SP_THREADS) - 1;
     const int s = s_lo + threadIdx.x;
     int my_g = -1;
-    uint64_t m1 = 0ull, mx = ~0ull;
+    uint64_t r1 = 0ull, rx = ~0ull;
     uint32_t m2 = 0u;
-    if (s < L) { my_g = emia_find_group(cap_off, G, s); m1 = do_rank ? k1[s] : 0ull; m2 = do_rank ? k2[s] : 0u; mx = kx[s]; }
-    const bool mine_ok = do_rank && (m1 != 0ull), mine_part = (mx != ~0ull);
+    if (s < L) { my_g = emia_find_group(cap_off, G, s); r1 = do_rank ? k1[s] : 0ull; m2 = do_rank ? k2[s] : 0u; rx = kx[s]; }
+    const bool mine_ok = do_rank && (r1 != 0ull), mine_part = (rx != ~0ull);
     if (!__syncthreads_or(mine_ok || mine_part)) return;            // a chunk of dead slots
+    const key_t m1 = nar1(r1), mx = narx(rx);
     const int g_lo = emia_find_group(cap_off, G, s_lo), g_hi = emia_find_group(cap_off, G, s_hi);
     int rank = 0, xr = 0;
     for (int g = g_lo; g <= g_hi; ++g) {
@@ -153,15 +164,15 @@ __global__ void __launch_bounds__(EMIA_SP_THREADS) k_sp_rank(const int32_t* __re
         for (int t0 = blockIdx.y * EMIA_SP_TILE; t0 < len; t0 += gridDim.y * EMIA_SP_TILE) {
             const int cnt = min(EMIA_SP_TILE, len - t0);
             for (int j = threadIdx.x; j < cnt; j += EMIA_SP_THREADS) {
-                if (do_rank) { s1[j] = k1[base + t0 + j]; s2[j] = k2[base + t0 + j]; }
-                sx[j] = kx[base + t0 + j];
+                if (do_rank) { s1[j] = nar1(k1[base + t0 + j]); s2[j] = k2[base + t0 + j]; }
+                sx[j] = narx(kx[base + t0 + j]);
             }
             __syncthreads();
             if (my_g == g) {
                 if (mine_ok) {
 #pragma unroll 8
                     for (int j = 0; j < cnt; ++j) {
-                        const uint64_t a = s1[j];
+                        const key_t a = s1[j];
                         rank += (a > m1) || (a == m1 && s2[j] > m2);
                     }
                 }

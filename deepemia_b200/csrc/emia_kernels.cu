@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <type_traits>
 #include "../../include/emia.h"
 #include "core/emia_common.cuh"
 #include "core/emia_contour.cuh"

@@ -194,6 +194,25 @@ __device__ bool emia_may_have_holes(const EmiaPad& M, const EmiaPad& T, int lane
     return __any_sync(0xffffffffu, found);
 }
 
+// true when every row of M holds at most one run of set pixels (then no background pixel has mask on both sides in its row,
+// so the mask has no holes).  Lanes own rows; ~10 instructions per word.
+__device__ bool emia_rows_single_run(const EmiaPad& M, int lane) {
+    bool ok = true;
+    for (int r = lane; r < M.rows; r += 32) {
+        int f = 0x7fffffff, l = -1, c = 0;
+        for (int w = 0; w < M.words; ++w) {
+            const uint32_t v = emia_pad_at(M, r, w);
+            if (v) {
+                c += __popc(v);
+                f = min(f, w * 32 + (__ffs((int)v) - 1));
+                l = max(l, w * 32 + (31 - __clz((int)v)));
+            }
+        }
+        if (c > 0 && c != l - f + 1) ok = false;
+    }
+    return !__any_sync(0xffffffffu, !ok);
+}
+
 // true when the mask in A is certainly ONE 8-connected component: every row is a single run of pixels, there is no empty row
 // between non-empty rows, and the runs of consecutive rows touch (also diagonally).  Lanes own rows.  (Sufficient, not necessary.)
 __device__ bool emia_single_blob(const EmiaPad& A, int lane) {
@@ -301,7 +320,7 @@ __global__ void __launch_bounds__(32 * EMIA_MORPH_WARPS) k_morph(
             // Shortcut (exact): a hole pixel has mask pixels to its left AND right in its row and above AND below in its column.
             // When no background pixel is enclosed that way — every blob-like particle — there is nothing to fill and the
             // flood is skipped.
-            if (words <= 32 && !emia_may_have_holes(cur, C, lane)) {
+            if (emia_rows_single_run(cur, lane) || (words <= 32 && !emia_may_have_holes(cur, C, lane))) {
                 for (int k = lane; k < plane; k += 32) other.p[k] = cur.p[k];
                 __syncwarp();
                 EmiaPad t = cur; cur = other; other = t;
@@ -565,7 +584,7 @@ __global__ void k_group_filter_area(const int32_t* __restrict__ cap_off, int G, 
 // postprocess_masks' column gate (mask_utils.py:62-68): np.sum(masks, axis=(0,1)) is a vector over the W frame
 // columns; K = number of columns whose total exceeds min_size; if K < len the list is truncated to its first K members
 // (K == 0 => empty list).  One CTA per group, column totals in shared memory.
-__global__ void __launch_bounds__(256) k_column_gate(const uint32_t* __restrict__ crops, const emia_inst_meta* __restrict__ meta,
+__global__ void __launch_bounds__(512) k_column_gate(const uint32_t* __restrict__ crops, const emia_inst_meta* __restrict__ meta,
                                                      const int64_t* __restrict__ crop_off, const int32_t* __restrict__ cap_off,
                                                      const int32_t* __restrict__ in_len, const int32_t* __restrict__ in_idx, int W,
                                                      int min_size, int32_t* __restrict__ out_len, int32_t* __restrict__ out_idx) {
@@ -621,7 +640,7 @@ extern "C" int emia_column_gate(const uint32_t* crops, const emia_inst_meta* met
         return emia_fail(EMIA_ERR_BAD_ARG, "emia_column_gate: %s", "null pointer");
     const size_t smem = (size_t)W * 4;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_column_gate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_column_gate<<<(unsigned)G, 256, smem, (cudaStream_t)stream>>>(crops, meta, crop_off, cap_off, in_len, in_idx, W, min_size,
+    k_column_gate<<<(unsigned)G, 512, smem, (cudaStream_t)stream>>>(crops, meta, crop_off, cap_off, in_len, in_idx, W, min_size,
                                                                    out_len, out_idx);
     return emia_check_launch("emia_column_gate launch: %s");
 }

@@ -62,8 +62,8 @@ __device__ __forceinline__ EmiaPlaceGeom emia_place_geom(const int32_t* sb, cons
 }
 
 __global__ void k_resize_place_plan(const int32_t* __restrict__ src_bbox, int64_t n, int Hs, int Ws, int th, int tw,
-                                    const int32_t* __restrict__ off_xy, int Hd, int Wd, emia_inst_meta* __restrict__ dst_meta,
-                                    int64_t* __restrict__ dst_crop_words) {
+                                    const int32_t* __restrict__ off_xy, const int32_t* __restrict__ alive, int Hd, int Wd,
+                                    emia_inst_meta* __restrict__ dst_meta, int64_t* __restrict__ dst_crop_words) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const EmiaNN my = emia_nn_make(Hs, th), mx = emia_nn_make(Ws, tw);
@@ -71,7 +71,7 @@ __global__ void k_resize_place_plan(const int32_t* __restrict__ src_bbox, int64_
     const EmiaPlaceGeom g = emia_place_geom(src_bbox + 4 * i, my, mx, ox, oy, Hd, Wd);
     emia_inst_meta m;
     m.valid = 1; m.reserved = 0;
-    if (g.gy0 < g.gy1) {
+    if (g.gy0 < g.gy1 && (!alive || alive[i])) {
         m.ry0 = g.gy0; m.ch = g.gy1 - g.gy0;
         m.rx0 = g.gx0; m.rx1 = g.gx1;
         m.wc0 = g.gx0 >> 5; m.cw = ((g.gx1 - 1) >> 5) - m.wc0 + 1;
@@ -87,10 +87,19 @@ __global__ void __launch_bounds__(128) k_resize_nearest_place(
     const uint32_t* __restrict__ src_crops, const emia_inst_meta* __restrict__ src_meta, const int64_t* __restrict__ src_crop_off,
     const int32_t* __restrict__ src_bbox, int64_t n, int Hs, int Ws, int th, int tw, const int32_t* __restrict__ off_xy, int Hd,
     int Wd, int edge_width, int tile_size, const emia_inst_meta* __restrict__ dst_meta, const int64_t* __restrict__ dst_crop_off,
-    uint32_t* __restrict__ dst_crops, int32_t* __restrict__ dst_bbox, int32_t* __restrict__ dst_area, int32_t* __restrict__ edge_flag) {
+    uint32_t* __restrict__ dst_crops, int32_t* __restrict__ dst_bbox, int32_t* __restrict__ dst_area, int32_t* __restrict__ edge_flag,
+    const int32_t* __restrict__ alive) {
     const int lane = threadIdx.x & 31;
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= n) return;
+    if (alive && !alive[i]) {                 // not a member of any list any more: no pixels, flagged as an edge mask
+        if (lane == 0) {
+            dst_area[i] = 0;
+            ((int4*)dst_bbox)[i] = make_int4(-1, -1, -1, -1);
+            if (edge_flag) edge_flag[i] = 1;
+        }
+        return;
+    }
     const EmiaNN my = emia_nn_make(Hs, th), mx = emia_nn_make(Ws, tw);
     const int ox = off_xy ? off_xy[2 * i] : 0, oy = off_xy ? off_xy[2 * i + 1] : 0;
     const EmiaPlaceGeom g = emia_place_geom(src_bbox + 4 * i, my, mx, ox, oy, Hd, Wd);
@@ -157,20 +166,21 @@ __global__ void __launch_bounds__(128) k_resize_nearest_place(
 }
 
 extern "C" int emia_resize_place_plan(const int32_t* src_bbox, int64_t n, int Hs, int Ws, int th, int tw, const int32_t* off_xy,
-                                      int Hd, int Wd, emia_inst_meta* dst_meta, int64_t* dst_crop_words, void* stream) {
+                                      const int32_t* alive, int Hd, int Wd, emia_inst_meta* dst_meta, int64_t* dst_crop_words,
+                                      void* stream) {
     if (n < 0 || Hs <= 0 || Ws <= 0 || th <= 0 || tw <= 0 || Hd <= 0 || Wd <= 0)
         return emia_fail(EMIA_ERR_BAD_ARG, "emia_resize_place_plan: %s", "bad shape");
     if (n == 0) return EMIA_OK;
     if (!src_bbox || !dst_meta || !dst_crop_words) return emia_fail(EMIA_ERR_BAD_ARG, "emia_resize_place_plan: %s", "null pointer");
-    k_resize_place_plan<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(src_bbox, n, Hs, Ws, th, tw, off_xy, Hd, Wd, dst_meta,
-                                                                                    dst_crop_words);
+    k_resize_place_plan<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(src_bbox, n, Hs, Ws, th, tw, off_xy, alive, Hd, Wd,
+                                                                                    dst_meta, dst_crop_words);
     return emia_check_launch("emia_resize_place_plan launch: %s");
 }
 extern "C" int emia_resize_nearest_place(const uint32_t* src_crops, const emia_inst_meta* src_meta, const int64_t* src_crop_off,
                                          const int32_t* src_bbox, int64_t n, int Hs, int Ws, int th, int tw, const int32_t* off_xy,
                                          int Hd, int Wd, int edge_width, int tile_size, const emia_inst_meta* dst_meta,
                                          const int64_t* dst_crop_off, uint32_t* dst_crops, int32_t* dst_bbox, int32_t* dst_area,
-                                         int32_t* edge_flag, void* stream) {
+                                         int32_t* edge_flag, const int32_t* alive, void* stream) {
     if (n < 0 || Hs <= 0 || Ws <= 0 || th <= 0 || tw <= 0 || Hd <= 0 || Wd <= 0)
         return emia_fail(EMIA_ERR_BAD_ARG, "emia_resize_nearest_place: %s", "bad shape");
     if (n == 0) return EMIA_OK;
@@ -178,7 +188,7 @@ extern "C" int emia_resize_nearest_place(const uint32_t* src_crops, const emia_i
         return emia_fail(EMIA_ERR_BAD_ARG, "emia_resize_nearest_place: %s", "null pointer");
     k_resize_nearest_place<<<(unsigned)((n * 32 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
         src_crops, src_meta, src_crop_off, src_bbox, n, Hs, Ws, th, tw, off_xy, Hd, Wd, edge_width, tile_size, dst_meta, dst_crop_off,
-        dst_crops, dst_bbox, dst_area, edge_flag);
+        dst_crops, dst_bbox, dst_area, edge_flag, alive);
     return emia_check_launch("emia_resize_nearest_place launch: %s");
 }
 

@@ -769,6 +769,23 @@ class GroupSpace:
             self._sections[k] = sec
         return sec
 
+    def range(self, k0, k1):
+        """Sections k0 .. k1-1 as ONE Groups object (their groups are contiguous in the space)."""
+        key = ("range", k0, k1)
+        sec = self._sections.get(key)
+        if sec is None:
+            a, b = int(self.g0[k0]), int(self.g0[k1])
+            l0, l1 = int(self.cap_abs[a]), int(self.cap_abs[b])
+            host = (self.cap_abs[a:b + 1] - self.cap_abs[a]).astype(np.int32)
+            tabs = self._rebased_tables()
+            dev_tab = tabs.get(key)
+            if dev_tab is None:
+                dev_tab = torch.as_tensor(host, device=self.dev)
+                tabs[key] = dev_tab
+            sec = Groups(cap_off_host=host, cap_off=dev_tab, length=self.length[a:b], idx=self.idx[l0:max(l1, l0 + 1)])
+            self._sections[key] = sec
+        return sec
+
     def group_index(self, k, j=0):
         return int(self.g0[k]) + j
 
@@ -888,7 +905,7 @@ def resize_place(iset, th, tw, Hd, Wd, off_xy=None, tile_size=None, overlap_rati
         off_xy = torch.as_tensor(off_xy, dtype=torch.int32, device=dev).contiguous()
         assert off_xy.shape == (n, 2)
     st = _stream()
-    _lib.check(lib.emia_resize_place_plan(_ptr(iset.bbox), n, iset.H, iset.W, th, tw, _ptr(off_xy), Hd, Wd, _ptr(meta), _ptr(crop_off), st),
+    _lib.check(lib.emia_resize_place_plan(_ptr(iset.bbox), n, iset.H, iset.W, th, tw, _ptr(off_xy), 0, Hd, Wd, _ptr(meta), _ptr(crop_off), st),
                "emia_resize_place_plan")
     exclusive_scan_(crop_off)
     total = int(crop_off[n].item()) if n else 0
@@ -903,7 +920,7 @@ def resize_place(iset, th, tw, Hd, Wd, off_xy=None, tile_size=None, overlap_rati
         edge_width = int(tile_size * overlap_ratio / 2)
     _lib.check(lib.emia_resize_nearest_place(_ptr(iset.crops), _ptr(iset.meta), _ptr(iset.crop_off), _ptr(iset.bbox), n, iset.H, iset.W,
                                              th, tw, _ptr(off_xy), Hd, Wd, edge_width, ts, _ptr(meta), _ptr(crop_off), _ptr(crops),
-                                             _ptr(bbox), _ptr(area), _ptr(edge), st), "emia_resize_nearest_place")
+                                             _ptr(bbox), _ptr(area), _ptr(edge), 0, st), "emia_resize_nearest_place")
     LAUNCHES["count"] += 2
     out = InstanceSet(n=n, H=Hd, W=Wd, meta=meta, crop_off=crop_off, crops=crops, bbox=bbox, area=area, scores=iset.scores,
                       classes=iset.classes, total_crop_words=total)
@@ -934,17 +951,18 @@ class Combined:
         self.total = 0
         self._parts = []
 
-    def plan(self, p, src, th, tw, off_xy=None):
+    def plan(self, p, src, th, tw, off_xy=None, alive=None):
         """Part p <- cv2.resize(mask, (tw, th), INTER_NEAREST) of every instance of `src`, placed at off_xy[i] (int32 [n,2] device
-        tensor of (x, y) offsets, or None).  Only the geometry is computed here."""
+        tensor of (x, y) offsets, or None).  alive (optional int32 [n]): instances with 0 are no longer in any list and are not
+        resampled.  Only the geometry is computed here."""
         lib = _lib.load()
         a, b = int(self.start[p]), int(self.start[p + 1])
         assert b - a == src.n
         if src.n:
-            _lib.check(lib.emia_resize_place_plan(_ptr(src.bbox), src.n, src.H, src.W, th, tw, _ptr(off_xy), self.H, self.W,
+            _lib.check(lib.emia_resize_place_plan(_ptr(src.bbox), src.n, src.H, src.W, th, tw, _ptr(off_xy), _ptr(alive), self.H, self.W,
                                                   _ptr(self.meta[a:]), _ptr(self.crop_off[a:]), _stream()), "emia_resize_place_plan")
             LAUNCHES["count"] += 1
-        self._parts.append((p, src, th, tw, off_xy))
+        self._parts.append((p, src, th, tw, off_xy, alive))
 
     def place(self, arena=None, tag="k3", edge=None):
         """Scan the crop sizes of all planned parts, size the crop buffer (exactly, or arena capacity + device-side guard) and
@@ -953,14 +971,14 @@ class Combined:
         n = self.n
         exclusive_scan_(self.crop_off)
         if arena is not None:
-            total = arena.cap(tag + ".crops", sum(int(src.total_crop_words) for _, src, _, _, _ in self._parts) + 64 * n + 1024)
+            total = arena.cap(tag + ".crops", sum(int(part[1].total_crop_words) for part in self._parts) + 64 * n + 1024)
             arena.guard(tag + ".crops", self.crop_off[n:], self.meta, n)
         else:
             total = int(self.crop_off[n].item()) if n else 0
         self.total = total
         self.crops = torch.empty(max(total, 1), dtype=torch.int32, device=self.dev)
         st = _stream()
-        for p, src, th, tw, off_xy in self._parts:
+        for p, src, th, tw, off_xy, alive in self._parts:
             a = int(self.start[p])
             if not src.n:
                 continue
@@ -974,7 +992,7 @@ class Combined:
                 _lib.check(lib.emia_resize_nearest_place(_ptr(src.crops), _ptr(src.meta), _ptr(src.crop_off), _ptr(src.bbox), src.n, src.H,
                                                          src.W, th, tw, _ptr(off_xy), self.H, self.W, ew, ts, _ptr(self.meta[a:]),
                                                          _ptr(self.crop_off[a:]), _ptr(self.crops), _ptr(self.bbox[a:]), _ptr(self.area[a:]),
-                                                         _ptr(ef), st), "emia_resize_nearest_place")
+                                                         _ptr(ef), _ptr(alive), st), "emia_resize_nearest_place")
             LAUNCHES["count"] += 1
             if src.scores is not None:
                 self.scores[a:a + src.n].copy_(src.scores)
@@ -1002,45 +1020,77 @@ def scale_scores(scores, weight, out=None):
     return out
 
 
-def select(iset, idx):
-    """A new InstanceSet holding instances idx (device or host int array) of `iset`, crops re-packed (device gathers only)."""
-    dev = iset.device
-    idx = torch.as_tensor(idx, dtype=torch.int64, device=dev)
-    k = int(idx.numel())
-    meta = iset.meta[idx].contiguous()
-    words = (meta[:, 2].to(torch.int64) * meta[:, 3].to(torch.int64))
-    crop_off = torch.zeros(k + 1, dtype=torch.int64, device=dev)
+def _gather_into(src, idx_t, k, meta, crop_off, a):
+    """Plan step of a gather: geometry of src[idx] into rows [a, a + k) of (meta, crop_off-as-sizes)."""
+    lib = _lib.load()
     if k:
-        crop_off[1:] = torch.cumsum(words, 0)
-    total = int(crop_off[k].item()) if k else 0
-    crops = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
-    if total:
-        # word j of the new buffer comes from old_off[inst(j)] + (j - new_off[inst(j)])
-        owner = torch.repeat_interleave(torch.arange(k, device=dev), words)
-        src = iset.crop_off[idx][owner] + (torch.arange(total, device=dev) - crop_off[:-1][owner])
-        crops[:total] = iset.crops[src]
-    pick = lambda t: None if t is None else t[idx].contiguous()
-    return InstanceSet(n=k, H=iset.H, W=iset.W, meta=meta, crop_off=crop_off, crops=crops, bbox=pick(iset.bbox), area=pick(iset.area),
-                       scores=pick(iset.scores), classes=pick(iset.classes), total_crop_words=total)
+        _lib.check(lib.emia_gather_plan(_ptr(src.meta), _ptr(idx_t), k, _ptr(meta[a:]), _ptr(crop_off[a:]), _stream()), "emia_gather_plan")
+        LAUNCHES["count"] += 1
+
+
+def _gather_copy(src, idx_t, k, dst, a):
+    lib = _lib.load()
+    if not k:
+        return
+    _lib.check(lib.emia_gather_crops(_ptr(src.crops), _ptr(src.crop_off), _ptr(src.bbox), _ptr(src.area), _ptr(idx_t), k, _ptr(dst.meta[a:]),
+                                     _ptr(dst.crop_off[a:]), _ptr(dst.crops), _ptr(dst.bbox[a:]), _ptr(dst.area[a:]), _stream()),
+               "emia_gather_crops")
+    LAUNCHES["count"] += 1
+    for name in ("scores", "classes"):
+        s_, d_ = getattr(src, name), getattr(dst, name)
+        if s_ is None or d_ is None:
+            continue
+        if idx_t is None:
+            d_[a:a + k].copy_(s_[:k])
+        else:
+            _lib.check(lib.emia_gather_b32(_ptr(s_), _ptr(idx_t), k, _ptr(d_[a:]), _stream()), "emia_gather_b32")
+            LAUNCHES["count"] += 1
+
+
+def _empty_set(n, H, W, dev, scores=True, classes=True):
+    return InstanceSet(n=n, H=H, W=W, meta=torch.empty((n, 8), dtype=torch.int32, device=dev),
+                       crop_off=torch.zeros(n + 1, dtype=torch.int64, device=dev), crops=None,
+                       bbox=torch.empty((n, 4), dtype=torch.int32, device=dev), area=torch.empty(n, dtype=torch.int32, device=dev),
+                       scores=torch.empty(n, dtype=torch.float32, device=dev) if scores else None,
+                       classes=torch.empty(n, dtype=torch.int32, device=dev) if classes else None)
+
+
+def select(iset, idx):
+    """A new InstanceSet holding instances idx (device or host int array) of `iset`, crops re-packed (emia_gather_* kernels)."""
+    dev = iset.device
+    idx_t = torch.as_tensor(np.asarray(idx, np.int32) if not torch.is_tensor(idx) else idx, dtype=torch.int32, device=dev).contiguous()
+    k = int(idx_t.numel())
+    out = _empty_set(k, iset.H, iset.W, dev, iset.scores is not None, iset.classes is not None)
+    _gather_into(iset, idx_t, k, out.meta, out.crop_off, 0)
+    exclusive_scan_(out.crop_off)
+    total = int(out.crop_off[k].item()) if k else 0
+    out.crops = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    out.total_crop_words = total
+    _gather_copy(iset, idx_t, k, out, 0)
+    return out
 
 
 def concat(isets):
-    """Concatenate InstanceSets of the same frame size (e.g. full-image pass + every tile, src/functions/inference.py:2452-2454)."""
+    """Concatenate InstanceSets of the same frame size (e.g. full-image pass + every tile, src/functions/inference.py:2452-2454):
+    one plan launch per part, one scan, one copy launch per part."""
     isets = [s for s in isets if s is not None]
     assert isets and all(s.H == isets[0].H and s.W == isets[0].W for s in isets)
     dev = isets[0].device
     n = sum(s.n for s in isets)
-    total = sum(s.total_crop_words for s in isets)
-    crop_off = torch.empty(n + 1, dtype=torch.int64, device=dev)
-    pos, base = 0, 0
-    for s in isets:
-        crop_off[pos:pos + s.n] = s.crop_off[:s.n] + base
-        pos += s.n; base += s.total_crop_words
-    crop_off[n] = base
-    crops = torch.cat([s.crops[:s.total_crop_words] for s in isets]) if total else torch.empty(1, dtype=torch.int32, device=dev)
-    cat = lambda name: (torch.cat([getattr(s, name)[:s.n] for s in isets]) if all(getattr(s, name) is not None for s in isets) else None)
-    return InstanceSet(n=n, H=isets[0].H, W=isets[0].W, meta=torch.cat([s.meta for s in isets]), crop_off=crop_off, crops=crops,
-                       bbox=cat("bbox"), area=cat("area"), scores=cat("scores"), classes=cat("classes"), total_crop_words=total)
+    out = _empty_set(n, isets[0].H, isets[0].W, dev, all(s.scores is not None for s in isets), all(s.classes is not None for s in isets))
+    a = 0
+    for s_ in isets:
+        _gather_into(s_, None, s_.n, out.meta, out.crop_off, a)
+        a += s_.n
+    exclusive_scan_(out.crop_off)
+    total = int(out.crop_off[n].item()) if n else 0
+    out.crops = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    out.total_crop_words = total
+    a = 0
+    for s_ in isets:
+        _gather_copy(s_, None, s_.n, out, a)
+        a += s_.n
+    return out
 
 
 def rle_encode(iset, idx=None):

@@ -252,14 +252,16 @@ int emia_column_gate(const uint32_t* crops, const emia_inst_meta* meta, const in
  * like `global_mask[y:y_end, x:x_end] = downscaled[:y_end - y, :x_end - x]`.
  * emia_resize_place_plan: destination geometry + crop sizes (caller scans).  emia_resize_nearest_place: destination crops,
  * bbox, area and (optional) edge_flag[i] = is_edge_mask(downscaled mask, tile_size, overlap) with edge_width =
- * int(tile_size * overlap_ratio / 2) — evaluated on the UNCLIPPED tile-sized mask; empty => 1. */
+ * int(tile_size * overlap_ratio / 2) — evaluated on the UNCLIPPED tile-sized mask; empty => 1.
+ * alive (optional, both calls): instances with alive[i] == 0 (no longer a member of any list) get an empty destination and edge
+ * flag 1 without being resampled. */
 int emia_resize_place_plan(const int32_t* src_bbox, int64_t n, int Hs, int Ws, int th, int tw, const int32_t* off_xy,
-                           int Hd, int Wd, emia_inst_meta* dst_meta, int64_t* dst_crop_words, void* stream);
+                           const int32_t* alive, int Hd, int Wd, emia_inst_meta* dst_meta, int64_t* dst_crop_words, void* stream);
 int emia_resize_nearest_place(const uint32_t* src_crops, const emia_inst_meta* src_meta, const int64_t* src_crop_off,
                               const int32_t* src_bbox, int64_t n, int Hs, int Ws, int th, int tw, const int32_t* off_xy,
                               int Hd, int Wd, int edge_width, int tile_size, const emia_inst_meta* dst_meta,
                               const int64_t* dst_crop_off, uint32_t* dst_crops, int32_t* dst_bbox, int32_t* dst_area,
-                              int32_t* edge_flag, void* stream);
+                              int32_t* edge_flag, const int32_t* alive, void* stream);
 /* list members whose flag[inst] == keep_value, list order kept */
 int emia_group_filter_flag(const int32_t* cap_off, int32_t G, const int32_t* in_len, const int32_t* in_idx,
                            const int32_t* flag, int32_t keep_value, int32_t* out_len, int32_t* out_idx, void* stream);

@@ -1,6 +1,6 @@
-"""CPU, world_size 2 over gloo: the one data-path collective of the path — the variable-length all-gather of bit-packed instance
-records for the cross-GPU de-duplication of a split micrograph (deepemia_b200/distributed.py) — reproduces the rank-major
-concatenation on every rank, including an empty rank and ragged sizes."""
+"""CPU, world_size 3 over gloo: the data-path exchange of the split-micrograph flow (deepemia_b200/distributed.py) — ONE size
+all-gather + ONE byte-packed payload all-gather of bit-packed instance records — reproduces the rank-major concatenation on
+every rank, including an empty rank, ragged sizes and the per-class list lengths that travel with the sizes."""
 import os
 import sys
 
@@ -59,9 +59,17 @@ def _worker(rank, world, port, out):
     masks, scores, classes = _rank_data(rank)
     iset = _cpu_instance_set(masks, scores, classes) if masks else _cpu_instance_set([], [], [])
     iset.H, iset.W = 64, 96
-    allset, counts = D.all_gather_instances(iset)
+    calls = {"n": 0}
+    real = dist.all_gather
+
+    def counting(*a, **k):
+        calls["n"] += 1
+        return real(*a, **k)
+    dist.all_gather = counting
+    allset, sizes = D.all_gather_packed(iset, extra=[rank + 1, 7])
+    dist.all_gather = real
     out.put((rank, allset.n, allset.meta.numpy(), allset.crop_off.numpy(), allset.crops[:allset.total_crop_words].numpy(),
-             allset.scores.numpy(), allset.classes.numpy(), allset.bbox.numpy(), counts.tolist()))
+             allset.scores.numpy(), allset.classes.numpy(), allset.bbox.numpy(), sizes.tolist(), calls["n"], allset.area.numpy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -81,13 +89,17 @@ def test_variable_length_all_gather_three_ranks():
         p.join(timeout=60)
         assert p.exitcode == 0
     parts = [_cpu_instance_set(*_rank_data(r)) for r in range(world) if len(_rank_data(r)[0])]
-    ref = engine.concat(parts)
-    for rank, n, meta, crop_off, crops, scores, classes, bbox, counts in results:
-        assert counts == [5, 0, 9] and n == 14
-        assert np.array_equal(meta, ref.meta.numpy()) and np.array_equal(crop_off, ref.crop_off.numpy())
-        assert np.array_equal(crops, ref.crops[:ref.total_crop_words].numpy())
-        assert np.array_equal(scores, ref.scores.numpy()) and np.array_equal(classes, ref.classes.numpy())
-        assert np.array_equal(bbox, ref.bbox.numpy())
+    cat = lambda name: np.concatenate([getattr(p, name).numpy()[:p.n] for p in parts])
+    ref_crops = np.concatenate([p.crops.numpy()[:p.total_crop_words] for p in parts])
+    bases = np.concatenate([[0], np.cumsum([p.total_crop_words for p in parts])])
+    ref_off = np.concatenate([p.crop_off.numpy()[:p.n] + b for p, b in zip(parts, bases)] + [[bases[-1]]])
+    for rank, n, meta, crop_off, crops, scores, classes, bbox, sizes, n_coll, area in results:
+        assert [s[0] for s in sizes] == [5, 0, 9] and n == 14 and n_coll == 2          # exactly two collectives
+        assert [s[2:] for s in sizes] == [[1, 7], [2, 7], [3, 7]]
+        assert np.array_equal(meta, cat("meta")) and np.array_equal(crop_off, ref_off)
+        assert np.array_equal(crops, ref_crops)
+        assert np.array_equal(scores, cat("scores")) and np.array_equal(classes, cat("classes"))
+        assert np.array_equal(bbox, cat("bbox")) and np.array_equal(area, cat("area"))
     # contiguous bands: rank-major order is the global tile order
     assert [D.band_of_rank(10, r, 3) for r in range(3)] == [(0, 4), (4, 7), (7, 10)]
     assert [D.band_of_rank(2, r, 4) for r in range(4)] == [(0, 1), (1, 2), (2, 2), (2, 2)]

@@ -47,14 +47,15 @@ def test_flow_matches_reference(cuda_device, name):
         assert int(classes[i]) == int(g["classes"][i])
 
 
-def test_split_micrograph_two_gpus(cuda_device):
-    """Config 3 across 2 GPUs (skipped on a 1-GPU box; the CPU suite covers the all-gather with gloo)."""
+@pytest.mark.parametrize("nproc", [1, 2])
+def test_split_micrograph(cuda_device, nproc):
+    """Config 3 over `nproc` GPUs (2: skipped on a 1-GPU box; the CPU suite covers the two collectives with gloo)."""
     import subprocess
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29611", os.path.join(HERE, "dist_split_micrograph.py")]
+    if torch.cuda.device_count() < nproc:
+        pytest.skip(f"needs {nproc} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
+           "--master-port", str(29611 + nproc), os.path.join(HERE, "dist_split_micrograph.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert r.stdout.count("OK") == 4
+    assert r.stdout.count("OK") == 2 * nproc
