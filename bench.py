@@ -237,11 +237,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flows", action="store_true", help="skip the config 2 / 3a / 3b / 4 legs")
     ap.add_argument("--flows-only", default="", help="comma list of config2,config3a,config3b,config4: run only those legs")
+    ap.add_argument("--workload", default="", help="config3a | config3b: ONE micrograph split over all ranks (torchrun), see bench_flows.run_split_workload")
     ap.add_argument("--breakdown", action="store_true", help="extra untimed pass with per-stage CUDA events (stderr)")
     ap.add_argument("--device-pass-only", action="store_true", help="profiling aid: run only the warm-up + timed device-resident steps")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.workload:
+        import bench_flows
+        return bench_flows.run_split_workload(args.workload, args.steps, args.warmup)
 
     import torch
     import torch.distributed as dist

@@ -506,7 +506,7 @@ def tile_based_inference_pipeline(predictor, image, target_class, small_classes,
 # =================================================================================================================
 def measure_masks(masks, classes, image_shape, um_pix, test_img, psum, class_names=None, original_image=None):
     """Rows of measurements_results.csv for one image: one row per external contour whose contourArea reaches the gate (Q12)."""
-    if len(masks) == 0:
+    if (masks.n if isinstance(masks, engine.InstanceSet) else len(masks)) == 0:
         return []
     iset = masks if isinstance(masks, engine.InstanceSet) else _bridge.upload(masks)
     engine.measure(iset, um_pix=um_pix, min_area=engine.default_min_area(image_shape[0], image_shape[1]))

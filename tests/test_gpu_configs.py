@@ -33,7 +33,8 @@ def test_config1_measurement_extraction_200_masks(cuda_device):
         np.testing.assert_allclose(a, b, rtol=1e-5, atol=0)
         exact += np.array_equal(a, b)
         assert [type(v) for v in r[3:15]] == [type(v) for v in q[3:15]]          # numpy scalar types of the CSV cells (Q14)
-    assert exact >= 0.95 * len(ref)
+    print(f"PARITY-COUNT config1: rows {len(ref)} bit-exact {exact}")
+    assert exact >= 193          # measured on B200: 193 of the 200 rows are bit-identical, the other 7 differ in the last float32 / float64 ulp (<= 1e-5 asserted above)
 
 
 def test_config3_8192_micrograph_tiles(cuda_device):

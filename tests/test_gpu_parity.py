@@ -173,7 +173,8 @@ def test_contours_and_measurements_match_opencv(cuda_device, single_pass):
             assert r[engine.REC_AREA] == cv2.contourArea(c) and r[engine.REC_PERIM] == cv2.arcLength(c, True)
             assert r[engine.REC_NVERT] == len(c)
     exact, total = _check_records(iset, masks, classes, H, W, 0.5)
-    assert exact >= 0.95 * total, f"only {exact}/{total} rows bit-exact"
+    print(f"PARITY-COUNT contours[{single_pass}]: rows {total} bit-exact {exact}")
+    assert total == 127 and exact >= 126, f"only {exact}/{total} rows bit-exact"       # measured on B200: 126 of 127
     # contours below the area gate are skipped before calculate_measurements (src/functions/inference.py:1176-1190): their records
     # carry area / perimeter / vertex count (checked above) and nothing else
     below = rec[rec[:, engine.REC_MEASURED] != 1.0]
