@@ -439,10 +439,10 @@ def main():
     del pipe_c
     # ---------------- end-to-end (host buffers) ----------------
     # pinned host copies of two shards; batches sized so that the H2D copy of batch b+1 hides behind the kernels of batch b
-    # without over-decomposing a small (multi-GPU) shard (every batch costs ~40 launches of host time): ~64 tiles per batch,
-    # at most 12 batches
+    # without over-decomposing a small (multi-GPU) shard (the latency-bound kernels of a batch cost ~0.5 ms whatever its size:
+    # measured on a 256-tile shard, 2 / 4 / 8 / 12 batches take 6.3 / 7.1 / 8.5 / 10.7 ms): ~128 tiles per batch, at most 12
     E = min(2, V)
-    e2e_batches = args.e2e_batches or int(max(2, min(12, round(len(shards[0]["tiles"]) / 64.0))))
+    e2e_batches = args.e2e_batches or int(max(2, min(12, round(len(shards[0]["tiles"]) / 128.0))))
     pipe_e2e = engine.TilePipeline(H, W, um_pix=UM_PIX, rules=rules, dedup_iou=DEDUP_IOU, frames=arena, variant=args.variant,
                                    batches=e2e_batches, paste_ctas_per_sm=args.paste_ctas, device=dev)
     hosts = []
@@ -461,14 +461,35 @@ def main():
     def e2e_leg(key):
         for hd in hosts:
             e2e_step(hd, key)
+            e2e_step(hd, key)
+        # the whole pipelined step (H2D copies, kernels of the three streams, D2H result copies) of every resident host shard
+        # captured in a CUDA graph: per step the host launches one graph and waits for the results
+        eg = []
+        if not args.no_graph:
+            pool_e = None
+            for hd in hosts:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool_e):
+                    r = pipe_e2e.run(hd[key], hd["boxes"], hd["scores"], hd["classes"], hd["offs"], to_host=True)
+                pool_e = g.pool()
+                eg.append((g, r, pipe_e2e._abort))
+
+        def one(i):
+            if eg:
+                g, r, ab = eg[i % E]
+                g.replay()
+                torch.cuda.current_stream().synchronize()
+                assert not int(ab.item()), "a capacity guard tripped in an end-to-end step"
+                return r
+            return e2e_step(hosts[i % E], key)
         for i in range(max(2, args.warmup)):
-            r = e2e_step(hosts[i % E], key)
+            r = one(i)
         barrier()
         wall, n_e = [], 0
         ev[0].record()
         for i in range(args.steps):
             t0 = time.perf_counter()
-            r = e2e_step(hosts[i % E], key)
+            r = one(i)
             n_e += hosts[i % E]["n"]
             wall.append(round((time.perf_counter() - t0) * 1e3, 2))
         ev[1].record()

@@ -1369,13 +1369,14 @@ class TilePipeline:
             LAUNCHES["count"] += 1
         crops = torch.empty(max(total_words, 1), dtype=torch.int32, device=dev)
         marks = torch.empty(max(2 * total_words, 1), dtype=torch.int32, device=dev)
-        # under CUDA-graph capture (or with one batch and device inputs there is nothing to overlap) everything runs on the
-        # caller's stream: the captured step is a single chain of kernel nodes
+        # under CUDA-graph capture with device inputs (one batch: nothing to overlap) everything runs on the caller's stream: the
+        # captured step is a single chain of kernel nodes
         capturing = torch.cuda.is_current_stream_capturing()
-        s_paste = main if capturing else self.s_paste
-        s_post = main if capturing else self.s_post
+        single = capturing and not host_in          # host inputs keep the three-stream pipeline: captured as parallel graph branches
+        s_paste = main if single else self.s_paste
+        s_post = main if single else self.s_post
         if capturing:
-            assert hints is not None and not host_in, "capture needs the sync-free path: run the shard once eagerly first"
+            assert hints is not None, "capture needs the sync-free path: run the shard once eagerly first"
             time_k1 = False
         s_paste.wait_stream(main); s_post.wait_stream(main)
         isets, ev_paste = [], []
