@@ -318,15 +318,15 @@ def ensemble_multiscale(heads, weights, image_hw, params, arena, sorted_iou=0.4,
             engine.filter_heads(iset, s0.section(c), p.target_class, p.confidence_threshold, out=s1.section(c))
         # postprocess_masks_universal: the operator chain depends on the class (erosion only for small classes), the minimum
         # size on class and scale (process_single_scale :2026-2031: int(base * scale^2) of the ORIGINAL image area)
-        post = None
+        # one launch for both kinds of class: selector 1 = opening (large classes), 2 = erosion only (small classes)
+        sel = None
         for c, p in enumerate(params):
-            members = engine.mark_members(iset, s1.section(c), -1)
-            src = post if post is not None else iset
-            post = engine.morph(src, [engine.MORPH_FILL, engine.MORPH_ERODE] if p.is_small else
-                                [engine.MORPH_FILL, engine.MORPH_ERODE, engine.MORPH_DILATE], apply=members, arena=arena, tag=f"ems{pi}.univ{c}")
+            sel = engine.mark_members(iset, s1.section(c), -1, value=2 if p.is_small else 1, into=sel)
+        post = engine.morph(iset, [engine.MORPH_FILL, engine.MORPH_ERODE, engine.MORPH_DILATE], apply=sel, arena=arena, tag=f"ems{pi}.univ",
+                            ops_b=[engine.MORPH_FILL, engine.MORPH_ERODE])
+        for c, p in enumerate(params):
             base_min = max(3, int(area0 * 0.000005)) if p.is_small else max(25, int(area0 * 0.0001))
-            min_size = base_min if s == 1.0 else int(base_min * (s ** 2))
-            engine.filter_area(post, s1.section(c), min_size, out=final.section(pi * C + c))
+            engine.filter_area(post, s1.section(c), int(base_min * (s ** 2)), out=final.section(pi * C + c))
         post.scores = engine.scale_scores(iset.scores, weights[m])
         posts.append(post)
         alive = engine.mark_members(post, final.range(pi * C, (pi + 1) * C), -1)      # survivors of the size filter, any class

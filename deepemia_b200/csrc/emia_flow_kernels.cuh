@@ -98,25 +98,26 @@ extern "C" int emia_group_filter_heads(const int32_t* cap_off, int32_t G, const 
     return emia_check_launch("emia_group_filter_heads launch: %s");
 }
 
-// flag[inst] = 1 for the members of lists longer than min_len (flag is cleared first; n_inst entries)
+// flag[inst] = value for the members of lists longer than min_len (n_inst entries; cleared first unless keep != 0)
 __global__ void k_group_mark_members(const int32_t* __restrict__ cap_off, int G, int L, const int32_t* __restrict__ in_len,
-                                     const int32_t* __restrict__ in_idx, int min_len, int32_t* __restrict__ flag) {
+                                     const int32_t* __restrict__ in_idx, int min_len, int value, int32_t* __restrict__ flag) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= L) return;
     const int g = emia_find_group(cap_off, G, s);
     const int len = in_len[g];
-    if (s - cap_off[g] < len && len > min_len) flag[in_idx[s]] = 1;
+    if (s - cap_off[g] < len && len > min_len) flag[in_idx[s]] = value;
 }
 extern "C" int emia_group_mark_members(const int32_t* cap_off, int32_t G, int32_t total_cap, const int32_t* in_len,
-                                       const int32_t* in_idx, int32_t min_len, int32_t* flag, int64_t n_inst, void* stream) {
+                                       const int32_t* in_idx, int32_t min_len, int32_t value, int32_t keep, int32_t* flag, int64_t n_inst,
+                                       void* stream) {
     if (G < 0 || total_cap < 0 || n_inst < 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_group_mark_members: %s", "bad argument");
     if (n_inst == 0) return EMIA_OK;
     if (!flag) return emia_fail(EMIA_ERR_BAD_ARG, "emia_group_mark_members: %s", "null pointer");
-    cudaMemsetAsync(flag, 0, (size_t)n_inst * 4, (cudaStream_t)stream);
+    if (!keep) cudaMemsetAsync(flag, 0, (size_t)n_inst * 4, (cudaStream_t)stream);
     if (G == 0 || total_cap == 0) return EMIA_OK;
     if (!cap_off || !in_len || !in_idx) return emia_fail(EMIA_ERR_BAD_ARG, "emia_group_mark_members: %s", "null pointer");
     k_group_mark_members<<<(unsigned)((total_cap + 127) / 128), 128, 0, (cudaStream_t)stream>>>(cap_off, G, total_cap, in_len, in_idx,
-                                                                                              min_len, flag);
+                                                                                              min_len, value, flag);
     return emia_check_launch("emia_group_mark_members launch: %s");
 }
 

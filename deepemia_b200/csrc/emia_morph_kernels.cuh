@@ -254,10 +254,15 @@ __device__ bool emia_single_blob(const EmiaPad& A, int lane) {
 
 // Planes of one instance: shared memory when a padded plane fits EMIA_MORPH_SMEM_WORDS words (every particle-sized mask does:
 // a 120 x 120-px mask is 122 x 6 = 732 words), else the caller's global workspace at pad_off[inst] (emia_morph_plan counts
-// only those instances).  EMIA_MORPH_WARPS instances per CTA, one warp each, no CTA-wide barrier.
-#define EMIA_MORPH_WARPS 4
+// only those instances).  One warp per instance, EMIA_MORPH_WARPS warps per CTA, no CTA-wide barrier; k_morph is a persistent
+// grid (a warp takes every gridDim.x * EMIA_MORPH_WARPS-th instance).
+#define EMIA_MORPH_WARPS 6
 #define EMIA_MORPH_SMEM_WORDS 1024
-#define EMIA_MORPH_SMEM_BYTES (EMIA_MORPH_WARPS * 3 * EMIA_MORPH_SMEM_WORDS * 4)
+#define EMIA_MORPH_SMEM_BYTES (EMIA_MORPH_WARPS * 2 * EMIA_MORPH_SMEM_WORDS * 4)      // two planes per warp: 48 KB per CTA, 4 CTAs / SM
+#define EMIA_MORPH_MAX_CTAS (148 * 4)                                               // persistent grid of k_morph
+// a THIRD plane is only needed by the rare instances that go through the hole test / flood: it lives in a global scratch slot
+// per resident warp (the first EMIA_MORPH_SCRATCH_WORDS words of `work`)
+#define EMIA_MORPH_SCRATCH_WORDS (EMIA_MORPH_MAX_CTAS * EMIA_MORPH_WARPS * EMIA_MORPH_SMEM_WORDS)
 
 // bbox / area of a crop-shaped output held in registers across the lanes (called by all 32 lanes)
 struct EmiaStat { int a, ymin, xmin, ymax, xmax; };
@@ -281,81 +286,93 @@ __device__ __forceinline__ void emia_stat_store(EmiaStat s, int lane, int64_t in
     }
 }
 
-// ops: up to 4 operator codes.  apply (optional): instances with apply[inst] == 0 are copied unchanged (the reference runs
-// process_masks_parallel only on lists of more than two masks, src/functions/inference.py:1443).  bbox_out / area_out
-// (optional): bbox / popcount of the result, so no separate statistics pass is needed.
+// ops: up to 4 operator codes per chain.  apply (optional) selects per instance: 0 = copied unchanged (the reference runs
+// process_masks_parallel only on lists of more than two masks, src/functions/inference.py:1443), 1 = chain A (op0..op3),
+// 2 = chain B (opb0..opb3: postprocess_masks_universal uses erosion only for small classes and an opening for the others,
+// :1786-1796, so one launch serves both kinds of class).  bbox_out / area_out (optional): bbox / popcount of the result.
 __global__ void __launch_bounds__(32 * EMIA_MORPH_WARPS) k_morph(
     const uint32_t* __restrict__ crops, const emia_inst_meta* __restrict__ meta, const int64_t* __restrict__ crop_off, int64_t n,
-    int H, int W, int op0, int op1, int op2, int op3, const int64_t* __restrict__ pad_off, uint32_t* __restrict__ work,
+    int H, int W, int op0, int op1, int op2, int op3, int opb0, int opb1, int opb2, int opb3, const int64_t* __restrict__ pad_off,
+    uint32_t* __restrict__ work,
     const emia_inst_meta* __restrict__ meta_out, const int64_t* __restrict__ crop_off_out, uint32_t* __restrict__ crops_out,
     const int32_t* __restrict__ apply, int32_t* __restrict__ bbox_out, int32_t* __restrict__ area_out) {
     extern __shared__ uint32_t s_planes[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t inst = (int64_t)blockIdx.x * EMIA_MORPH_WARPS + warp;
-    if (inst >= n) return;
-    const emia_inst_meta m = meta[inst];
-    const emia_inst_meta mo = meta_out[inst];
-    EmiaStat st;
-    emia_stat_init(st);
-    if (m.ch <= 0 || m.cw <= 0) { emia_stat_store(st, lane, inst, bbox_out, area_out); return; }
-    const int rows = m.ch + 2, words = m.cw + 2;
-    const int plane = rows * words;
-    uint32_t* base = (plane <= EMIA_MORPH_SMEM_WORDS) ? (s_planes + warp * 3 * EMIA_MORPH_SMEM_WORDS) : (work + 3 * pad_off[inst]);
-    EmiaPad A{base, rows, words}, B{base + plane, rows, words}, C{base + 2 * plane, rows, words};
-    const uint32_t* crop = crops + crop_off[inst];
-    for (int k = lane; k < plane; k += 32) {
-        const int pr = k / words, pc = k - pr * words;
-        uint32_t v = 0u;
-        if (pr >= 1 && pr <= m.ch && pc >= 1 && pc <= m.cw) v = crop[(size_t)(pr - 1) * m.cw + (pc - 1)];
-        A.p[k] = v;
-    }
-    __syncwarp();
-    const int ops[4] = {op0, op1, op2, op3};
-    EmiaPad cur = A, other = B;
-    const bool on = (apply == nullptr) || (apply[inst] != 0);
-    for (int o = 0; on && o < 4; ++o) {
-        const int op = ops[o];
-        if (op == 0) break;
-        if (op == EMIA_MORPH_FILL) {
-            // Shortcut (exact): a hole pixel has mask pixels to its left AND right in its row and above AND below in its column.
-            // When no background pixel is enclosed that way — every blob-like particle — there is nothing to fill and the
-            // flood is skipped.
-            if (emia_rows_single_run(cur, lane) || (words <= 32 && !emia_may_have_holes(cur, C, lane))) {
-                for (int k = lane; k < plane; k += 32) other.p[k] = cur.p[k];
-                __syncwarp();
-                EmiaPad t = cur; cur = other; other = t;
-                continue;
+    const int slot = blockIdx.x * EMIA_MORPH_WARPS + warp;
+    for (int64_t inst = slot; inst < n; inst += (int64_t)gridDim.x * EMIA_MORPH_WARPS) {
+        const emia_inst_meta m = meta[inst];
+        const emia_inst_meta mo = meta_out[inst];
+        EmiaStat st;
+        emia_stat_init(st);
+        if (m.ch <= 0 || m.cw <= 0) { emia_stat_store(st, lane, inst, bbox_out, area_out); continue; }
+        const uint32_t* crop = crops + crop_off[inst];
+        uint32_t* out = crops_out + crop_off_out[inst];
+        const int sel = apply ? apply[inst] : 1;
+        if (sel == 0) {
+            // pass-through: the input bits in the output geometry (identical, or grown by one pixel), no planes involved
+            for (int k = lane; k < mo.ch * mo.cw; k += 32) {
+                const int r = k / mo.cw, c = k - r * mo.cw;
+                const int ir = mo.ry0 + r - m.ry0, ic = mo.wc0 + c - m.wc0;
+                const uint32_t v = ((unsigned)ir < (unsigned)m.ch && (unsigned)ic < (unsigned)m.cw) ? crop[(size_t)ir * m.cw + ic] : 0u;
+                out[k] = v;
+                emia_stat_word(st, v, mo.ry0 + r, mo.wc0 + c);
             }
-            // background reachable from the padded border (4-connected) ; holes = the rest of the background
-            for (int k = lane; k < plane; k += 32) {
-                const int pr = k / words, pc = k - pr * words;
-                const bool ring = (pr == 0 || pr == rows - 1 || pc == 0 || pc == words - 1);
-                C.p[k] = ~cur.p[k];                       // allowed = background
-                other.p[k] = ring ? ~cur.p[k] : 0u;       // seeds
-            }
-            __syncwarp();
-            emia_flood(other, C, 0, lane);
-            for (int k = lane; k < plane; k += 32) {
-                const int pr = k / words, pc = k - pr * words;
-                const bool inner = (pr >= 1 && pr <= m.ch && pc >= 1 && pc <= m.cw);
-                other.p[k] = inner ? ~other.p[k] : 0u;    // mask | holes = everything the flood did not reach
-            }
-            __syncwarp();
-        } else {
-            emia_cross_op(other, cur, op == EMIA_MORPH_DILATE, m.ry0, m.wc0, H, W, lane);
+            emia_stat_store(st, lane, inst, bbox_out, area_out);
+            continue;
         }
-        EmiaPad t = cur; cur = other; other = t;
+        const int rows = m.ch + 2, words = m.cw + 2;
+        const int plane = rows * words;
+        const bool in_smem = plane <= EMIA_MORPH_SMEM_WORDS;
+        uint32_t* base = in_smem ? (s_planes + warp * 2 * EMIA_MORPH_SMEM_WORDS) : (work + EMIA_MORPH_SCRATCH_WORDS + 3 * pad_off[inst]);
+        EmiaPad A{base, rows, words}, B{base + plane, rows, words};
+        EmiaPad C{in_smem ? (work + (size_t)slot * EMIA_MORPH_SMEM_WORDS) : (base + 2 * plane), rows, words};
+        for (int k = lane; k < plane; k += 32) {
+            const int pr = k / words, pc = k - pr * words;
+            uint32_t v = 0u;
+            if (pr >= 1 && pr <= m.ch && pc >= 1 && pc <= m.cw) v = crop[(size_t)(pr - 1) * m.cw + (pc - 1)];
+            A.p[k] = v;
+        }
+        __syncwarp();
+        const int ops[4] = {sel == 2 ? opb0 : op0, sel == 2 ? opb1 : op1, sel == 2 ? opb2 : op2, sel == 2 ? opb3 : op3};
+        EmiaPad cur = A, other = B;
+        for (int o = 0; o < 4; ++o) {
+            const int op = ops[o];
+            if (op == 0) break;
+            if (op == EMIA_MORPH_FILL) {
+                // Shortcut (exact): a hole pixel has mask pixels to its left AND right in its row and above AND below in its
+                // column.  When no background pixel is enclosed that way — every blob-like particle — there is nothing to fill.
+                if (emia_rows_single_run(cur, lane) || (words <= 32 && !emia_may_have_holes(cur, C, lane))) continue;
+                // background reachable from the padded border (4-connected) ; holes = the rest of the background
+                for (int k = lane; k < plane; k += 32) {
+                    const int pr = k / words, pc = k - pr * words;
+                    const bool ring = (pr == 0 || pr == rows - 1 || pc == 0 || pc == words - 1);
+                    C.p[k] = ~cur.p[k];                       // allowed = background
+                    other.p[k] = ring ? ~cur.p[k] : 0u;       // seeds
+                }
+                __syncwarp();
+                emia_flood(other, C, 0, lane);
+                for (int k = lane; k < plane; k += 32) {
+                    const int pr = k / words, pc = k - pr * words;
+                    const bool inner = (pr >= 1 && pr <= m.ch && pc >= 1 && pc <= m.cw);
+                    other.p[k] = inner ? ~other.p[k] : 0u;    // mask | holes = everything the flood did not reach
+                }
+                __syncwarp();
+            } else {
+                emia_cross_op(other, cur, op == EMIA_MORPH_DILATE, m.ry0, m.wc0, H, W, lane);
+            }
+            EmiaPad t = cur; cur = other; other = t;
+        }
+        // output geometry: the input's, or (a chain that dilates first) the crop grown by one pixel towards every frame border —
+        // out-of-frame neighbours are ignored by the erosion, so a closing can grow a mask that ends one pixel short of the border
+        for (int k = lane; k < mo.ch * mo.cw; k += 32) {
+            const int r = k / mo.cw, c = k - r * mo.cw;
+            const uint32_t v = emia_pad_at(cur, mo.ry0 + r - (m.ry0 - 1), mo.wc0 + c - (m.wc0 - 1));
+            out[k] = v;
+            emia_stat_word(st, v, mo.ry0 + r, mo.wc0 + c);
+        }
+        emia_stat_store(st, lane, inst, bbox_out, area_out);
+        __syncwarp();
     }
-    // output geometry: the input's, or (a chain that dilates first) the crop grown by one pixel towards every frame border —
-    // out-of-frame neighbours are ignored by the erosion, so a closing can grow a mask that ends one pixel short of the border
-    uint32_t* out = crops_out + crop_off_out[inst];
-    for (int k = lane; k < mo.ch * mo.cw; k += 32) {
-        const int r = k / mo.cw, c = k - r * mo.cw;
-        const uint32_t v = emia_pad_at(cur, mo.ry0 + r - (m.ry0 - 1), mo.wc0 + c - (m.wc0 - 1));
-        out[k] = v;
-        emia_stat_word(st, v, mo.ry0 + r, mo.wc0 + c);
-    }
-    emia_stat_store(st, lane, inst, bbox_out, area_out);
 }
 
 // first-come overlap removal + "more than one 8-connected component => zero" (postprocess_masks tail), one warp per list slot.
@@ -379,7 +396,8 @@ __global__ void __launch_bounds__(32 * EMIA_MORPH_WARPS) k_overlap_first_come(
     emia_stat_init(st);
     if (m.ch <= 0 || m.cw <= 0) { emia_stat_store(st, lane, inst, bbox_out, area_out); return; }
     const int rows = m.ch + 2, words = m.cw + 2, plane = rows * words;
-    uint32_t* wb = (plane <= EMIA_MORPH_SMEM_WORDS) ? (s_planes + warp * 3 * EMIA_MORPH_SMEM_WORDS) : (work + 3 * pad_off[inst]);
+    uint32_t* wb = (plane <= EMIA_MORPH_SMEM_WORDS) ? (s_planes + warp * 2 * EMIA_MORPH_SMEM_WORDS)
+                                                      : (work + EMIA_MORPH_SCRATCH_WORDS + 3 * pad_off[inst]);
     EmiaPad A{wb, rows, words}, R{wb + plane, rows, words};
     const uint32_t* crop = crops + crop_off[inst];
     for (int k = lane; k < plane; k += 32) {
@@ -503,6 +521,7 @@ extern "C" int emia_morph_grow_plan(const emia_inst_meta* meta, int64_t n, int H
     return emia_check_launch("emia_morph_grow_plan launch: %s");
 }
 
+extern "C" size_t emia_morph_scratch_words(void) { return (size_t)EMIA_MORPH_SCRATCH_WORDS; }
 extern "C" int emia_morph_plan(const emia_inst_meta* meta, int64_t n, int64_t* pad_words, void* stream) {
     if (n < 0) return emia_fail(EMIA_ERR_BAD_ARG, "emia_morph_plan: %s", "bad n");
     if (n == 0) return EMIA_OK;
@@ -522,6 +541,16 @@ extern "C" int emia_morph(const uint32_t* crops, const emia_inst_meta* meta, con
                           const int32_t* ops_host, int32_t n_ops, const int64_t* pad_off, uint32_t* work,
                           const emia_inst_meta* meta_out, const int64_t* crop_off_out, uint32_t* crops_out,
                           const int32_t* apply_flag, int32_t* bbox_out, int32_t* area_out, void* stream) {
+    // n_ops > 4: two chains — ops_host[0..3] (zero-padded) for apply_flag 1, ops_host[4..n_ops) for apply_flag 2
+    int opsb[4] = {0, 0, 0, 0};
+    if (n_ops > 4 && n_ops <= 8 && ops_host) {
+        for (int i = 4; i < n_ops; ++i) {
+            if (ops_host[i] < 0 || ops_host[i] > 3) return emia_fail(EMIA_ERR_BAD_ARG, "emia_morph: %s", "unknown operator");
+            opsb[i - 4] = ops_host[i];
+        }
+        n_ops = 4;
+        while (n_ops > 1 && ops_host[n_ops - 1] == 0) --n_ops;
+    }
     if (n < 0 || n_ops < 1 || n_ops > 4 || !ops_host) return emia_fail(EMIA_ERR_BAD_ARG, "emia_morph: %s", "bad argument");
     if (n == 0) return EMIA_OK;
     if (!crops || !meta || !crop_off || !pad_off || !work || !crops_out) return emia_fail(EMIA_ERR_BAD_ARG, "emia_morph: %s", "null pointer");
@@ -533,9 +562,10 @@ extern "C" int emia_morph(const uint32_t* crops, const emia_inst_meta* meta, con
         ops[i] = ops_host[i];
     }
     emia_morph_smem_attr();
-    k_morph<<<(unsigned)((n + EMIA_MORPH_WARPS - 1) / EMIA_MORPH_WARPS), 32 * EMIA_MORPH_WARPS, EMIA_MORPH_SMEM_BYTES, (cudaStream_t)stream>>>(
-        crops, meta, crop_off, n, H, W, ops[0], ops[1], ops[2], ops[3], pad_off, work, meta_out, crop_off_out, crops_out, apply_flag,
-        bbox_out, area_out);
+    const int64_t want = (n + EMIA_MORPH_WARPS - 1) / EMIA_MORPH_WARPS;
+    k_morph<<<(unsigned)(want < EMIA_MORPH_MAX_CTAS ? want : EMIA_MORPH_MAX_CTAS), 32 * EMIA_MORPH_WARPS, EMIA_MORPH_SMEM_BYTES, (cudaStream_t)stream>>>(
+        crops, meta, crop_off, n, H, W, ops[0], ops[1], ops[2], ops[3], opsb[0], opsb[1], opsb[2], opsb[3], pad_off, work, meta_out,
+        crop_off_out, crops_out, apply_flag, bbox_out, area_out);
     return emia_check_launch("emia_morph launch: %s");
 }
 extern "C" int emia_overlap_first_come(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, const int32_t* bbox,

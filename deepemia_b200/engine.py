@@ -291,7 +291,7 @@ def _pad_plan(iset, arena=None, tag="k2"):
         arena.guard(tag + ".work", pad_off[iset.n:], iset.meta, iset.n)
     else:
         total = int(pad_off[iset.n].item()) if iset.n else 0
-    work = torch.empty(max(3 * total, 1), dtype=torch.int32, device=iset.device)
+    work = torch.empty(int(lib.emia_morph_scratch_words()) + 3 * total + 1, dtype=torch.int32, device=iset.device)
     iset.extra["pad_plan"] = (pad_off, work)
     return pad_off, work
 
@@ -314,15 +314,20 @@ def _derived(iset, crops, geometry=None, bbox=None, area=None):
     return out
 
 
-def morph(iset, ops, apply=None, arena=None, tag="k2"):
+def morph(iset, ops, apply=None, arena=None, tag="k2", ops_b=None):
     """K2: apply `ops` (MORPH_FILL / MORPH_ERODE / MORPH_DILATE, 3x3 cross, at most 4) to every instance (apply: optional int32
-    flag per instance, 0 = pass through unchanged).  The result has the geometry of the input, or — a chain that dilates
+    selector per instance, 0 = pass through unchanged, 1 = `ops`, 2 = `ops_b`).  The result has the geometry of the input, or — a chain that dilates
     first — the crop grown by one pixel.  bbox / area of the result come from the same kernel.  With an arena: no host sync."""
     lib = _lib.load()
+    chains = [list(ops)] + ([list(ops_b)] if ops_b is not None else [])
+    grows = False
+    for ch in chains:
+        structuring = [int(o) for o in ch if int(o) != MORPH_FILL]
+        grows = grows or (bool(structuring) and structuring[0] == MORPH_DILATE)
+    if ops_b is not None:
+        ops = list(ops) + [0] * (4 - len(ops)) + list(ops_b)
     ops = np.ascontiguousarray(ops, dtype=np.int32)
     pad_off, work = _pad_plan(iset, arena, tag)
-    structuring = [int(o) for o in ops if int(o) != MORPH_FILL]
-    grows = bool(structuring) and structuring[0] == MORPH_DILATE
     geometry = None
     meta_out = crop_off_out = None
     if grows and iset.n:
@@ -410,14 +415,15 @@ def filter_heads(iset, groups, target_class, min_score, zero_score_empties=False
     return out
 
 
-def mark_members(iset, groups, min_len):
-    """int32 [n] flag: 1 for the members of lists longer than min_len (the `len(processed_masks) > 2` gate of
-    process_masks_parallel, src/functions/inference.py:1443)."""
+def mark_members(iset, groups, min_len, value=1, into=None):
+    """int32 [n] flag: `value` for the members of lists longer than min_len (the `len(processed_masks) > 2` gate of
+    process_masks_parallel, src/functions/inference.py:1443), 0 elsewhere; `into`: add to an existing flag array."""
     lib = _lib.load()
-    flag = torch.empty(max(iset.n, 1), dtype=torch.int32, device=iset.device)
+    flag = into if into is not None else torch.empty(max(iset.n, 1), dtype=torch.int32, device=iset.device)
     _lib.check(lib.emia_group_mark_members(_ptr(groups.cap_off), groups.G, groups.total_cap, _ptr(groups.length), _ptr(groups.idx),
-                                           int(min_len), _ptr(flag), iset.n, _stream()), "emia_group_mark_members")
-    LAUNCHES["count"] += 2
+                                           int(min_len), int(value), 1 if into is not None else 0, _ptr(flag), iset.n, _stream()),
+               "emia_group_mark_members")
+    LAUNCHES["count"] += 2 if into is None else 1
     return flag
 
 

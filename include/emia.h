@@ -208,7 +208,9 @@ int emia_containment_rules(const uint32_t* crops, const emia_inst_meta* meta, co
  * skimage.measure.label in postprocess_masks (src/utils/mask_utils.py:70-84), process_masks_parallel
  * (src/functions/inference.py:189-203) and postprocess_masks_universal (inference.py:1778-1806).
  * The work planes of an instance live in shared memory when its padded crop ((ch + 2) x (cw + 2) words) has at most 1024 words;
- * emia_morph_plan: global plane size of the LARGER instances only (0 for the others; caller scans -> pad_off); work = 3 * pad_off[n] words.
+ * emia_morph_plan: global plane size of the LARGER instances only (0 for the others; caller scans -> pad_off);
+ * work = emia_morph_scratch_words() + 3 * pad_off[n] words (the fixed part is one spare plane per resident warp for the rare
+ * instances that need the hole test / flood).
  * emia_morph: applies n_ops (<= 4) operators in order (1 = fill holes, 2 = erode, 3 = dilate) to every crop.
  * emia_overlap_first_come: list member k loses the pixels of members 0..k-1 (in list order), then is zeroed when it has
  *   more than one 8-connected component (mask_utils.py:77-82); members keep their place in the list (Q6).
@@ -216,6 +218,7 @@ int emia_containment_rules(const uint32_t* crops, const emia_inst_meta* meta, co
 #define EMIA_MORPH_FILL 1
 #define EMIA_MORPH_ERODE 2
 #define EMIA_MORPH_DILATE 3
+size_t emia_morph_scratch_words(void);
 int emia_morph_plan(const emia_inst_meta* meta, int64_t n, int64_t* pad_words, void* stream);
 /* meta_out / crop_off_out (NULL: the input geometry): geometry of the result.  A chain whose first structuring operator is a
  * dilation (closing, plain dilation) can grow a mask by one pixel — also a closing, next to the frame border, where the
@@ -223,7 +226,9 @@ int emia_morph_plan(const emia_inst_meta* meta, int64_t n, int64_t* pad_words, v
 int emia_morph_grow_plan(const emia_inst_meta* meta, int64_t n, int H, int W, emia_inst_meta* meta_out, int64_t* crop_words,
                          void* stream);
 /* apply_flag (optional): instances with apply_flag[i] == 0 pass through unchanged (process_masks_parallel only runs on lists of
- * more than two masks, inference.py:1443; see emia_group_mark_members).  bbox_out / area_out (optional): bbox / popcount of
+ * more than two masks, inference.py:1443; see emia_group_mark_members); n_ops in 5..8 gives a SECOND operator chain
+ * ops_host[4..n_ops) that is applied to the instances with apply_flag[i] == 2 (postprocess_masks_universal: erosion only for small
+ * classes, opening for the others, inference.py:1786-1796), ops_host[0..4) zero-padded being the chain of apply_flag 1.  bbox_out / area_out (optional): bbox / popcount of
  * the result (emia_overlap_first_come: of the list members only), which saves the emia_crop_stats pass. */
 int emia_morph(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off, int64_t n, int H, int W,
                const int32_t* ops_host, int32_t n_ops, const int64_t* pad_off, uint32_t* work,
@@ -310,7 +315,8 @@ int emia_image_gray_hist(const uint8_t* image, int H, int W, int channels, uint6
  * the head outputs of all units (tiles / images / scales / models) of a batch are processed by one launch per step.
  * emia_group_filter_heads : members with meta.valid (Boxes.nonempty()), class == target_class (< 0: any) and score >= min_score
  *   (inference.py:1411-1420, :1519-1523); zero_score_empties: a list still holding a score == 0 becomes empty (mask_utils.py:59).
- * emia_group_mark_members : flag[inst] = 1 for members of lists longer than min_len, 0 elsewhere (inference.py:1443 `len > 2`).
+ * emia_group_mark_members : flag[inst] = value for members of lists longer than min_len (inference.py:1443 `len > 2`); the other
+ *   entries are cleared first unless keep != 0 (several calls can build one selector array).
  * emia_group_flatten      : output list s = members of the groups grp_list[seg_start[s] .. seg_start[s+1]) concatenated
  *   (`full_image_masks + all_tile_masks` :2452; `all_masks.extend` :1563, :1958); its slots start at out_cap_off[s]; id_add[g]
  *   (optional, per input group) is added to the member ids of group g.
@@ -325,7 +331,7 @@ int emia_group_filter_heads(const int32_t* cap_off, int32_t G, const int32_t* in
                             const emia_inst_meta* meta, const int32_t* classes, const float* scores, int32_t target_class,
                             float min_score, int32_t zero_score_empties, int32_t* out_len, int32_t* out_idx, void* stream);
 int emia_group_mark_members(const int32_t* cap_off, int32_t G, int32_t total_cap, const int32_t* in_len, const int32_t* in_idx,
-                            int32_t min_len, int32_t* flag, int64_t n_inst, void* stream);
+                            int32_t min_len, int32_t value, int32_t keep, int32_t* flag, int64_t n_inst, void* stream);
 int emia_group_flatten(const int32_t* cap_off, int32_t G, const int32_t* in_len, const int32_t* in_idx, const int32_t* grp_list,
                        const int32_t* seg_start, int32_t S, const int32_t* id_add, const int32_t* out_cap_off, int32_t* out_len,
                        int32_t* out_idx, void* stream);
