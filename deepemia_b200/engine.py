@@ -1,7 +1,8 @@
 """Device-resident engine over libemia.so: instances stay bit-packed in HBM from the mask head to the CSV row.
 
-PyTorch is used only for device memory, streams and (in bench.py) torch.distributed; every computation on the path is
-a kernel of libemia.so called through the C ABI (include/emia.h) with raw tensor pointers.
+Every computation on the path is a kernel of libemia.so called through the C ABI (include/emia.h) with raw tensor pointers.
+PyTorch provides device memory (torch.empty / zeros), streams, events and CUDA graphs, memcpy-type plumbing (copy_, clone, cat of
+already-computed arrays, the identity index lists of a layout) and — in bench.py / distributed.py — torch.distributed.
 """
 import math
 from dataclasses import dataclass, field
@@ -22,11 +23,18 @@ LAUNCHES = {"count": 0}   # kernels launched through the ABI (bench.py reports i
 STAGE_TIMING = {"enabled": False, "events": []}   # (name, start, end) CUDA events when enabled (bench.py --breakdown)
 
 
+NVTX = {"enabled": bool(int(__import__("os").environ.get("EMIA_NVTX", "0")))}   # EMIA_NVTX=1: one NVTX range per stage (nsys / ncu --nvtx)
+
+
 class _stage:
+    """A named stage of the path: an NVTX range when EMIA_NVTX=1, CUDA events when STAGE_TIMING is enabled (bench.py --breakdown)."""
+
     def __init__(self, name):
         self.name = name
 
     def __enter__(self):
+        if NVTX["enabled"]:
+            torch.cuda.nvtx.range_push("emia:" + self.name)
         if STAGE_TIMING["enabled"]:
             self.a = torch.cuda.Event(enable_timing=True); self.b = torch.cuda.Event(enable_timing=True)
             self.a.record()
@@ -36,6 +44,8 @@ class _stage:
         if STAGE_TIMING["enabled"]:
             self.b.record()
             STAGE_TIMING["events"].append((self.name, self.a, self.b))
+        if NVTX["enabled"]:
+            torch.cuda.nvtx.range_pop()
         return False
 
 
