@@ -269,11 +269,14 @@ def main():
     if want_cpu:
         import bench_flows
         arm = CpuArm(protos)
-        legs = {f: arm.submit(bench_flows.oracle_leg, f) for f in flows}
+        legs = {f: arm.submit(bench_flows.oracle_leg, f) for f in flows if f != "scalebar"}
     if args.flows_only:
         import bench_flows
         out = {}
         for f in flows:
+            if f == "scalebar":
+                out[f] = bench_flows.run_scalebar_leg(dev, args.steps, args.warmup)
+                continue
             out[f] = bench_flows.run_workload(f, dev, args.steps, args.warmup, leg=legs[f].get() if f in legs else None)
         if arm is not None:
             arm.close()
@@ -650,6 +653,8 @@ def main():
         for f in flows:
             import bench_flows
             line[f] = bench_flows.run_workload(f, dev, args.steps, args.warmup, leg=legs[f].get() if f in legs else None)
+        if flows and not args.flows_only:
+            line["scalebar"] = bench_flows.run_scalebar_leg(dev, args.steps, args.warmup)
         print(json.dumps(line))
     if arm is not None:
         arm.close()

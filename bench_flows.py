@@ -441,3 +441,86 @@ def run_split_workload(name, steps, warmup):
                           "same_result_on_all_ranks": bool(same_on_all_ranks), "parity_vs_single_gpu_batched_flow": bool(ok)}))
     dist.barrier()
     dist.destroy_process_group()
+
+
+# ---- row f3: scale-bar line detection for a batch of frames (not a BASELINE config: reported beside them) ---------------------
+def _scalebar_cpu(strips, x0):
+    """The OpenCV calls of detect_scale_bar (src/utils/scalebar_ocr.py:140, :200, :207-214, :247-249) frame by frame."""
+    import cv2
+    res = []
+    for s in strips:
+        gray = cv2.cvtColor(np.ascontiguousarray(s[:, x0:]), cv2.COLOR_BGR2GRAY)
+        edges = cv2.Canny(gray, 50, 150, apertureSize=3)
+        lines = cv2.HoughLinesP(edges, 1, np.pi / 180, threshold=50, minLineLength=20, maxLineGap=10)
+        lines = np.zeros((0, 4), np.int32) if lines is None else lines[:, 0, :]
+        sums = []
+        for x1, y1, x2, y2 in lines:
+            m = np.zeros_like(gray)
+            cv2.line(m, (int(x1), int(y1)), (int(x2), int(y2)), 255, 2)
+            sums.append((int(gray[m > 0].sum()), int((m > 0).sum())))
+        res.append((lines, np.asarray(sums, np.int64).reshape(-1, 2)))
+    return res
+
+
+def run_scalebar_leg(dev, steps, warmup, B=1024, cpu_sample=128):
+    import cv2
+    import torch
+    from deepemia_b200 import engine, synthetic as syn
+    rh, W, x0, cap = 92, 1024, 512, 256
+    variants = [syn.scalebar_strips(900 + v, B, rh, W, x0) for v in range(2)]
+    d_in = [torch.as_tensor(v, device=dev) for v in variants]
+    roi = (x0, 0, W, rh)
+
+    def step(t):
+        gray, edges = engine.scalebar_edges(t, roi, 50, 150)
+        lines, n = engine.hough_lines_p(edges, max_lines=cap)
+        return lines, n, engine.line_means(gray, lines, n)
+    for i in range(max(warmup, 2)):
+        step(d_in[i % 2])
+    torch.cuda.synchronize()
+    l0 = engine.LAUNCHES["count"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        res = step(d_in[i % 2])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = (engine.LAUNCHES["count"] - l0) // steps
+    # end to end: strips in pinned host memory -> device -> lines, counts and grey sums back on the host
+    pin = [torch.as_tensor(v).pin_memory() for v in variants]
+    stage = torch.empty_like(d_in[0])
+    hres = None
+
+    def e2e(i):
+        stage.copy_(pin[i % 2], non_blocking=True)
+        lines, n, sums = step(stage)
+        out = (lines.cpu(), n.cpu(), sums.cpu())
+        return out
+    for i in range(2):
+        hres = e2e(i)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(steps):
+        hres = e2e(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1)
+    # CPU leg + parity on a sample of the variant the last e2e step used
+    v = (steps - 1) % 2
+    t0 = time.perf_counter()
+    cres = _scalebar_cpu(variants[v][:cpu_sample], x0)
+    secs = time.perf_counter() - t0
+    lines_h, n_h, sums_h = (a.numpy() for a in hres)
+    ok = all(int(n_h[b]) == len(cl) and np.array_equal(lines_h[b, :len(cl)], cl) and np.array_equal(sums_h[b, :len(cl)], cs)
+             for b, (cl, cs) in enumerate(cres))
+    return {"workload": f"scale-bar line detection (row f3): {B} frames per step, ROI {W - x0}x{rh} px of a 1024x768 frame's info strip: BGR2GRAY -> "
+                        "Canny(50,150) -> HoughLinesP(1, pi/180, 50, 20, 10) -> mean grey under every line (thickness-2 mask)",
+            "metric": "frames_per_sec", "unit": "frames/s", "value": B * steps / (ms * 1e-3), "ms_per_step": ms / steps,
+            "gpu_launches_per_step": int(launches), "mean_lines_per_frame": float(n_h.mean()),
+            "e2e": {"value": B * steps / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e / steps,
+                    "h2d_bytes_per_step": int(variants[0].nbytes), "d2h_bytes_per_step": int(sum(a.nbytes for a in (lines_h, n_h, sums_h)))},
+            "cpu_baseline": {"value": cpu_sample / secs, "unit": "frames/s", "cores": int(cv2.getNumThreads()), "kind": "port",
+                             "sample": f"{cpu_sample} of the {B} frames: the reference's own OpenCV calls (cv2 {cv2.__version__}) in one process, "
+                                       f"{secs:.2f} s"},
+            "parity_vs_gpu_on_sample": bool(ok)}

@@ -801,3 +801,4 @@ extern "C" int emia_paste_threshold_bitpack(const float* probs, const float* box
 #include "emia_morph_kernels.cuh"
 #include "emia_tile_kernels.cuh"
 #include "emia_flow_kernels.cuh"
+#include "emia_scalebar_kernels.cuh"

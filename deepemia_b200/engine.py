@@ -1189,6 +1189,76 @@ def color_sums(iset, image):
     return out[:iset.n]
 
 
+# ---- row f3: scale-bar line detection (src/utils/scalebar_ocr.py:140-249), batched -------------------------------------------
+def hough_tables(W, H, rho=1.0, theta=np.pi / 180):
+    """(trig float32 [2 * numangle], numangle, numrho) exactly as cv2.HoughLinesP builds them (float rho / theta parameters,
+    computeNumangle(0, pi, theta), (float)(cos((double)n * theta) / rho))."""
+    rho32, theta32 = np.float32(rho), np.float32(theta)
+    th = float(theta32)
+    numangle = int(math.floor(math.pi / th)) + 1
+    if numangle > 1 and abs(math.pi - (numangle - 1) * th) < th / 2:
+        numangle -= 1
+    irho = float(np.float32(1) / rho32)
+    numrho = int(np.rint(np.float32((W + H) * 2 + 1) / rho32))
+    trig = np.empty(2 * numangle, np.float32)
+    for a in range(numangle):
+        trig[2 * a] = np.float32(math.cos(a * th) * irho)
+        trig[2 * a + 1] = np.float32(math.sin(a * th) * irho)
+    return trig, numangle, numrho
+
+
+def scalebar_edges(images, roi, low=50, high=150):
+    """images: uint8 [B,H,W,3] (BGR) or [B,H,W] (host array or device tensor); roi = (x0, y0, x1, y1) inside the images.
+    Returns (gray, edges) uint8 device tensors [B, y1-y0, x1-x0]: cv2.cvtColor(BGR2GRAY) and cv2.Canny(gray, low, high)."""
+    lib = _lib.load()
+    dev = images.device if isinstance(images, torch.Tensor) and images.is_cuda else _need_cuda(None)
+    img = torch.as_tensor(np.ascontiguousarray(images) if isinstance(images, np.ndarray) else images, device=dev).contiguous()
+    assert img.dtype == torch.uint8 and img.dim() in (3, 4)
+    B, H, W = (int(v) for v in img.shape[:3])
+    ch = 1 if img.dim() == 3 else int(img.shape[3])
+    x0, y0, x1, y1 = (int(v) for v in roi)
+    rw, rh = x1 - x0, y1 - y0
+    gray = torch.empty((B, max(rh, 0), max(rw, 0)), dtype=torch.uint8, device=dev)
+    edges = torch.empty_like(gray)
+    _lib.check(lib.emia_scalebar_edges(_ptr(img), B, H, W, ch, x0, y0, rw, rh, int(math.floor(low)), int(math.floor(high)), _ptr(gray),
+                                       _ptr(edges), _stream()), "emia_scalebar_edges")
+    LAUNCHES["count"] += 3
+    return gray, edges
+
+
+def hough_lines_p(edges, rho=1.0, theta=np.pi / 180, threshold=50, min_line_length=20, max_line_gap=10, max_lines=1024):
+    """cv2.HoughLinesP on every image of edges [B,H,W] (uint8 device tensor): (lines int32 [B,max_lines,4], n_lines int32 [B]),
+    lines in OpenCV's output order."""
+    lib = _lib.load()
+    assert edges.is_cuda and edges.dtype == torch.uint8 and edges.dim() == 3 and edges.is_contiguous()
+    B, H, W = (int(v) for v in edges.shape)
+    dev = edges.device
+    trig, numangle, numrho = hough_tables(W, H, rho, theta)
+    trig_t = torch.as_tensor(trig, device=dev)
+    lines = torch.zeros((B, max_lines, 4), dtype=torch.int32, device=dev)
+    n_lines = torch.zeros(max(B, 1), dtype=torch.int32, device=dev)
+    nbytes = int(lib.emia_hough_workspace_bytes(B, H, W, numangle, numrho))
+    ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+    _lib.check(lib.emia_hough_lines_p(_ptr(edges), B, H, W, _ptr(trig_t), numangle, numrho, int(threshold), int(min_line_length),
+                                      int(max_line_gap), int(max_lines), _ptr(lines), _ptr(n_lines), _ptr(ws), nbytes, _stream()),
+               "emia_hough_lines_p")
+    LAUNCHES["count"] += 1
+    return lines, n_lines[:B]
+
+
+def line_means(gray, lines, n_lines):
+    """int64 [B,max_lines,2] = (sum of gray, pixel count) under cv2.line(mask, p1, p2, 255, 2) of every line; the reference's
+    cv2.mean(gray_roi, mask=line_mask)[0] is sum * (1.0 / count)."""
+    lib = _lib.load()
+    assert gray.is_cuda and gray.dtype == torch.uint8 and gray.dim() == 3 and gray.is_contiguous()
+    B, H, W = (int(v) for v in gray.shape)
+    out = torch.zeros((B, int(lines.shape[1]), 2), dtype=torch.int64, device=gray.device)
+    _lib.check(lib.emia_line_mean(_ptr(gray), B, H, W, _ptr(lines), _ptr(n_lines), int(lines.shape[1]), _ptr(out), _stream()),
+               "emia_line_mean")
+    LAUNCHES["count"] += 1
+    return out
+
+
 _rule_cache = {}
 
 

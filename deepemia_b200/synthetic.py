@@ -226,3 +226,24 @@ def ensemble_multiscale_heads(seed0, n_images, h, w, n_particles=100, scales=(0.
         res[s] = [(np.concatenate(r[0]), np.concatenate(r[1]), np.concatenate(r[2]).astype(np.float32), np.concatenate(r[3]),
                    np.asarray(r[4], np.int64)) for r in per_model]
     return res
+
+
+def scalebar_strips(seed, B, rh=92, W=1024, x0=512):
+    """B info strips [B, rh, W, 3] (BGR uint8) of SEM frames — the rows a scale-bar ROI covers (row f3 bench / tests): dark band with
+    detector noise, one to three white bars, a caption and a few stray annotation lines right of x0; micrograph texture left of it."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    out = np.empty((B, rh, W, 3), np.uint8)
+    for b in range(B):
+        g = np.clip(20 + rng.integers(-4, 5, (rh, W)), 0, 255).astype(np.uint8)
+        tex = cv2.resize(rng.integers(30, 200, (rh // 6 + 1, x0 // 6 + 1), dtype=np.uint8), (x0, rh), interpolation=cv2.INTER_CUBIC)
+        g[:, :x0] = tex
+        for _ in range(int(rng.integers(1, 4))):
+            bx, by = x0 + int(rng.integers(20, (W - x0) // 2)), int(rng.integers(12, rh - 30))
+            g[by:by + int(rng.integers(3, 6)), bx:bx + int(rng.integers(40, (W - x0) // 2 - 30))] = 255
+        cv2.putText(g, f"{int(rng.integers(1, 900))} nm", (x0 + int(rng.integers(30, 200)), rh - 12), cv2.FONT_HERSHEY_SIMPLEX, 0.5, 255, 1)
+        for _ in range(int(rng.integers(0, 4))):
+            cv2.line(g, (x0 + int(rng.integers(0, W - x0)), int(rng.integers(0, rh))), (x0 + int(rng.integers(0, W - x0)), int(rng.integers(0, rh))),
+                     int(rng.integers(120, 256)), int(rng.integers(1, 3)))
+        out[b] = g[:, :, None]
+    return out

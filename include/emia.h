@@ -349,6 +349,26 @@ int emia_capacity_guard(const int64_t* total, int64_t capacity, int32_t* abort_f
 int emia_capacity_guard_ranges(const int64_t* offsets, const int64_t* bounds, int32_t B, int64_t capacity, int32_t* abort_flag,
                                void* stream);
 
+/* ---- row f3: scale-bar line detection for a batch of micrographs (csrc/emia_scalebar_kernels.cuh, core/emia_scalebar.cuh) -------
+ * Replaces the OpenCV calls of detect_scale_bar (src/utils/scalebar_ocr.py:140 cv2.cvtColor(BGR2GRAY), :200 cv2.Canny(gray, 50, 150,
+ * apertureSize=3), :207-214 cv2.HoughLinesP(edges, 1, pi/180, threshold=50, minLineLength=20, maxLineGap=10), :247-249 cv2.line(mask,
+ * p1, p2, 255, 2) + cv2.mean(gray, mask)); results are bit-identical to OpenCV 4.x.  The OCR (EasyOCR) is not part of this library.
+ * emia_scalebar_edges : images [B][H][W][channels] bytes (3: BGR, 1: grey); region (rx, ry, rw, rh) inside every image;
+ *   gray [B][rh][rw] and edges [B][rh][rw] (0 / 255) are written.
+ * emia_hough_lines_p  : edges [B][H][W]; trig[2a] = (float)(cos(a * theta) / rho), trig[2a+1] = (float)(sin(a * theta) / rho) for
+ *   a < numangle; numrho = cvRound((2 (W + H) + 1) / rho); lines [B][max_lines][4] = (x1, y1, x2, y2) in OpenCV's output order;
+ *   n_lines[b] = lines found (those beyond max_lines are dropped).  workspace: emia_hough_workspace_bytes().
+ * emia_line_mean      : sum_count [B][max_lines][2] = {sum of gray, pixel count} under the thickness-2 line of every output line
+ *   (end points inside the region, as HoughLinesP's are); cv2.mean(...)[0] = sum * (1.0 / count). */
+int emia_scalebar_edges(const uint8_t* images, int32_t B, int32_t H, int32_t W, int32_t channels, int32_t rx, int32_t ry,
+                        int32_t rw, int32_t rh, int32_t low, int32_t high, uint8_t* gray, uint8_t* edges, void* stream);
+size_t emia_hough_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t numangle, int32_t numrho);
+int emia_hough_lines_p(const uint8_t* edges, int32_t B, int32_t H, int32_t W, const float* trig, int32_t numangle,
+                       int32_t numrho, int32_t threshold, int32_t min_line_length, int32_t max_line_gap, int32_t max_lines,
+                       int32_t* lines, int32_t* n_lines, void* workspace, size_t workspace_bytes, void* stream);
+int emia_line_mean(const uint8_t* gray, int32_t B, int32_t H, int32_t W, const int32_t* lines, const int32_t* n_lines,
+                   int32_t max_lines, int64_t* sum_count, void* stream);
+
 /* pairwise helpers (drop-in for iou / calculate_iou / calculate_containment on explicit pairs):
  * out[k] = {intersection, area_a, area_b} for pairs (pa[k], pb[k]). */
 int emia_pair_counts(const uint32_t* crops, const emia_inst_meta* meta, const int64_t* crop_off,

@@ -11,6 +11,7 @@
 #include "../../deepemia_b200/csrc/core/emia_measure.cuh"
 #include "../../deepemia_b200/csrc/core/emia_paste.cuh"
 #include "../../deepemia_b200/csrc/core/emia_moments.cuh"
+#include "../../deepemia_b200/csrc/core/emia_scalebar.cuh"
 
 static void pack_bits(const uint8_t* mask, int H, int W, std::vector<uint32_t>& bits, int& ww) {
     ww = (W + 31) / 32;
@@ -95,5 +96,91 @@ void sim_moments(const uint8_t* mask, int H, int W, double* out) {
     for (int y = 0; y < H; ++y)
         for (int c = 0; c < ww; ++c) emia_word_moments(bits[(size_t)y * ww + c], c * 32, y, acc);
     emia_complete_moments(acc, out);
+}
+// ---- row f3: scale-bar line detection (emia_scalebar.cuh) -------------------------------------------------------------
+void sim_bgr2gray(const uint8_t* bgr, int n, uint8_t* gray) {
+    for (int i = 0; i < n; ++i) gray[i] = emia_bgr2gray(bgr[3 * i], bgr[3 * i + 1], bgr[3 * i + 2]);
+}
+// cv2.Canny(gray, low, high): edges 0 / 255
+void sim_canny(const uint8_t* gray, int H, int W, int low, int high, uint8_t* edges) {
+    std::vector<uint8_t> map((size_t)H * W);
+    std::vector<int> stack;
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            int c = emia_canny_classify(gray, H, W, W, x, y, low, high);
+            map[(size_t)y * W + x] = (uint8_t)c;
+            if (c == 2) stack.push_back(y * W + x);
+        }
+    while (!stack.empty()) {
+        int p = stack.back(); stack.pop_back();
+        int y = p / W, x = p % W;
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                int xx = x + dx, yy = y + dy;
+                if (xx < 0 || yy < 0 || xx >= W || yy >= H) continue;
+                if (map[(size_t)yy * W + xx] == 0) { map[(size_t)yy * W + xx] = 2; stack.push_back(yy * W + xx); }
+            }
+    }
+    for (size_t i = 0; i < map.size(); ++i) edges[i] = map[i] == 2 ? 255 : 0;
+}
+// cv2.HoughLinesP(edges, rho=1/irho, theta, threshold, minLineLength, maxLineGap): serial orchestration of the core pieces
+// (the kernel runs the same pieces warp-cooperatively).  trig: 2*numangle floats.  returns the number of lines (x1,y1,x2,y2).
+int sim_hough_lines_p(const uint8_t* edges, int H, int W, const float* trig, int numangle, int numrho, int threshold, int line_len,
+                      int line_gap, int* lines, int max_lines) {
+    std::vector<int> accum((size_t)numangle * numrho, 0);
+    std::vector<uint8_t> mask((size_t)H * W);
+    std::vector<int> nz;
+    for (int i = 0; i < H * W; ++i) { mask[i] = edges[i] != 0; if (edges[i]) nz.push_back(i); }
+    uint64_t rng = (uint64_t)-1;
+    int nl = 0;
+    for (int count = (int)nz.size(); count > 0; --count) {
+        int idx = emia_cv_rng_uniform0(rng, count);
+        int p = nz[idx];
+        nz[idx] = nz[count - 1];
+        int i = p / W, j = p % W;
+        if (!mask[p]) continue;
+        int max_val = threshold - 1, max_n = 0;
+        for (int n = 0; n < numangle; ++n) {
+            int r = emia_hough_rho_bin(j, i, trig[2 * n], trig[2 * n + 1], numrho);
+            int val = ++accum[(size_t)n * numrho + r];
+            if (max_val < val) { max_val = val; max_n = n; }
+        }
+        if (max_val < threshold) continue;
+        EmiaHoughWalk w = emia_hough_walk_setup(j, i, trig[2 * max_n], trig[2 * max_n + 1]);
+        int end[2][2] = {{j, i}, {j, i}};
+        int steps[2] = {0, 0};
+        for (int k = 0; k < 2; ++k) {
+            int gap = 0;
+            for (int t = 0;; ++t) {
+                int j1, i1;
+                emia_hough_walk_at(w, k, t, j1, i1);
+                if (j1 < 0 || j1 >= W || i1 < 0 || i1 >= H) break;
+                if (mask[(size_t)i1 * W + j1]) { gap = 0; end[k][0] = j1; end[k][1] = i1; steps[k] = t; }
+                else if (++gap > line_gap) break;
+            }
+        }
+        int adx = end[1][0] - end[0][0], ady = end[1][1] - end[0][1];
+        bool good = (adx < 0 ? -adx : adx) >= line_len || (ady < 0 ? -ady : ady) >= line_len;
+        for (int k = 0; k < 2; ++k)
+            for (int t = 0; t <= steps[k]; ++t) {
+                int j1, i1;
+                emia_hough_walk_at(w, k, t, j1, i1);
+                if (mask[(size_t)i1 * W + j1]) {
+                    if (good)
+                        for (int n = 0; n < numangle; ++n)
+                            accum[(size_t)n * numrho + emia_hough_rho_bin(j1, i1, trig[2 * n], trig[2 * n + 1], numrho)]--;
+                    mask[(size_t)i1 * W + j1] = 0;
+                }
+            }
+        if (good) {
+            if (nl < max_lines) { lines[4 * nl] = end[0][0]; lines[4 * nl + 1] = end[0][1]; lines[4 * nl + 2] = end[1][0]; lines[4 * nl + 3] = end[1][1]; }
+            ++nl;
+        }
+    }
+    return nl;
+}
+// cv2.line(mask, p1, p2, 255, 2): mask (zeroed by the caller) gets 255 on the covered pixels
+void sim_thick_line(uint8_t* mask, int H, int W, int x1, int y1, int x2, int y2) {
+    emia_cv_thick_line2(W, H, x1, y1, x2, y2, [&](int x, int y) { mask[(size_t)y * W + x] = 255; });
 }
 }  // extern "C"

@@ -213,3 +213,56 @@ def test_wavelength_mirror_matches_reference_text():
     assert M.rgb_to_wavelength(0, 255, 0) == 620 - 170 / 270 * 60.0
     assert M.rgb_to_wavelength(0, 0, 255) == 620 - 170 / 270 * 120.0
     assert abs(M.rgb_to_wavelength(30, 200, 120) - (620 - 170 / 270 * (60 * ((120 / 255 - 30 / 255) / (200 / 255 - 30 / 255)) + 120) / 2)) < 1e-9
+
+
+# ---- row f3: scale-bar line detection core (core/emia_scalebar.cuh) vs OpenCV -------------------------------------------------
+def _sb_frame(rng, H, W):
+    img = cv2.GaussianBlur(rng.integers(0, 90, (H, W, 3)).astype(np.uint8), (5, 5), 0)
+    for _ in range(int(rng.integers(1, 5))):
+        x0, y0 = int(rng.integers(5, W - 60)), int(rng.integers(5, H - 10))
+        cv2.rectangle(img, (x0, y0), (x0 + int(rng.integers(20, min(200, W - x0 - 2))), y0 + int(rng.integers(1, 6))), (255, 255, 255), -1)
+    if rng.random() < 0.5:
+        cv2.putText(img, "500 nm", (int(rng.integers(0, W // 2)), int(rng.integers(15, H))), cv2.FONT_HERSHEY_SIMPLEX, 0.6, (255, 255, 255), 2)
+    if rng.random() < 0.5:
+        cv2.line(img, (int(rng.integers(0, W)), int(rng.integers(0, H))), (int(rng.integers(0, W)), int(rng.integers(0, H))), (220, 220, 220),
+                 int(rng.integers(1, 4)))
+    return img
+
+
+def test_scalebar_core_bit_exact_vs_opencv(L):
+    """BGR2GRAY, Canny, HoughLinesP (OpenCV's random visiting order included) and the thickness-2 line mask of the device core are
+    bit-identical to cv2 on synthetic strips, pure-noise images (dense edges: hundreds of lines) and non-default parameters."""
+    from deepemia_b200.engine import hough_tables
+    rng = np.random.default_rng(0)
+    n_lines = 0
+    for it in range(150):
+        H, W = int(rng.integers(20, 120)), int(rng.integers(80, 400))
+        img = _sb_frame(rng, H, W) if it % 3 else rng.integers(0, 256, (H, W, 3)).astype(np.uint8)
+        gray = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)
+        g2 = np.zeros_like(gray)
+        L.sim_bgr2gray(_p(np.ascontiguousarray(img)), H * W, _p(g2))
+        assert (g2 == gray).all()
+        lo, hi = (50, 150) if it % 2 else (int(rng.integers(10, 100)), int(rng.integers(100, 300)))
+        e = cv2.Canny(gray, lo, hi, apertureSize=3)
+        e2 = np.zeros_like(e)
+        L.sim_canny(_p(gray), H, W, lo, hi, _p(e2))
+        assert (e == e2).all(), it
+        if it % 2:
+            rho, theta, thr, ml, mg = 1.0, np.pi / 180, 50, 20, 10
+        else:
+            rho, theta = float(rng.choice([1.0, 2.0, 0.5])), float(rng.choice([np.pi / 180, np.pi / 90, np.pi / 360]))
+            thr, ml, mg = int(rng.integers(10, 60)), int(rng.integers(5, 40)), int(rng.integers(0, 15))
+        lines = cv2.HoughLinesP(e, rho, theta, threshold=thr, minLineLength=ml, maxLineGap=mg)
+        ref = np.zeros((0, 4), np.int32) if lines is None else lines[:, 0, :]
+        trig, numangle, numrho = hough_tables(W, H, rho, theta)
+        out = np.zeros((8192, 4), np.int32)
+        nl = L.sim_hough_lines_p(_p(e), H, W, _p(trig), numangle, numrho, thr, ml, mg, _p(out), len(out))
+        assert nl == len(ref) and (out[:nl] == ref).all(), (it, nl, len(ref))
+        n_lines += nl
+        for x1, y1, x2, y2 in list(ref[:8]) + [rng.integers(0, [W, H, W, H]) for _ in range(4)]:
+            m = np.zeros((H, W), np.uint8)
+            cv2.line(m, (int(x1), int(y1)), (int(x2), int(y2)), 255, 2)
+            m2 = np.zeros((H, W), np.uint8)
+            L.sim_thick_line(_p(m2), H, W, int(x1), int(y1), int(x2), int(y2))
+            assert (m == m2).all(), (it, x1, y1, x2, y2)
+    assert n_lines > 2000

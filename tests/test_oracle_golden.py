@@ -166,3 +166,61 @@ def test_oracle_flows_match_reference_golden():
                                                           small, conf, ts, ov, kw.get("iou_threshold", 0.7),
                                                           kw.get("edge_filter_enabled", True))
         _check_flow(gold, name, m, s)
+
+
+def _scalebar_golden():
+    import json
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import scalebar_cases
+    g = np.load(os.path.join(here, "golden", "scalebar_golden.npz"), allow_pickle=False)
+    return scalebar_cases, g, json.loads(str(g["config_json"]))
+
+
+def test_oracle_scalebar_matches_reference_golden():
+    """oracle.scalebar (cv2 calls + the reference's scalar logic) == the unmodified detect_scale_bar on every case."""
+    from oracle import scalebar as osb
+    cases, g, cfg = _scalebar_golden()
+    positives = 0
+    for name in cases.CASES:
+        image, ocr, kw = cases.build(name, cfg["scale_bar_rois"]["default"])
+        roi = kw.pop("roi_config", None) or cfg["scale_bar_rois"]["default"]
+        kw.pop("dataset_name", None)
+        psum, um = osb.detect_scale_bar(image, ocr, roi, thresholds=cfg["scalebar_thresholds"], **kw)
+        assert psum == str(g[name + "/psum"]), name
+        assert float(um) == float(g[name + "/um_pix"]), name
+        positives += psum != "0"
+    assert positives >= 10
+
+
+def test_scalebar_host_logic_matches_reference_golden():
+    """The host half of the mirror (filters, merge_collinear_segments, selection) fed with OpenCV's lines / line sums reproduces the
+    reference result of every golden case (the device half is checked against OpenCV in tests/test_gpu_scalebar.py)."""
+    from oracle import scalebar as osb
+    from deepemia_b200.utils import scalebar_ocr as sb
+    cases, g, cfg = _scalebar_golden()
+    th = cfg["scalebar_thresholds"]
+    sb.set_config_provider(lambda name: cfg)
+    try:
+        for name in cases.CASES:
+            image, ocr, kw = cases.build(name, cfg["scale_bar_rois"]["default"])
+            roi = kw.pop("roi_config", None) or sb.get_scalebar_roi_for_dataset(kw.get("dataset_name"))
+            it, pt, gap, mll, emf = sb._thresholds(kw.get("dataset_name"), kw.get("intensity_threshold", 200), kw.get("proximity_threshold", 50))
+            assert (gap, mll, emf) == (th["merge_gap"], th["min_line_length"], th["edge_margin_factor"])
+            d = {}
+            osb.detect_scale_bar(image, ocr, roi, thresholds=th, details=d)
+            psum, centre, _ = sb._first_number(ocr)
+            longest, length = None, 0
+            if centre is not None and d["lines"] is not None:
+                lines = d["lines"][:, 0, :]
+                sums = []
+                for x1, y1, x2, y2 in lines:
+                    m = np.zeros_like(d["gray"])
+                    cv2.line(m, (int(x1), int(y1)), (int(x2), int(y2)), 255, 2)
+                    sums.append((int(d["gray"][m > 0].sum()), int((m > 0).sum())))
+                longest, length, _ = sb.select_scale_line(lines, sums, centre, d["gray"].shape[1], d["gray"].shape[0], it, pt, gap, mll, emf)
+            got = (psum, float(psum) / length) if longest else ("0", 1)
+            assert got[0] == str(g[name + "/psum"]) and float(got[1]) == float(g[name + "/um_pix"]), name
+    finally:
+        sb.set_config_provider(None)
