@@ -92,7 +92,8 @@ EMIA_HD int emia_canny_classify(const uint8_t* g, int H, int W, int pitch, int x
 // ------------------------------------------------------------------------------------------------------------------
 EMIA_HD int emia_hough_rho_bin(int j, int i, float c, float s, int numrho) {
     float v = (float)j * c + (float)i * s;        // never contracted (-fmad=false / -ffp-contract=off)
-    return emia_cv_round_f(v) + (numrho - 1) / 2;
+    int r = emia_cv_round_f(v) + (numrho - 1) / 2;
+    return r < 0 ? 0 : (r >= numrho ? numrho - 1 : r);        // no effect with OpenCV's numrho; keeps a caller's bad table in bounds
 }
 
 struct EmiaHoughWalk {

@@ -86,16 +86,38 @@ extern "C" size_t emia_hough_workspace_bytes(int32_t B, int32_t H, int32_t W, in
     return per * (size_t)B + 256;
 }
 
+// Point state of one image.  FAST: the mask as a bit plane and the point list (up to HOUGH_NZ_SMEM entries) in shared memory — a
+// skipped point (already removed by an earlier line) then costs a few dozen cycles instead of two dependent L2 round trips;
+// otherwise (regions above HOUGH_FAST_PIXELS) bytes / ints in the global workspace.
+#define HOUGH_FAST_PIXELS (128 * 1024)
+#define HOUGH_NZ_SMEM 6144
+
+template <bool FAST>
+struct HoughMask {
+    uint32_t* bits;     // FAST
+    uint8_t* bytes;     // !FAST
+    __device__ __forceinline__ bool get(int t) const { return FAST ? ((bits[t >> 5] >> (t & 31)) & 1u) != 0 : bytes[t] != 0; }
+    __device__ __forceinline__ void clear(int t) const {
+        if (FAST) atomicAnd(&bits[t >> 5], ~(1u << (t & 31)));
+        else bytes[t] = 0;
+    }
+};
+
+template <bool FAST>
 __global__ void __launch_bounds__(32) k_hough_lines_p(const uint8_t* __restrict__ edges_all, int H, int W, const float* __restrict__ trig,
                                                       int numangle, int numrho, int threshold, int line_len, int line_gap, int max_lines,
                                                       int32_t* __restrict__ lines_all, int32_t* __restrict__ n_lines, uint8_t* ws) {
+    extern __shared__ uint32_t hsm[];
     const int lane = threadIdx.x, b = blockIdx.x;
     const int n = H * W;
     const size_t mask_bytes = ((size_t)n + 15) & ~(size_t)15;
     const size_t per = (size_t)numangle * numrho * 4 + (size_t)n * 4 + mask_bytes;
     int* accum = (int*)(ws + per * b);
     int* nz = accum + (size_t)numangle * numrho;
-    uint8_t* mask = (uint8_t*)(nz + n);
+    HoughMask<FAST> mask;
+    mask.bytes = (uint8_t*)(nz + n);
+    mask.bits = hsm;
+    const int mask_words = (n + 31) >> 5;
     const uint8_t* edges = edges_all + (size_t)b * n;
     int32_t* lines = lines_all + (size_t)b * max_lines * 4;
     for (size_t t = lane; t < (size_t)numangle * numrho; t += 32) accum[t] = 0;
@@ -104,12 +126,28 @@ __global__ void __launch_bounds__(32) k_hough_lines_p(const uint8_t* __restrict_
     for (int base = 0; base < n; base += 32) {
         int t = base + lane;
         bool on = t < n && edges[t] != 0;
-        if (t < n) mask[t] = on ? 1 : 0;
         unsigned bal = __ballot_sync(0xffffffffu, on);
+        if (FAST) { if (lane == 0) hsm[base >> 5] = bal; }
+        else if (t < n) mask.bytes[t] = on ? 1 : 0;
         if (on) nz[count + __popc(bal & ((1u << lane) - 1u))] = t;
         count += __popc(bal);
     }
     __syncwarp();
+    if (FAST && count <= HOUGH_NZ_SMEM) {
+        int* nzs = (int*)(hsm + mask_words);
+        for (int t = lane; t < count; t += 32) nzs[t] = nz[t];
+        nz = nzs;
+        __syncwarp();
+    }
+    // the angles of this lane (slot s: angle s * 32 + lane) for tables of up to 256 angles
+    float tc[8], ts[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+        int a = s * 32 + lane;
+        tc[s] = a < numangle ? trig[2 * a] : 0.f;
+        ts[s] = a < numangle ? trig[2 * a + 1] : 0.f;
+    }
+    const bool small_table = numangle <= 256;
     uint64_t rng = (uint64_t)-1;
     int nl = 0;
     for (; count > 0; --count) {
@@ -118,14 +156,26 @@ __global__ void __launch_bounds__(32) k_hough_lines_p(const uint8_t* __restrict_
         __syncwarp();
         if (lane == 0) nz[idx] = nz[count - 1];
         __syncwarp();
-        if (!mask[p]) continue;
+        if (!mask.get(p)) continue;
         const int i = p / W, j = p - i * W;
-        // votes: lane handles the angles lane, lane + 32, ...; best = first angle reaching the largest count
+        // votes: all read-modify-writes of a lane are issued before the first result is looked at; best = first angle reaching the
+        // largest count
         int best_val = threshold - 1, best_n = 0x7fffffff;
-        for (int a = lane; a < numangle; a += 32) {
-            int r = emia_hough_rho_bin(j, i, trig[2 * a], trig[2 * a + 1], numrho);
-            int val = atomicAdd(&accum[(size_t)a * numrho + r], 1) + 1;      // independent read-modify-writes in flight, not a load -> store chain
-            if (val > best_val) { best_val = val; best_n = a; }
+        if (small_table) {
+            int vals[8];
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                int a = s * 32 + lane;
+                vals[s] = a < numangle ? atomicAdd(&accum[(size_t)a * numrho + emia_hough_rho_bin(j, i, tc[s], ts[s], numrho)], 1) + 1 : -1;
+            }
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+                if (vals[s] > best_val) { best_val = vals[s]; best_n = s * 32 + lane; }
+        } else {
+            for (int a = lane; a < numangle; a += 32) {
+                int val = atomicAdd(&accum[(size_t)a * numrho + emia_hough_rho_bin(j, i, trig[2 * a], trig[2 * a + 1], numrho)], 1) + 1;
+                if (val > best_val) { best_val = val; best_n = a; }
+            }
         }
         for (int o = 16; o > 0; o >>= 1) {
             int ov = __shfl_xor_sync(0xffffffffu, best_val, o), on_ = __shfl_xor_sync(0xffffffffu, best_n, o);
@@ -141,7 +191,7 @@ __global__ void __launch_bounds__(32) k_hough_lines_p(const uint8_t* __restrict_
                 int j1, i1;
                 emia_hough_walk_at(w, k, base + lane, j1, i1);
                 bool inb = j1 >= 0 && j1 < W && i1 >= 0 && i1 < H;
-                bool on = inb && mask[(size_t)i1 * W + j1];
+                bool on = inb && mask.get(i1 * W + j1);
                 unsigned b_in = __ballot_sync(0xffffffffu, inb), b_on = __ballot_sync(0xffffffffu, on);
                 // serial semantics over the 32 probes (every lane computes the same thing from the ballots)
                 for (int q = 0; q < 32; ++q) {
@@ -161,8 +211,8 @@ __global__ void __launch_bounds__(32) k_hough_lines_p(const uint8_t* __restrict_
                 bool on = false;
                 if (t <= steps[k]) {
                     emia_hough_walk_at(w, k, t, j1, i1);
-                    on = mask[(size_t)i1 * W + j1] != 0;
-                    if (on) mask[(size_t)i1 * W + j1] = 0;
+                    on = mask.get(i1 * W + j1);
+                    if (on) mask.clear(i1 * W + j1);
                 }
                 unsigned b_on = __ballot_sync(0xffffffffu, on);
                 if (good) {
@@ -170,8 +220,16 @@ __global__ void __launch_bounds__(32) k_hough_lines_p(const uint8_t* __restrict_
                         int q = __ffs((int)b_on) - 1;
                         b_on &= b_on - 1;
                         int jq = __shfl_sync(0xffffffffu, j1, q), iq = __shfl_sync(0xffffffffu, i1, q);
-                        for (int a = lane; a < numangle; a += 32)
-                            atomicSub(&accum[(size_t)a * numrho + emia_hough_rho_bin(jq, iq, trig[2 * a], trig[2 * a + 1], numrho)], 1);
+                        if (small_table) {
+#pragma unroll
+                            for (int s = 0; s < 8; ++s) {
+                                int a = s * 32 + lane;
+                                if (a < numangle) atomicSub(&accum[(size_t)a * numrho + emia_hough_rho_bin(jq, iq, tc[s], ts[s], numrho)], 1);
+                            }
+                        } else {
+                            for (int a = lane; a < numangle; a += 32)
+                                atomicSub(&accum[(size_t)a * numrho + emia_hough_rho_bin(jq, iq, trig[2 * a], trig[2 * a + 1], numrho)], 1);
+                        }
                     }
                 }
             }
@@ -190,15 +248,21 @@ __global__ void __launch_bounds__(32) k_hough_lines_p(const uint8_t* __restrict_
 extern "C" int emia_hough_lines_p(const uint8_t* edges, int32_t B, int32_t H, int32_t W, const float* trig, int32_t numangle,
                                   int32_t numrho, int32_t threshold, int32_t min_line_length, int32_t max_line_gap, int32_t max_lines,
                                   int32_t* lines, int32_t* n_lines, void* workspace, size_t workspace_bytes, void* stream) {
-    if (B < 0 || H <= 0 || W <= 0 || numangle <= 0 || numrho < (W + H) * 2 + 1 || max_lines <= 0 || (int64_t)H * W > (int64_t)1 << 30)
-        return emia_fail(EMIA_ERR_BAD_ARG, "emia_hough_lines_p: %s", "bad argument (numrho must be at least 2 (W + H) + 1)");
+    if (B < 0 || H <= 0 || W <= 0 || numangle <= 0 || numrho <= 0 || max_lines <= 0 || (int64_t)H * W > (int64_t)1 << 30)
+        return emia_fail(EMIA_ERR_BAD_ARG, "emia_hough_lines_p: %s", "bad argument");
     if (B == 0) return EMIA_OK;
     if (!edges || !trig || !lines || !n_lines || !workspace) return emia_fail(EMIA_ERR_BAD_ARG, "emia_hough_lines_p: %s", "null pointer");
     if (workspace_bytes < emia_hough_workspace_bytes(B, H, W, numangle, numrho))
         return emia_fail(EMIA_ERR_WORKSPACE, "emia_hough_lines_p: %s", "workspace too small");
     uint8_t* ws = (uint8_t*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-    k_hough_lines_p<<<(unsigned)B, 32, 0, (cudaStream_t)stream>>>(edges, H, W, trig, numangle, numrho, threshold, min_line_length,
-                                                                  max_line_gap, max_lines, lines, n_lines, ws);
+    if ((int64_t)H * W <= HOUGH_FAST_PIXELS) {
+        size_t smem = ((size_t)(H * W + 31) / 32 + HOUGH_NZ_SMEM) * 4;
+        k_hough_lines_p<true><<<(unsigned)B, 32, smem, (cudaStream_t)stream>>>(edges, H, W, trig, numangle, numrho, threshold, min_line_length,
+                                                                               max_line_gap, max_lines, lines, n_lines, ws);
+    } else {
+        k_hough_lines_p<false><<<(unsigned)B, 32, 0, (cudaStream_t)stream>>>(edges, H, W, trig, numangle, numrho, threshold, min_line_length,
+                                                                             max_line_gap, max_lines, lines, n_lines, ws);
+    }
     return emia_check_launch("emia_hough_lines_p launch: %s");
 }
 
