@@ -660,12 +660,28 @@ def run_inference(dataset_name, output_dir, visualize=True, threshold=0.65, draw
     rois = dataset_config.get("scale_bar_rois", {})
     roi_config = rois.get(dataset_name, rois.get("default", {"x_start_factor": 0.667, "y_start_factor": 0.866, "width_factor": 1.0,
                                                             "height_factor": 0.067}))
-    scale_bar = scale_bar_fn or ((lambda im: _PROVIDERS["scale_bar"](im, roi_config, dataset_name)) if _PROVIDERS["scale_bar"] else None)
+    user_fn = scale_bar_fn or ((lambda im: _PROVIDERS["scale_bar"](im, roi_config, dataset_name)) if _PROVIDERS["scale_bar"] else None)
     os.makedirs(output_dir, exist_ok=True)
+    from ..utils import scalebar_ocr as _sb
+    if cfg_fn and _sb._state["config"] is None:
+        _sb.set_config_provider(cfg_fn)
+    own_detector = user_fn is None and (_sb._state["ocr"] is not None or _sb.easyocr_available())
+
+    def scale_bar(im, name):
+        if user_fn is not None:
+            return user_fn(im)
+        if not own_detector:
+            return "0", 1.0
+        # the reference's own call (inference.py:751-762): on a copy; with draw_scalebar the debug overlay is saved next to the results
+        work = im.copy()
+        r = _sb.detect_scale_bar(work, roi_config=roi_config, dataset_name=dataset_name, draw_debug=bool(draw_scalebar))
+        if draw_scalebar:
+            cv2.imwrite(os.path.join(output_dir, f"{name}_scalebar_debug.png"), work)
+        return r
     img_ids, encoded, meas_rows = [], [], []
     for name, image in images:
         try:
-            psum, um_pix = scale_bar(image) if scale_bar is not None else ("0", 1.0)
+            psum, um_pix = scale_bar(image, name)
         except Exception:
             psum, um_pix = "0", 1.0                                     # inference.py:767-773
         d = _infer_image_dev(predictors, image, num_classes, small_classes, dataset_name=dataset_name, **kw)

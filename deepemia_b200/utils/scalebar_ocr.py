@@ -43,6 +43,11 @@ def set_ocr_reader(fn):
     _state["ocr"] = fn
 
 
+def easyocr_available():
+    import importlib.util
+    return importlib.util.find_spec("easyocr") is not None
+
+
 def _config(dataset_name):
     return (_state["config"](dataset_name) or {}) if _state["config"] else {}
 
