@@ -528,9 +528,43 @@ def main():
     same16 = len(ref_valid) == len(got_valid) and all(np.array_equal(a, b) for a, b in zip(ref_valid, got_valid))
     ms_e2e16, n_e2e16 = ms_e2e32, n_e2e32            # (slot names of the reduction below: the second leg is the fp32 one)
     res_h = res_h16
+    # the floor of the end-to-end step: the SAME bytes moved (H2D of the fp16 head outputs on one stream, D2H of the results on
+    # another) with no kernel in between — (i) by all ranks at once, as in the e2e leg, (ii) by one rank at a time.  On an HGX
+    # board two GPUs share one PCIe switch uplink: (i) / (ii) shows how much of the multi-GPU e2e time is the host link.
+    d2h_bytes = int(sum(v.numel() * v.element_size() for r in res_h for v in r["host"].values()))
+    cp_dev = {k: torch.empty_like(hosts[0][k], device=dev) for k in ("probs16", "boxes", "scores", "classes")}
+    cp_out_d = torch.empty(max(d2h_bytes, 1), dtype=torch.uint8, device=dev)
+    cp_out_h = torch.empty(max(d2h_bytes, 1), dtype=torch.uint8).pin_memory()
+    s_up, s_down = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def copy_only(steps):
+        torch.cuda.synchronize()
+        ev[2].record()
+        for i in range(steps):
+            hd = hosts[i % E]
+            s_up.wait_stream(torch.cuda.current_stream()); s_down.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s_up):
+                for k, t in cp_dev.items():
+                    t[:hd[k].shape[0]].copy_(hd[k][:t.shape[0]], non_blocking=True)
+            with torch.cuda.stream(s_down):
+                cp_out_h.copy_(cp_out_d, non_blocking=True)
+            torch.cuda.current_stream().wait_stream(s_up); torch.cuda.current_stream().wait_stream(s_down)
+        ev[3].record()
+        torch.cuda.synchronize()
+        return ev[2].elapsed_time(ev[3]) / steps
+    copy_only(2)
+    barrier()
+    ms_copy_all = copy_only(args.steps)
+    barrier()
+    ms_copy_solo = 0.0
+    for r in range(world):
+        if r == rank:
+            ms_copy_solo = copy_only(args.steps)
+        barrier()
     if sampler is not None:
         sampler.terminate()
-    t = torch.tensor([ms_total, ms_e2e, float(np.sum(k1_ms)), ms_e2e16, ms_crops, k1c_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, ms_e2e, float(np.sum(k1_ms)), ms_e2e16, ms_crops, k1c_ms, ms_copy_all, ms_copy_solo], dtype=torch.float64,
+                     device=dev)
     cnt = torch.tensor([float(n_done), float(n_e2e), float(n_e2e16), float(n_c)], dtype=torch.float64, device=dev)
     per_rank = [t.clone() for _ in range(world)]
     if world > 1:
@@ -538,7 +572,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     per_rank_ms = [round(float(x[0].item()) / args.steps, 3) for x in per_rank]
-    ms_total, ms_e2e, k1_sum, ms_e2e16, ms_crops, k1c_ms = t.tolist()
+    ms_total, ms_e2e, k1_sum, ms_e2e16, ms_crops, k1c_ms, ms_copy_all, ms_copy_solo = t.tolist()
     n_global, n_e2e_g, n_e2e16_g, n_c_g = cnt.tolist()
     if rank == 0:
         ms_step = ms_total / args.steps
@@ -589,7 +623,11 @@ def main():
             "clocks": _clock_summary(clk_path, local),
             "e2e": {"value": e2e_val, "unit": "instances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps, "rank0_wall_ms_per_step": e2e_wall, "host_shards_rotated": E,
-                    "head_probabilities": "fp16"},
+                    "head_probabilities": "fp16",
+                    "copies_only_ms_per_step": {"all_ranks_at_once": ms_copy_all, "one_rank_at_a_time": ms_copy_solo,
+                                                "note": "the same H2D + D2H bytes from / to the same pinned buffers with no kernel in between "
+                                                        "(max over ranks): the floor the host link sets for this step; when the first exceeds the second "
+                                                        "the ranks are sharing PCIe uplinks / host memory bandwidth"}},
             "e2e_fp32_heads": {"value": n_e2e16_g / (ms_e2e16 * 1e-3), "unit": "instances/s", "h2d_bytes_per_step": h2d32,
                                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e16 / args.steps, "identical_results_to_fp16": bool(same16),
                                "note": "the same step with the 28x28 probabilities transported as fp32 (a predictor run without AMP)"},
