@@ -19,6 +19,7 @@ REC_FIELDS = 16
  REC_SPHER, REC_AREA, REC_PERIM, REC_NVERT, REC_MEASURED) = range(16)
 
 FUSED_K4 = True
+MEASURE_ORDER = bool(int(__import__("os").environ.get("EMIA_MEASURE_ORDER", "1")))   # length-sorted work order of K5b/c (0: list order)
 LAUNCHES = {"count": 0}   # kernels launched through the ABI (bench.py reports it as gpu_launches)
 STAGE_TIMING = {"enabled": False, "events": []}   # (name, start, end) CUDA events when enabled (bench.py --breakdown)
 
@@ -598,11 +599,20 @@ def measure_list(iset, groups, um_pix=1.0, min_area=None, capacity=None, abort=N
     rec_inst = torch.empty(max(n_rec, 1), dtype=torch.int32, device=dev)
     scratch = torch.empty(max(n_scr, 16), dtype=torch.uint8, device=dev)
     if L:
+        order = None
+        if MEASURE_ORDER and L >= 1024:
+            # work order: slots sorted by vertex count (a warp of the morphometry kernel is as slow as its longest contour)
+            order = torch.empty(L, dtype=torch.int32, device=dev)
+            bins = torch.empty(128, dtype=torch.int32, device=dev)
+            with _stage("k5_order"):
+                _lib.check(lib.emia_list_measure_order(L, _ptr(item_inst), _ptr(offs[0]), _ptr(iset.cont_off), _ptr(iset.cstart),
+                                                       iset.cstart_stride, _ptr(order), _ptr(bins), st), "emia_list_measure_order")
+            LAUNCHES["count"] += 2
         with _stage("k5_measure"):
             _lib.check(lib.emia_contour_measure_list(L, _ptr(item_inst), _ptr(offs[0]), _ptr(offs[1]), _ptr(iset.cont_off),
                                                      _ptr(iset.pt_off), _ptr(iset.cstart), iset.cstart_stride, float(um_pix),
                                                      float(min_area), _ptr(iset.pts), _ptr(records), _ptr(rec_inst), _ptr(scratch),
-                                                     _ptr(abort) if capacity is not None else 0, st),
+                                                     _ptr(abort) if capacity is not None else 0, _ptr(order) if order is not None else 0, st),
                        "emia_contour_measure_list")
         LAUNCHES["count"] += 2
     if capacity is not None:

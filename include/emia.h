@@ -152,14 +152,20 @@ int emia_contour_measure_stored(const emia_inst_meta* meta, int64_t n, const int
  * emia_list_measure_plan: per list slot s (total_cap slots): item_inst[s] = instance id (-1 for a dead slot),
  *   rec_cnt[s] / scr_cnt[s] = number of records / scratch bytes (caller scans both, total_cap + 1 entries).
  * emia_contour_measure_list: records of slot s at rec_off[s] + j (OpenCV contour order), rec_inst = instance id per record.
- *   inst_cont_off (per instance) is only needed for the packed cstart layout (cstart_stride == 0). */
+ *   inst_cont_off (per instance) is only needed for the packed cstart layout (cstart_stride == 0).  order (optional, n_items
+ *   entries from emia_list_measure_order; NULL = list order): the order in which the slots are WORKED ON — the results do not depend
+ *   on it.
+ * emia_list_measure_order: order[] = the slots sorted by vertex count, longest first, dead slots last (a warp is as slow as its
+ *   longest contour); bins = 128 int32 of workspace (cleared inside). */
 int emia_list_measure_plan(const int32_t* cap_off, int32_t G, int32_t total_cap, const int32_t* in_len,
                            const int32_t* in_idx, const int64_t* n_contours, const int64_t* scratch_bytes,
                            int32_t* item_inst, int64_t* rec_cnt, int64_t* scr_cnt, void* stream);
 int emia_contour_measure_list(int64_t n_items, const int32_t* item_inst, const int64_t* rec_off, const int64_t* scr_off,
                               const int64_t* inst_cont_off, const int64_t* pt_off, const int32_t* cstart,
                               int32_t cstart_stride, double um_pix, double min_area, const uint32_t* pts, double* records,
-                              int32_t* rec_inst, uint8_t* scratch, const int32_t* abort_flag, void* stream);
+                              int32_t* rec_inst, uint8_t* scratch, const int32_t* abort_flag, const int32_t* order, void* stream);
+int emia_list_measure_order(int64_t n_items, const int32_t* item_inst, const int64_t* rec_off, const int64_t* inst_cont_off,
+                            const int32_t* cstart, int32_t cstart_stride, int32_t* order, int32_t* bins, void* stream);
 
 /* ---- K4: mask-IoU de-duplication and spatial constraints ----------------------------------------------------
  * All operate on G groups at once; see "Instance layout".  total_cap = cap_off[G] (the host knows it).

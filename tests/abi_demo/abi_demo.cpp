@@ -101,7 +101,7 @@ int main(int argc, char** argv) {
     int32_t* rec_inst = dalloc<int32_t>(n_rec);
     uint8_t* scratch = dalloc<uint8_t>(n_scr + 16);
     const double min_area = 5.0 > H * W * 0.000005 * 0.05 ? 5.0 : H * W * 0.000005 * 0.05;
-    EK(emia_contour_measure_list(n, item_inst, rec_off, scr_off, nullptr, pt_cap, cstart, capc + 1, 0.5, min_area, pts, records, rec_inst, scratch, nullptr, st));
+    EK(emia_contour_measure_list(n, item_inst, rec_off, scr_off, nullptr, pt_cap, cstart, capc + 1, 0.5, min_area, pts, records, rec_inst, scratch, nullptr, nullptr, st));
     CK(cudaStreamSynchronize(st));
 
     std::vector<int32_t> klen(T), kidx(n), rinst(n_rec);
