@@ -144,7 +144,7 @@ static int emia_group_pipeline(int mode, const uint32_t* crops, const emia_inst_
     if (max_cap > 0 && max_cap <= EMIA_FUSED_MAX_CAP) {
         // every group fits one SM's shared memory: one CTA per group, no global workspace
         const size_t smem = emia_fused_smem_bytes(max_cap);
-        cudaFuncSetAttribute(k_group_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        emia_need_dyn_smem((const void*)k_group_fused, smem);
         k_group_fused<<<(unsigned)G, EMIA_FUSED_THREADS, smem, st>>>(crops, meta, crop_off, bbox, area, perim0, n_contours, scores, classes,
                                                                     cap_off, in_len, in_idx, mode, thr, max_aspect, rule_active, rule_max_iou,
                                                                     num_classes, max_cap, out_len, out_idx);
@@ -277,7 +277,7 @@ extern "C" int emia_containment_rules(const uint32_t* crops, const emia_inst_met
             cudaMemcpyAsync(rem_b, rem_a, (size_t)L * 4, cudaMemcpyDeviceToDevice, st);
             if (max_cap > 0 && max_cap <= EMIA_FUSED_MAX_CAP) {
                 const size_t smem = emia_fused_smem_bytes(max_cap);
-                cudaFuncSetAttribute(k_containment_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                emia_need_dyn_smem((const void*)k_containment_fused, smem);
                 k_containment_fused<<<(unsigned)G, EMIA_FUSED_THREADS, smem, st>>>(crops, meta, crop_off, bbox, area, classes, cap_off, in_len,
                                                                                   in_idx, child, parent, containment_threshold, max_cap, rem_a, rem_b);
             } else {

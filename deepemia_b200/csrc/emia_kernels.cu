@@ -28,6 +28,29 @@ static int emia_check_launch(const char* what) {
     if (e != cudaSuccess) return emia_fail(EMIA_ERR_LAUNCH, what, cudaGetErrorString(e));
     return EMIA_OK;
 }
+// Opt-in dynamic shared memory of a kernel: the limit is only ever RAISED.  A per-call cudaFuncSetAttribute(..., exactly what this
+// launch needs) lowers it again after a larger launch — harmless for plain launches and for graph replays (the node keeps its own
+// attributes), but a tool that re-launches captured kernel nodes one by one (ncu) then sees a launch above the function's current
+// limit ("LaunchFailed" on the first graph replay of a 2048-tile step whose second captured shard was smaller).
+#include <mutex>
+static void emia_need_dyn_smem(const void* fn, size_t bytes) {
+    static std::mutex mu;
+    static const void* fns[64];
+    static size_t cur[64];
+    static int devs[64];
+    static int nfn = 0;
+    if (bytes <= 48 * 1024) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> g(mu);
+    for (int i = 0; i < nfn; ++i)
+        if (fns[i] == fn && devs[i] == dev) {
+            if (bytes > cur[i]) { cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); cur[i] = bytes; }
+            return;
+        }
+    if (nfn < 64) { fns[nfn] = fn; cur[nfn] = bytes; devs[nfn] = dev; ++nfn; }
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
 static int emia_num_sms() {
     static int sms = 0;
     if (!sms) {
@@ -773,7 +796,7 @@ extern "C" int emia_paste_threshold_bitpack(const float* probs, const float* box
     if (variant == 1 && frames) {
         if (pitch_words * 4 > EMIA_BULK_BYTES) return emia_fail(EMIA_ERR_UNSUPPORTED, "emia_paste_threshold_bitpack: %s", "variant 1 needs a frame row <= 16 KB");
         const size_t smem = 2 * EMIA_BULK_BYTES + EMIA_MASK_SIDE * EMIA_MASK_SIDE * 4 + (size_t)max_cols * 12;
-        cudaFuncSetAttribute(k_paste_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        emia_need_dyn_smem((const void*)k_paste_bulk, smem);
         const int64_t per_sm = ctas_req ? ctas_req : 4;
         const unsigned grid = (unsigned)(n < (int64_t)sms * per_sm ? n : (int64_t)sms * per_sm);
         k_paste_bulk<<<grid, EMIA_PASTE_THREADS, smem, st>>>(probs, (const float4*)boxes, meta, crop_off, n, scale_x, scale_y, H, W,
@@ -784,11 +807,11 @@ extern "C" int emia_paste_threshold_bitpack(const float* probs, const float* box
     const int64_t per_sm = ctas_req ? ctas_req : 8;
     const unsigned grid = (unsigned)(n < (int64_t)sms * per_sm ? n : (int64_t)sms * per_sm);
     if (frames) {
-        cudaFuncSetAttribute(k_paste<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        emia_need_dyn_smem((const void*)k_paste<true>, smem);
         k_paste<true><<<grid, EMIA_PASTE_THREADS, smem, st>>>(probs, (const float4*)boxes, meta, crop_off, n, scale_x, scale_y, H, W,
                                                               frames, frame_slots, pitch_words, crops, bbox, area, max_cols, abort_flag);
     } else {
-        cudaFuncSetAttribute(k_paste<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        emia_need_dyn_smem((const void*)k_paste<false>, smem);
         k_paste<false><<<grid, EMIA_PASTE_THREADS, smem, st>>>(probs, (const float4*)boxes, meta, crop_off, n, scale_x, scale_y, H, W,
                                                                nullptr, 1, pitch_words, crops, bbox, area, max_cols, abort_flag);
     }

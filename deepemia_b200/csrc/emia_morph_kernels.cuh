@@ -669,7 +669,7 @@ extern "C" int emia_column_gate(const uint32_t* crops, const emia_inst_meta* met
     if (!crops || !meta || !crop_off || !cap_off || !in_len || !in_idx || !out_len || !out_idx)
         return emia_fail(EMIA_ERR_BAD_ARG, "emia_column_gate: %s", "null pointer");
     const size_t smem = (size_t)W * 4;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k_column_gate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    emia_need_dyn_smem((const void*)k_column_gate, smem);
     k_column_gate<<<(unsigned)G, 512, smem, (cudaStream_t)stream>>>(crops, meta, crop_off, cap_off, in_len, in_idx, W, min_size,
                                                                    out_len, out_idx);
     return emia_check_launch("emia_column_gate launch: %s");

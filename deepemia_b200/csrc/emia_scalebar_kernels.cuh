@@ -311,12 +311,7 @@ extern "C" int emia_line_mean(const uint8_t* gray, int32_t B, int32_t H, int32_t
     if (!gray || !lines || !n_lines || !sum_count) return emia_fail(EMIA_ERR_BAD_ARG, "emia_line_mean: %s", "null pointer");
     size_t smem = (((size_t)H * W + 31) / 32) * 4;
     if (smem > 200 * 1024) return emia_fail(EMIA_ERR_BAD_ARG, "emia_line_mean: %s", "region above 1.6 Mpixel (the bit plane lives in shared memory)");
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        if (cudaFuncSetAttribute(k_line_mean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)) != cudaSuccess)
-            return emia_fail(EMIA_ERR_LAUNCH, "emia_line_mean: %s", "cannot raise the shared-memory limit");
-        configured = 200 * 1024;
-    }
+    emia_need_dyn_smem((const void*)k_line_mean, smem);
     k_line_mean<<<dim3((unsigned)max_lines, (unsigned)B), 32, smem, (cudaStream_t)stream>>>(gray, H, W, lines, n_lines, max_lines, sum_count);
     return emia_check_launch("emia_line_mean launch: %s");
 }
