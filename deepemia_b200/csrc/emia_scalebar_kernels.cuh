@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(32) k_hough_lines_p(const uint8_t* __restrict_
     const int mask_words = (n + 31) >> 5;
     const uint8_t* edges = edges_all + (size_t)b * n;
     int32_t* lines = lines_all + (size_t)b * max_lines * 4;
-    for (size_t t = lane; t < (size_t)numangle * numrho; t += 32) accum[t] = 0;
+    for (size_t t = lane; t < (size_t)numangle * numrho; t += 32) __stcg(&accum[t], 0);
     // stage 1: the non-zero points in row-major order
     int count = 0;
     for (int base = 0; base < n; base += 32) {
@@ -150,38 +150,66 @@ __global__ void __launch_bounds__(32) k_hough_lines_p(const uint8_t* __restrict_
     const bool small_table = numangle <= 256;
     uint64_t rng = (uint64_t)-1;
     int nl = 0;
-    for (; count > 0; --count) {
-        int idx = emia_cv_rng_uniform0(rng, count);
-        int p = nz[idx];
-        __syncwarp();
-        if (lane == 0) nz[idx] = nz[count - 1];
-        __syncwarp();
-        if (!mask.get(p)) continue;
-        const int i = p / W, j = p - i * W;
-        // votes: all read-modify-writes of a lane are issued before the first result is looked at; best = first angle reaching the
-        // largest count
-        int best_val = threshold - 1, best_n = 0x7fffffff;
+    // rho bin of angle slot s (tables of up to 256 angles) / of angle a
+    auto cell = [&](int s, int j, int i) -> int* {
+        return &accum[(size_t)(s * 32 + lane) * numrho + emia_hough_rho_bin(j, i, tc[s], ts[s], numrho)];
+    };
+    // (largest count, first angle reaching it) over the warp
+    auto reduce_best = [&](int& best_val, int& best_n) {
+        for (int o = 16; o > 0; o >>= 1) {
+            int ov = __shfl_xor_sync(0xffffffffu, best_val, o), on_ = __shfl_xor_sync(0xffffffffu, best_n, o);
+            if (ov > best_val || (ov == best_val && on_ < best_n)) { best_val = ov; best_n = on_; }
+        }
+    };
+    // votes of ONE point.  A cell (angle a, rho bin) is only ever touched by lane a % 32 of this warp, so no atomic is needed: the
+    // lane loads its (up to 8) cells back to back, adds and stores.  (Atomics WITH a returned value were the first version: 75 % of
+    // the kernel's stall samples sat on them — about one returned atomic per 35 cycles per warp however many were in flight, while
+    // the fire-and-forget reductions of the un-voting cost 30x less per operation.)  ld / st .cg: the cells live in L2.
+    auto vote_point = [&](int j, int i, int& best_val, int& best_n) {
+        best_val = threshold - 1; best_n = 0x7fffffff;
         if (small_table) {
+            int* c[8];
             int vals[8];
 #pragma unroll
-            for (int s = 0; s < 8; ++s) {
-                int a = s * 32 + lane;
-                vals[s] = a < numangle ? atomicAdd(&accum[(size_t)a * numrho + emia_hough_rho_bin(j, i, tc[s], ts[s], numrho)], 1) + 1 : -1;
-            }
+            for (int s = 0; s < 8; ++s) c[s] = cell(s, j, i);
+#pragma unroll
+            for (int s = 0; s < 8; ++s) vals[s] = (s * 32 + lane) < numangle ? __ldcg(c[s]) + 1 : -1;
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+                if ((s * 32 + lane) < numangle) __stcg(c[s], vals[s]);
 #pragma unroll
             for (int s = 0; s < 8; ++s)
                 if (vals[s] > best_val) { best_val = vals[s]; best_n = s * 32 + lane; }
         } else {
             for (int a = lane; a < numangle; a += 32) {
-                int val = atomicAdd(&accum[(size_t)a * numrho + emia_hough_rho_bin(j, i, trig[2 * a], trig[2 * a + 1], numrho)], 1) + 1;
+                int* c = &accum[(size_t)a * numrho + emia_hough_rho_bin(j, i, trig[2 * a], trig[2 * a + 1], numrho)];
+                const int val = __ldcg(c) + 1;
+                __stcg(c, val);
                 if (val > best_val) { best_val = val; best_n = a; }
             }
         }
-        for (int o = 16; o > 0; o >>= 1) {
-            int ov = __shfl_xor_sync(0xffffffffu, best_val, o), on_ = __shfl_xor_sync(0xffffffffu, best_n, o);
-            if (ov > best_val || (ov == best_val && on_ < best_n)) { best_val = ov; best_n = on_; }
+        reduce_best(best_val, best_n);
+    };
+    auto unvote_point = [&](int j, int i) {
+        if (small_table) {
+            int* c[8];
+            int vals[8];
+#pragma unroll
+            for (int s = 0; s < 8; ++s) c[s] = cell(s, j, i);
+#pragma unroll
+            for (int s = 0; s < 8; ++s) vals[s] = (s * 32 + lane) < numangle ? __ldcg(c[s]) - 1 : 0;
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+                if ((s * 32 + lane) < numangle) __stcg(c[s], vals[s]);
+        } else {
+            for (int a = lane; a < numangle; a += 32) {
+                int* c = &accum[(size_t)a * numrho + emia_hough_rho_bin(j, i, trig[2 * a], trig[2 * a + 1], numrho)];
+                __stcg(c, __ldcg(c) - 1);
+            }
         }
-        if (best_val < threshold) continue;
+    };
+    // the most voted line through (j, i): walk both ways, then remove its points (and, for an accepted line, their votes)
+    auto take_line = [&](int j, int i, int best_n) {
         EmiaHoughWalk w = emia_hough_walk_setup(j, i, trig[2 * best_n], trig[2 * best_n + 1]);
         int end_x[2], end_y[2], steps[2];
         for (int k = 0; k < 2; ++k) {
@@ -219,17 +247,7 @@ __global__ void __launch_bounds__(32) k_hough_lines_p(const uint8_t* __restrict_
                     while (b_on) {
                         int q = __ffs((int)b_on) - 1;
                         b_on &= b_on - 1;
-                        int jq = __shfl_sync(0xffffffffu, j1, q), iq = __shfl_sync(0xffffffffu, i1, q);
-                        if (small_table) {
-#pragma unroll
-                            for (int s = 0; s < 8; ++s) {
-                                int a = s * 32 + lane;
-                                if (a < numangle) atomicSub(&accum[(size_t)a * numrho + emia_hough_rho_bin(jq, iq, tc[s], ts[s], numrho)], 1);
-                            }
-                        } else {
-                            for (int a = lane; a < numangle; a += 32)
-                                atomicSub(&accum[(size_t)a * numrho + emia_hough_rho_bin(jq, iq, trig[2 * a], trig[2 * a + 1], numrho)], 1);
-                        }
+                        unvote_point(__shfl_sync(0xffffffffu, j1, q), __shfl_sync(0xffffffffu, i1, q));
                     }
                 }
             }
@@ -241,6 +259,26 @@ __global__ void __launch_bounds__(32) k_hough_lines_p(const uint8_t* __restrict_
             }
             ++nl;
         }
+    };
+    // next point of OpenCV's random visiting order (the order depends on nothing but the point count)
+    auto draw = [&]() -> int {
+        int idx = emia_cv_rng_uniform0(rng, count);
+        int p = nz[idx];
+        __syncwarp();
+        if (lane == 0) nz[idx] = nz[count - 1];
+        __syncwarp();
+        --count;
+        return p;
+    };
+    // (A window of several points voting at once — exact, because a point's counts do not depend on later points unless a line is
+    // accepted in between, which is rolled back — was built and measured: no gain, the votes were throughput- not latency-bound.)
+    while (count > 0) {
+        const int p = draw();
+        if (!mask.get(p)) continue;
+        const int i = p / W, j = p - i * W;
+        int bv, bn;
+        vote_point(j, i, bv, bn);
+        if (bv >= threshold) take_line(j, i, bn);
     }
     if (lane == 0) n_lines[b] = nl;
 }
@@ -257,6 +295,8 @@ extern "C" int emia_hough_lines_p(const uint8_t* edges, int32_t B, int32_t H, in
     uint8_t* ws = (uint8_t*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     if ((int64_t)H * W <= HOUGH_FAST_PIXELS) {
         size_t smem = ((size_t)(H * W + 31) / 32 + HOUGH_NZ_SMEM) * 4;
+        static const char* pad_env = getenv("EMIA_HOUGH_SMEM_PAD_KB");     // experiment knob: fewer frames in flight per SM
+        if (pad_env) { smem += (size_t)atoi(pad_env) * 1024; emia_need_dyn_smem((const void*)k_hough_lines_p<true>, smem); }
         k_hough_lines_p<true><<<(unsigned)B, 32, smem, (cudaStream_t)stream>>>(edges, H, W, trig, numangle, numrho, threshold, min_line_length,
                                                                                max_line_gap, max_lines, lines, n_lines, ws);
     } else {
