@@ -103,16 +103,18 @@ struct HoughMask {
     }
 };
 
+#define HOUGH_THREADS 128
 template <bool FAST>
-__global__ void __launch_bounds__(32) k_hough_lines_p(const uint8_t* __restrict__ edges_all, int H, int W, const float* __restrict__ trig,
-                                                      int numangle, int numrho, int threshold, int line_len, int line_gap, int max_lines,
-                                                      int32_t* __restrict__ lines_all, int32_t* __restrict__ n_lines, uint8_t* ws) {
+__global__ void __launch_bounds__(HOUGH_THREADS) k_hough_lines_p(const uint8_t* __restrict__ edges_all, int H, int W, const float* __restrict__ trig,
+                                                                 int numangle, int numrho, int threshold, int line_len, int line_gap, int max_lines,
+                                                                 int32_t* __restrict__ lines_all, int32_t* __restrict__ n_lines, uint8_t* ws) {
     extern __shared__ uint32_t hsm[];
-    const int lane = threadIdx.x, b = blockIdx.x;
+    __shared__ int s_cnt[HOUGH_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = blockIdx.x;
     const int n = H * W;
     const size_t mask_bytes = ((size_t)n + 15) & ~(size_t)15;
     const size_t per = (size_t)numangle * numrho * 4 + (size_t)n * 4 + mask_bytes;
-    int* accum = (int*)(ws + per * b);
+    int* accum = (int*)(ws + per * b);          // cleared by the caller-side memset of emia_hough_lines_p
     int* nz = accum + (size_t)numangle * numrho;
     HoughMask<FAST> mask;
     mask.bytes = (uint8_t*)(nz + n);
@@ -120,25 +122,48 @@ __global__ void __launch_bounds__(32) k_hough_lines_p(const uint8_t* __restrict_
     const int mask_words = (n + 31) >> 5;
     const uint8_t* edges = edges_all + (size_t)b * n;
     int32_t* lines = lines_all + (size_t)b * max_lines * 4;
-    for (size_t t = lane; t < (size_t)numangle * numrho; t += 32) __stcg(&accum[t], 0);
-    // stage 1: the non-zero points in row-major order
-    int count = 0;
-    for (int base = 0; base < n; base += 32) {
+    // stage 1: the non-zero points in row-major order.  Each of the four warps compacts a contiguous quarter of the pixels into
+    // the start of that quarter's own range of the list; the pieces are then moved together (into shared memory when they fit).
+    const int chunk = ((mask_words + HOUGH_THREADS / 32 - 1) / (HOUGH_THREADS / 32)) * 32;      // pixels per warp, a multiple of 32
+    const int c0 = min(n, warp * chunk), c1 = min(n, c0 + chunk);
+    int my_count = 0;
+    for (int base = c0; base < c1; base += 32) {
         int t = base + lane;
-        bool on = t < n && edges[t] != 0;
+        bool on = t < c1 && edges[t] != 0;
         unsigned bal = __ballot_sync(0xffffffffu, on);
         if (FAST) { if (lane == 0) hsm[base >> 5] = bal; }
-        else if (t < n) mask.bytes[t] = on ? 1 : 0;
-        if (on) nz[count + __popc(bal & ((1u << lane) - 1u))] = t;
-        count += __popc(bal);
+        else if (t < c1) mask.bytes[t] = on ? 1 : 0;
+        if (on) nz[c0 + my_count + __popc(bal & ((1u << lane) - 1u))] = t;
+        my_count += __popc(bal);
     }
-    __syncwarp();
+    if (lane == 0) s_cnt[warp] = my_count;
+    __syncthreads();
+    int count = 0, my_off = 0;
+    for (int w = 0; w < HOUGH_THREADS / 32; ++w) { if (w == warp) my_off = count; count += s_cnt[w]; }
     if (FAST && count <= HOUGH_NZ_SMEM) {
         int* nzs = (int*)(hsm + mask_words);
-        for (int t = lane; t < count; t += 32) nzs[t] = nz[t];
+        for (int t = lane; t < my_count; t += 32) nzs[my_off + t] = nz[c0 + t];
         nz = nzs;
-        __syncwarp();
+        __syncthreads();
+        if (warp != 0) return;
+    } else {
+        // (dense frames) close the gaps in place, piece after piece
+        __syncthreads();
+        if (warp != 0) return;
+        int dst = s_cnt[0];
+        for (int w = 1; w < HOUGH_THREADS / 32; ++w) {
+            const int src = min(n, w * chunk), cnt = s_cnt[w];
+            for (int t0 = 0; t0 < cnt; t0 += 32) {
+                const int t = t0 + lane;
+                const int v = t < cnt ? nz[src + t] : 0;
+                __syncwarp();
+                if (t < cnt) nz[dst + t] = v;
+                __syncwarp();
+            }
+            dst += cnt;
+        }
     }
+    __syncwarp();
     // the angles of this lane (slot s: angle s * 32 + lane) for tables of up to 256 angles
     float tc[8], ts[8];
 #pragma unroll
@@ -190,22 +215,16 @@ __global__ void __launch_bounds__(32) k_hough_lines_p(const uint8_t* __restrict_
         }
         reduce_best(best_val, best_n);
     };
+    // un-voting: fire-and-forget reductions (nothing waits for them; a later load of the same cell by the same lane is ordered
+    // behind them) — a line of 70 points is 70 x 180 decrements, which as load / store pairs were one L2 round trip per point
     auto unvote_point = [&](int j, int i) {
         if (small_table) {
-            int* c[8];
-            int vals[8];
-#pragma unroll
-            for (int s = 0; s < 8; ++s) c[s] = cell(s, j, i);
-#pragma unroll
-            for (int s = 0; s < 8; ++s) vals[s] = (s * 32 + lane) < numangle ? __ldcg(c[s]) - 1 : 0;
 #pragma unroll
             for (int s = 0; s < 8; ++s)
-                if ((s * 32 + lane) < numangle) __stcg(c[s], vals[s]);
+                if ((s * 32 + lane) < numangle) atomicSub(cell(s, j, i), 1);
         } else {
-            for (int a = lane; a < numangle; a += 32) {
-                int* c = &accum[(size_t)a * numrho + emia_hough_rho_bin(j, i, trig[2 * a], trig[2 * a + 1], numrho)];
-                __stcg(c, __ldcg(c) - 1);
-            }
+            for (int a = lane; a < numangle; a += 32)
+                atomicSub(&accum[(size_t)a * numrho + emia_hough_rho_bin(j, i, trig[2 * a], trig[2 * a + 1], numrho)], 1);
         }
     };
     // the most voted line through (j, i): walk both ways, then remove its points (and, for an accepted line, their votes)
@@ -270,15 +289,81 @@ __global__ void __launch_bounds__(32) k_hough_lines_p(const uint8_t* __restrict_
         --count;
         return p;
     };
-    // (A window of several points voting at once — exact, because a point's counts do not depend on later points unless a line is
-    // accepted in between, which is rolled back — was built and measured: no gain, the votes were throughput- not latency-bound.)
-    while (count > 0) {
-        const int p = draw();
-        if (!mask.get(p)) continue;
-        const int i = p / W, j = p - i * W;
-        int bv, bn;
-        vote_point(j, i, bv, bn);
-        if (bv >= threshold) take_line(j, i, bn);
+    if (small_table) {
+        // A WINDOW of KW points votes at once: their cells are loaded back to back (one L2 round trip for the window instead of one
+        // per point).  This is exact: the counts a point sees do not depend on LATER points, and an earlier point of the window
+        // that hits the same cell is forwarded in registers (a cell belongs to one lane); only an accepted line makes the order
+        // matter — then the speculative votes of the later points are taken back, the line is removed and the rest of the window is
+        // redone one by one, as OpenCV does.
+        constexpr int KW = 4;
+        while (count > 0) {
+            int wj[KW], wi[KW], nw = 0;
+#pragma unroll
+            for (int k = 0; k < KW; ++k) { wj[k] = 0; wi[k] = 0; }
+            while (nw < KW && count > 0) {
+                const int p = draw();
+                if (!mask.get(p)) continue;
+                const int i = p / W, j = p - i * W;
+#pragma unroll
+                for (int k = 0; k < KW; ++k)
+                    if (k == nw) { wj[k] = j; wi[k] = i; }
+                ++nw;
+            }
+            int idx[KW][8], vals[KW][8];
+#pragma unroll
+            for (int k = 0; k < KW; ++k)
+#pragma unroll
+                for (int s = 0; s < 8; ++s)
+                    idx[k][s] = (k < nw && (s * 32 + lane) < numangle)
+                                    ? (s * 32 + lane) * numrho + emia_hough_rho_bin(wj[k], wi[k], tc[s], ts[s], numrho) : -1;
+#pragma unroll
+            for (int k = 0; k < KW; ++k)
+#pragma unroll
+                for (int s = 0; s < 8; ++s) vals[k][s] = idx[k][s] >= 0 ? __ldcg(accum + idx[k][s]) : -2;
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+#pragma unroll
+                for (int k = 0; k < KW; ++k) {
+                    int v = vals[k][s];
+#pragma unroll
+                    for (int q = 0; q < KW; ++q)
+                        if (q < k && idx[q][s] == idx[k][s]) v = vals[q][s];        // the latest earlier vote on the same cell
+                    vals[k][s] = v + 1;
+                    if (idx[k][s] >= 0) __stcg(accum + idx[k][s], vals[k][s]);        // same address: program order, the last one stays
+                }
+            bool redo = false;
+#pragma unroll
+            for (int k = 0; k < KW; ++k) {
+                if (k >= nw) continue;
+                if (redo) {
+                    if (!mask.get(wi[k] * W + wj[k])) continue;
+                    int bv, bn;
+                    vote_point(wj[k], wi[k], bv, bn);
+                    if (bv >= threshold) take_line(wj[k], wi[k], bn);
+                    continue;
+                }
+                int bv = threshold - 1, bn = 0x7fffffff;
+#pragma unroll
+                for (int s = 0; s < 8; ++s)
+                    if (idx[k][s] >= 0 && vals[k][s] > bv) { bv = vals[k][s]; bn = s * 32 + lane; }
+                reduce_best(bv, bn);
+                if (bv < threshold) continue;
+#pragma unroll
+                for (int q = 0; q < KW; ++q)
+                    if (q > k && q < nw) unvote_point(wj[q], wi[q]);
+                take_line(wj[k], wi[k], bn);
+                redo = true;
+            }
+        }
+    } else {
+        while (count > 0) {
+            const int p = draw();
+            if (!mask.get(p)) continue;
+            const int i = p / W, j = p - i * W;
+            int bv, bn;
+            vote_point(j, i, bv, bn);
+            if (bv >= threshold) take_line(j, i, bn);
+        }
     }
     if (lane == 0) n_lines[b] = nl;
 }
@@ -293,15 +378,18 @@ extern "C" int emia_hough_lines_p(const uint8_t* edges, int32_t B, int32_t H, in
     if (workspace_bytes < emia_hough_workspace_bytes(B, H, W, numangle, numrho))
         return emia_fail(EMIA_ERR_WORKSPACE, "emia_hough_lines_p: %s", "workspace too small");
     uint8_t* ws = (uint8_t*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    const size_t per = (size_t)numangle * numrho * 4 + (size_t)H * W * 4 + (((size_t)H * W + 15) & ~(size_t)15);
+    if (cudaMemset2DAsync(ws, per, 0, (size_t)numangle * numrho * 4, (size_t)B, (cudaStream_t)stream) != cudaSuccess)
+        return emia_fail(EMIA_ERR_LAUNCH, "emia_hough_lines_p: %s", "clearing the accumulators failed");
     if ((int64_t)H * W <= HOUGH_FAST_PIXELS) {
         size_t smem = ((size_t)(H * W + 31) / 32 + HOUGH_NZ_SMEM) * 4;
         static const char* pad_env = getenv("EMIA_HOUGH_SMEM_PAD_KB");     // experiment knob: fewer frames in flight per SM
         if (pad_env) { smem += (size_t)atoi(pad_env) * 1024; emia_need_dyn_smem((const void*)k_hough_lines_p<true>, smem); }
-        k_hough_lines_p<true><<<(unsigned)B, 32, smem, (cudaStream_t)stream>>>(edges, H, W, trig, numangle, numrho, threshold, min_line_length,
-                                                                               max_line_gap, max_lines, lines, n_lines, ws);
+        k_hough_lines_p<true><<<(unsigned)B, HOUGH_THREADS, smem, (cudaStream_t)stream>>>(edges, H, W, trig, numangle, numrho, threshold,
+                                                                                          min_line_length, max_line_gap, max_lines, lines, n_lines, ws);
     } else {
-        k_hough_lines_p<false><<<(unsigned)B, 32, 0, (cudaStream_t)stream>>>(edges, H, W, trig, numangle, numrho, threshold, min_line_length,
-                                                                             max_line_gap, max_lines, lines, n_lines, ws);
+        k_hough_lines_p<false><<<(unsigned)B, HOUGH_THREADS, 0, (cudaStream_t)stream>>>(edges, H, W, trig, numangle, numrho, threshold,
+                                                                                        min_line_length, max_line_gap, max_lines, lines, n_lines, ws);
     }
     return emia_check_launch("emia_hough_lines_p launch: %s");
 }
