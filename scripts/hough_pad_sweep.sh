@@ -1,5 +1,5 @@
 # experiment: frames in flight of the Hough kernel (shared-memory padding per CTA) vs step time
-for pad in 0 26 46 84; do
+for pad in ${PADS:-0 26 46 84}; do
   EMIA_HOUGH_SMEM_PAD_KB=$pad python bench.py --flows-only scalebar --no-cpu-baseline 2>/dev/null > gpurun_out/hp_$pad.json
   python - "$pad" <<'PY'
 import json, sys
