@@ -20,6 +20,7 @@ REC_FIELDS = 16
 
 FUSED_K4 = True
 MEASURE_ORDER = bool(int(__import__("os").environ.get("EMIA_MEASURE_ORDER", "1")))   # length-sorted work order of K5b/c (0: list order)
+MEASURE_ORDER_MIN_SLOTS = 65536
 LAUNCHES = {"count": 0}   # kernels launched through the ABI (bench.py reports it as gpu_launches)
 STAGE_TIMING = {"enabled": False, "events": []}   # (name, start, end) CUDA events when enabled (bench.py --breakdown)
 
@@ -600,8 +601,10 @@ def measure_list(iset, groups, um_pix=1.0, min_area=None, capacity=None, abort=N
     scratch = torch.empty(max(n_scr, 16), dtype=torch.uint8, device=dev)
     if L:
         order = None
-        if MEASURE_ORDER and L >= 1024:
-            # work order: slots sorted by vertex count (a warp of the morphometry kernel is as slow as its longest contour)
+        if MEASURE_ORDER and L >= MEASURE_ORDER_MIN_SLOTS:
+            # work order: slots sorted by vertex count (a warp of the morphometry kernel is as slow as its longest contour).  Measured:
+            # 1 M slots -0.80 ms, 128 K slots -0.04 ms, 8 K - 44 K slots (the batched flows) +0.06 ... +0.17 ms (three more graph
+            # nodes and a scattered hull pass for a stage that is only 0.1 ms there) - hence the threshold
             order = torch.empty(L, dtype=torch.int32, device=dev)
             bins = torch.empty(128, dtype=torch.int32, device=dev)
             with _stage("k5_order"):
