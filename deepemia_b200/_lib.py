@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libemia.so")
+LIB_PATH = os.environ.get("EMIA_LIB_PATH") or os.path.join(_HERE, "libemia.so")     # override: kernel-variant experiments
 
 c_void_p, c_int, c_int64, c_float, c_double, c_size_t = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float,
                                                          ctypes.c_double, ctypes.c_size_t)
