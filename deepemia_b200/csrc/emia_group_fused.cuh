@@ -74,12 +74,16 @@ __device__ __forceinline__ int emia_crop_inter_oct(const uint32_t* __restrict__ 
             // four independent word pairs per trip: the loads of a trip are issued back to back (the crops sit in L2 / HBM and
             // a CTA has few warps, so memory-level parallelism inside the pair is what hides the latency)
             const int oa = -ga.x * ga.w - ga.y, ob = -gb.x * gb.w - gb.y;
+            // tt / wc by a multiply-high: exact for tt < 2^16, 2 <= wc < 2^16 (two integer divisions per word were 15 % of the kernel's
+            // instructions); wc == 1 has no 32-bit reciprocal
+            const uint32_t inv_wc = wc > 1 ? (uint32_t)((0x100000000ull + (uint32_t)wc - 1u) / (uint32_t)wc) : 0u;
             for (int t = sl; t < nw; t += 32) {
                 uint32_t wa[4], wb[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int tt = t + 8 * u;
-                    const int r = r0 + tt / wc, c = c0 + tt % wc;
+                    const int rq = wc > 1 ? (int)__umulhi((uint32_t)tt, inv_wc) : tt;
+                    const int r = r0 + rq, c = c0 + (tt - rq * wc);
                     const bool in = tt < nw;
                     wa[u] = in ? pa[r * ga.w + c + oa] : 0u;
                     wb[u] = in ? pb[r * gb.w + c + ob] : 0u;
