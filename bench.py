@@ -441,11 +441,14 @@ def main():
     assert not pipe_c.aborted()
     del pipe_c
     # ---------------- end-to-end (host buffers) ----------------
-    # pinned host copies of two shards; batches sized so that the H2D copy of batch b+1 hides behind the kernels of batch b
-    # without over-decomposing a small (multi-GPU) shard (the latency-bound kernels of a batch cost ~0.5 ms whatever its size:
-    # measured on a 256-tile shard, 2 / 4 / 8 / 12 batches take 6.3 / 7.1 / 8.5 / 10.7 ms): ~128 tiles per batch, at most 12
+    # pinned host copies of two shards.  Tile batches: the H2D copy of batch b+1 runs beside the kernels of batch b, but every batch
+    # pays the latency-bound kernels' fixed ~0.4 ms again, so the count is small.  Measured with fp16 head outputs
+    # (scripts/e2e_batches_sweep.sh, ms per step): 2048 tiles: 5 / 6 / 8 / 12 / 16 batches -> 36.4 / 36.8 / 34.8 / 36.6 / 37.8;
+    # 1024 tiles: 4 / 6 / 8 -> 19.1 / 19.5 / 19.9; 512 tiles: 2 / 3 / 4 / 6 -> 11.5 / 10.9 / 10.9 / 11.3; 256 tiles: 2 / 3 / 4 ->
+    # 6.3 / 6.3 / 7.1.  Hence 256 tiles per batch for shards of 1024 tiles and more, 128 below, at least 2 and at most 8.
     E = min(2, V)
-    e2e_batches = args.e2e_batches or int(max(2, min(12, round(len(shards[0]["tiles"]) / 128.0))))
+    n_tiles = len(shards[0]["tiles"])
+    e2e_batches = args.e2e_batches or int(max(2, min(8, round(n_tiles / (256.0 if n_tiles >= 1024 else 128.0)))))
     pipe_e2e = engine.TilePipeline(H, W, um_pix=UM_PIX, rules=rules, dedup_iou=DEDUP_IOU, frames=arena, variant=args.variant,
                                    batches=e2e_batches, paste_ctas_per_sm=args.paste_ctas, device=dev)
     hosts = []

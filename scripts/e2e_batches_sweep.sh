@@ -1,6 +1,6 @@
-# e2e step time vs number of tile batches of the three-stream pipeline (one GPU)
+# e2e step time vs number of tile batches of the three-stream pipeline (one GPU; TILES = shard size)
 for nb in ${BATCHES:-8 12 16 24}; do
-  python bench.py --no-flows --no-cpu-baseline --e2e-batches $nb 2>/dev/null > gpurun_out/e2e_$nb.json
+  python bench.py --no-flows --no-cpu-baseline --tiles ${TILES:-2048} --e2e-batches $nb 2>/dev/null > gpurun_out/e2e_$nb.json
   python - "$nb" <<'PY'
 import json, sys
 d = json.load(open(f"gpurun_out/e2e_{sys.argv[1]}.json"))
