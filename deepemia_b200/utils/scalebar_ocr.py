@@ -205,7 +205,8 @@ def _draw_debug(image, rect, text_info, merged, longest, max_length):
 
 def detect_scale_bars(images, roi_config=None, intensity_threshold=200, proximity_threshold=50, dataset_name=None, draw_debug=False,
                       ocr=None, return_details=False):
-    """detect_scale_bar for a batch: images = list of equally shaped HxWx3 BGR uint8 arrays, or one [B,H,W,3] array / device tensor.
+    """detect_scale_bar for a batch: images = list of HxWx3 BGR uint8 arrays (one launch per stage and distinct frame size), or one
+    [B,H,W,3] array / device tensor.
     Returns [(psum, um_pix)] (with return_details: also a dict per image with edges, lines, merged segments)."""
     if roi_config is None:
         roi_config = get_scalebar_roi_for_dataset(dataset_name)
@@ -216,10 +217,22 @@ def detect_scale_bars(images, roi_config=None, intensity_threshold=200, proximit
         for im in images:
             if not isinstance(im, np.ndarray):
                 raise ScaleBarDetectionError("Input image is not a numpy array.")
-        if len({im.shape for im in images}) > 1:
-            raise ScaleBarDetectionError("detect_scale_bars needs equally shaped images (call it once per shape)")
         if not images:
             return []
+        shapes = {}
+        for k, im in enumerate(images):
+            shapes.setdefault(im.shape, []).append(k)
+        if len(shapes) > 1:
+            # frames of different sizes (a dataset mixing microscopes): one batch per size, results back in input order
+            if return_details:
+                raise ScaleBarDetectionError("return_details needs equally shaped images")
+            out = [None] * len(images)
+            for idx in shapes.values():
+                res = detect_scale_bars([images[k] for k in idx], roi_config, intensity_threshold, proximity_threshold, dataset_name,
+                                        draw_debug, ocr)
+                for k, r in zip(idx, res):
+                    out[k] = r
+            return out
         B, (h, w) = len(images), images[0].shape[:2]
     elif isinstance(images, (np.ndarray, torch.Tensor)):
         B, h, w = (int(v) for v in images.shape[:3])
