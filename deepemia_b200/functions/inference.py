@@ -679,9 +679,17 @@ def run_inference(dataset_name, output_dir, visualize=True, threshold=0.65, draw
             cv2.imwrite(os.path.join(output_dir, f"{name}_scalebar_debug.png"), work)
         return r
     img_ids, encoded, meas_rows = [], [], []
-    for name, image in images:
+    # the scale bars of ALL images in one launch per stage (and frame size) when the package's own detector is in use; a failure
+    # of the batch falls back to the reference's per-image call with its per-image try / except (inference.py:750-773)
+    batch_bars = None
+    if own_detector and not draw_scalebar and len(images) > 1:
         try:
-            psum, um_pix = scale_bar(image, name)
+            batch_bars = _sb.detect_scale_bars([im for _, im in images], roi_config=roi_config, dataset_name=dataset_name)
+        except Exception:
+            batch_bars = None
+    for k, (name, image) in enumerate(images):
+        try:
+            psum, um_pix = batch_bars[k] if batch_bars is not None else scale_bar(image, name)
         except Exception:
             psum, um_pix = "0", 1.0                                     # inference.py:767-773
         d = _infer_image_dev(predictors, image, num_classes, small_classes, dataset_name=dataset_name, **kw)
