@@ -398,13 +398,19 @@ extern "C" int emia_hough_lines_p(const uint8_t* edges, int32_t B, int32_t H, in
 __global__ void __launch_bounds__(32) k_line_mean(const uint8_t* __restrict__ gray_all, int H, int W, const int32_t* __restrict__ lines_all,
                                                   const int32_t* __restrict__ n_lines, int max_lines, int64_t* __restrict__ out) {
     extern __shared__ uint32_t plane[];
-    const int b = blockIdx.y, l = blockIdx.x, lane = threadIdx.x;
+    const int b = blockIdx.y, lane = threadIdx.x;
     int nl = n_lines[b];
-    if (l >= (nl < max_lines ? nl : max_lines)) return;
+    nl = nl < max_lines ? nl : max_lines;
     const int words = (H * W + 31) / 32;
-    for (int t = lane; t < words; t += 32) plane[t] = 0;
-    __syncwarp();
+    // a frame has ~10 lines and room for hundreds: the grid covers 32 line slots per frame and loops over the rest
+    for (int l = blockIdx.x; l < nl; l += gridDim.x) {
     const int32_t* ln = lines_all + ((size_t)b * max_lines + l) * 4;
+    // only the rows the thick line can touch (its half width and its end caps reach one pixel: two rows of slack) are cleared / read
+    const int ry0 = max(0, min(ln[1], ln[3]) - 2), ry1 = min(H - 1, max(ln[1], ln[3]) + 2);
+    const int wlo = max(0, (ry0 * W) >> 5), whi = min(words, ((ry1 + 1) * W + 31) >> 5);
+    __syncwarp();
+    for (int t = wlo + lane; t < whi; t += 32) plane[t] = 0;
+    __syncwarp();
     if (lane == 0) {
         uint32_t* pl = plane;
         emia_cv_thick_line2(W, H, ln[0], ln[1], ln[2], ln[3], [pl, W](int x, int y) { int t = y * W + x; pl[t >> 5] |= 1u << (t & 31); });
@@ -412,7 +418,7 @@ __global__ void __launch_bounds__(32) k_line_mean(const uint8_t* __restrict__ gr
     __syncwarp();
     const uint8_t* gray = gray_all + (size_t)b * H * W;
     long long sum = 0, cnt = 0;
-    for (int t = lane; t < words; t += 32) {
+    for (int t = wlo + lane; t < whi; t += 32) {
         uint32_t v = plane[t];
         cnt += __popc(v);
         while (v) {
@@ -429,6 +435,7 @@ __global__ void __launch_bounds__(32) k_line_mean(const uint8_t* __restrict__ gr
         out[((size_t)b * max_lines + l) * 2] = sum;
         out[((size_t)b * max_lines + l) * 2 + 1] = cnt;
     }
+    }
 }
 
 extern "C" int emia_line_mean(const uint8_t* gray, int32_t B, int32_t H, int32_t W, const int32_t* lines, const int32_t* n_lines,
@@ -440,6 +447,6 @@ extern "C" int emia_line_mean(const uint8_t* gray, int32_t B, int32_t H, int32_t
     size_t smem = (((size_t)H * W + 31) / 32) * 4;
     if (smem > 200 * 1024) return emia_fail(EMIA_ERR_BAD_ARG, "emia_line_mean: %s", "region above 1.6 Mpixel (the bit plane lives in shared memory)");
     emia_need_dyn_smem((const void*)k_line_mean, smem);
-    k_line_mean<<<dim3((unsigned)max_lines, (unsigned)B), 32, smem, (cudaStream_t)stream>>>(gray, H, W, lines, n_lines, max_lines, sum_count);
+    k_line_mean<<<dim3((unsigned)(max_lines < 32 ? max_lines : 32), (unsigned)B), 32, smem, (cudaStream_t)stream>>>(gray, H, W, lines, n_lines, max_lines, sum_count);
     return emia_check_launch("emia_line_mean launch: %s");
 }
